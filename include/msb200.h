@@ -1,0 +1,134 @@
+/*
+ * msb200.h -- C ABI of libmsb200.so, the B200 (sm_100a) implementation of MotifScan's
+ * motif-scanning hot path.
+ *
+ * The reference exposes this path as a CPython extension module, `motifscan.motif.cscore`
+ * (reference motifscan/motif/cscore.c:479-494), with two methods:
+ *     c_scan_motif(pwms, cutoffs, seqs, strand, n_threads)   cscore.c:399-476
+ *     c_score(pwms, seqs, strand, n_threads)                 cscore.c:231-302
+ * called from motifscan/scanner.py:125 and motifscan/cli/motif.py:134.  This header is what a
+ * binding for that module binds instead (see INTEGRATION.md for the ctypes stub): plain
+ * pointers and sizes, no Python and no torch types.
+ *
+ * Conventions
+ *   - every function returns MSB_OK (0) or a negative MSB_E* code; msb_last_error() returns a
+ *     thread-local message for the last failure on the calling thread.  Nothing calls exit()
+ *     (the reference does on hit-allocation failure, cscore.c:360-363).
+ *   - the library keeps no global mutable state: all state hangs off an msb_ctx (one device,
+ *     one stream).  Different contexts may be used from different host threads concurrently
+ *     (the reference's file-scope globals, cscore.c:26-34, make it single-caller).
+ *   - PWMs are passed flat: motif m is the row-major 4 x lens[m] block at mats + mat_off[m]
+ *     (rows A, C, G, T -- the reference's `double *matrix[4]`, cscore.c:6-11).
+ *   - sequences are passed flat: sequence i is the ASCII bytes seq_bytes[seq_off[i] ..
+ *     seq_off[i+1]).  Encoding follows cscore.c:81-114: A/a C/c G/g T/t -> 0..3, any other
+ *     byte is "N" (contributes 0 to a score, cscore.c:346).
+ *   - strand: 1 forward, 2 reverse, 3 both (cscore.c:176-177).
+ *   - n_threads of the reference API has no equivalent here and is dropped.
+ */
+#ifndef MSB200_H
+#define MSB200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define MSB_OK 0
+#define MSB_EINVAL -1   /* bad argument (the reference performs no validation, cscore.c:117-120) */
+#define MSB_ENOMEM -2   /* host or device allocation failed (reference: MemoryError / exit(1)) */
+#define MSB_ECUDA -3    /* CUDA runtime error, no usable device, or kernel image mismatch */
+#define MSB_ESHORT -4   /* c_score: a sequence is shorter than the longest motif (reference: UB) */
+
+typedef struct msb_ctx msb_ctx;       /* one device + one stream + reusable scratch */
+typedef struct msb_motifs msb_motifs; /* device-resident motif set: fp64 PWMs, cutoffs, tables */
+typedef struct msb_seqs msb_seqs;     /* device-resident sequence set: 2-bit codes + N mask */
+typedef struct msb_result msb_result; /* host-resident sites of one scan, reference order */
+
+const char *msb_last_error(void);
+int msb_version(void);
+int msb_device_count(int *count);
+
+/* ---- context ------------------------------------------------------------------------------ */
+/* `stream` is an optional cudaStream_t (as void*) to launch on, e.g. torch's current stream;
+ * NULL makes the context create and own a non-blocking stream. */
+int msb_ctx_create(int device, void *stream, msb_ctx **ctx);
+int msb_ctx_destroy(msb_ctx *ctx);
+int msb_ctx_sync(msb_ctx *ctx);
+/* Per-phase device times (ms, CUDA events on the context's stream) of the last msb_scan /
+ * msb_score / msb_seqs_from_ascii on this context.  Index by MSB_T_*. */
+enum { MSB_T_H2D = 0, MSB_T_ENCODE, MSB_T_PREFILTER, MSB_T_EXACT, MSB_T_ORDER, MSB_T_D2H,
+       MSB_T_SCORE, MSB_T_SELECT, MSB_T_COUNT };
+int msb_ctx_timings(const msb_ctx *ctx, double *ms, int n);
+/* Counters of the last msb_scan: index by MSB_C_*. */
+enum { MSB_C_CANDIDATES = 0, MSB_C_DIRTY, MSB_C_HITS, MSB_C_LAUNCHES, MSB_C_RETRIES,
+       MSB_C_PREFILTER_LAUNCHES, MSB_C_COUNT };
+int msb_ctx_counters(const msb_ctx *ctx, int64_t *v, int n);
+
+/* Tuning knob for experiments: "prefilter_w" = windows per thread of the prefilter (4 or 8). */
+int msb_set_option(const char *name, int value);
+
+/* Pinned host memory for callers that want full-speed H2D (cudaHostAlloc / cudaFreeHost). */
+int msb_pinned_alloc(int64_t bytes, void **ptr);
+int msb_pinned_free(void *ptr);
+
+/* ---- motif set (replaces convert_pwm + get_max_raw_score, cscore.c:36-79) ------------------- */
+/* cutoffs may be NULL: every cutoff is then 1, as in cscore.c:71-75. */
+int msb_motifs_create(msb_ctx *ctx, int32_t n_motifs, const int32_t *lens, const double *mats,
+                      const int64_t *mat_off, const double *cutoffs, msb_motifs **out);
+int msb_motifs_set_cutoffs(msb_motifs *motifs, const double *cutoffs);
+int msb_motifs_count(const msb_motifs *motifs, int32_t *n_motifs);
+/* max_raw_score per motif exactly as cscore.c:36-48 computes it. */
+int msb_motifs_max_raw(const msb_motifs *motifs, double *out);
+int msb_motifs_destroy(msb_motifs *motifs);
+
+/* ---- sequence set (replaces convert_seq, cscore.c:81-114) ----------------------------------- */
+/* Copies the bytes to the device and encodes + packs them there. */
+int msb_seqs_from_ascii(msb_ctx *ctx, int64_t n_seqs, const char *seq_bytes,
+                        const int64_t *seq_off, msb_seqs **out);
+int msb_seqs_count(const msb_seqs *seqs, int64_t *n_seqs, int64_t *total_bp);
+/* Parity accessor: decode the packed device representation back to the reference's int8 codes
+ * (0..3, -1) for all sequences, concatenated like the input. */
+int msb_seqs_codes(msb_ctx *ctx, const msb_seqs *seqs, int8_t *codes);
+int msb_seqs_destroy(msb_seqs *seqs);
+
+/* ---- scan (replaces scan_motif_thread + scan_motif, cscore.c:317-476) ----------------------- */
+/* Sites come back motif-major, then (sequence, start) ascending, forward before reverse at the
+ * same start -- the order of the reference's per-motif lists.  Scores are the reference's
+ * doubles bit for bit; the hit predicate is score - cutoff >= -1e-10. */
+int msb_scan(msb_ctx *ctx, const msb_motifs *motifs, const msb_seqs *seqs, int strand,
+             msb_result **out);
+/* Device-only variant for measurement: same kernels, results left on the device, no D2H. */
+int msb_scan_device(msb_ctx *ctx, const msb_motifs *motifs, const msb_seqs *seqs, int strand,
+                    int64_t *n_sites);
+int msb_result_total(const msb_result *res, int64_t *n_sites);
+int msb_result_counts(const msb_result *res, int64_t *counts /* n_motifs */);
+/* Borrowed pointers into the result (valid until msb_result_destroy): n_sites entries each. */
+int msb_result_arrays(const msb_result *res, const int32_t **seq_idx, const int32_t **start,
+                      const double **score, const int8_t **strand /* 1 or 2 */);
+int msb_result_destroy(msb_result *res);
+
+/* ---- score (replaces motif_score_thread + motif_score, cscore.c:174-302) -------------------- */
+/* out is n_motifs x n_seqs row-major: the offset-0 window score of every sequence. */
+int msb_score(msb_ctx *ctx, const msb_motifs *motifs, const msb_seqs *seqs, int strand,
+              double *out);
+/* Fused `motif --build` step (cli/motif.py:133-137 + motif/__init__.py:378-401): score as
+ * above with strand 3, then for every motif return the n_ranks order statistics
+ * sorted_descending(scores)[ranks[k]] without moving the score matrix to the host.
+ * out is n_motifs x n_ranks row-major. */
+int msb_score_select(msb_ctx *ctx, const msb_motifs *motifs, const msb_seqs *seqs, int strand,
+                     int32_t n_ranks, const int64_t *ranks, double *out);
+
+/* ---- one-shot mirrors of the two reference methods ----------------------------------------- */
+int msb_c_scan_motif(int device, int32_t n_motifs, const int32_t *lens, const double *mats,
+                     const int64_t *mat_off, const double *cutoffs, int64_t n_seqs,
+                     const char *seq_bytes, const int64_t *seq_off, int strand,
+                     msb_result **out);
+int msb_c_score(int device, int32_t n_motifs, const int32_t *lens, const double *mats,
+                const int64_t *mat_off, int64_t n_seqs, const char *seq_bytes,
+                const int64_t *seq_off, int strand, double *out);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* MSB200_H */

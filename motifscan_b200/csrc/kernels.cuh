@@ -1,0 +1,370 @@
+// kernels.cuh -- device code of libmsb200 (sm_100a).
+//
+//   encode_pack_kernel      ASCII -> 2-bit codes + N mask            (cscore.c:81-114)
+//   prefilter_kernel        every window x every motif x both strands, 16-bit fixed point,
+//                           conservative: emits a superset of the hits  (cscore.c:336-355)
+//   exact_candidates_kernel fp64 re-score of candidates in the reference's accumulation
+//                           order + the reference's hit predicate       (cscore.c:344-389)
+//   exact_dirty_kernel      the same for windows that touch a non-ACGT base
+//   exact_slow_kernel       the same for motifs the table path cannot take (L > 32, non-finite)
+//   decode_sites_kernel     sorted keys -> (seq_idx, start, strand) + per-motif counts
+//   score0_kernel           offset-0 window score of every sequence     (cscore.c:191-223)
+#pragma once
+#include "common.cuh"
+
+namespace msb {
+
+// Largest s with poff[s] <= p.  Empty sequences share a start with their successor and are
+// skipped because the search returns the LAST such s.
+__device__ __forceinline__ int64_t find_seq(const int64_t *__restrict__ poff, int64_t n_seqs,
+                                            int64_t p) {
+    int64_t lo = 0, hi = n_seqs;  // invariant: poff[lo] <= p, answer in [lo, hi)
+    while (hi - lo > 1) {
+        int64_t mid = (lo + hi) >> 1;
+        if (__ldg(poff + mid) <= p) lo = mid; else hi = mid;
+    }
+    return lo;
+}
+
+// The reference's int8 code of packed position q: 0..3, or -1 for anything but ACGT/acgt.
+__device__ __forceinline__ int base_code(const SeqView &S, int64_t q) {
+    uint32_t m = __ldg(S.nmask + (q >> 5));
+    if ((m >> (q & 31)) & 1u) return -1;
+    uint32_t w = __ldg(S.codes + (q >> 4));
+    return (int) ((w >> ((q & 15) * 2)) & 3u);
+}
+
+// ---------------------------------------------------------------------------------------------
+// encode + pack.  One thread per 32-base block of the packed space.
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+encode_pack_kernel(const uint8_t *__restrict__ ascii, const int64_t *__restrict__ seq_off,
+                   const int64_t *__restrict__ poff, const int32_t *__restrict__ len,
+                   int64_t n_seqs, int64_t n_blocks, uint32_t *__restrict__ codes,
+                   uint32_t *__restrict__ nmask) {
+    int64_t b = (int64_t) blockIdx.x * blockDim.x + threadIdx.x;
+    if (b >= n_blocks) return;
+    int64_t p = b * kPadBases;
+    int64_t s = find_seq(poff, n_seqs, p);
+    int64_t j = p - __ldg(poff + s);
+    int n = (int) min((int64_t) kPadBases, (int64_t) __ldg(len + s) - j);
+    const uint8_t *src = ascii + __ldg(seq_off + s) + j;
+    uint32_t lo = 0, hi = 0, mask = 0;
+#pragma unroll
+    for (int k = 0; k < kPadBases; k++) {
+        if (k < n) {
+            uint32_t c = (uint32_t) __ldg(src + k) | 0x20u;  // fold case (cscore.c:91-108)
+            uint32_t code = 0, isn = 0;
+            if (c == 0x61u) code = 0;        // A a
+            else if (c == 0x63u) code = 1;   // C c
+            else if (c == 0x67u) code = 2;   // G g
+            else if (c == 0x74u) code = 3;   // T t
+            else isn = 1;                    // default: -1 (cscore.c:109-110)
+            if (k < 16) lo |= code << (2 * k); else hi |= code << (2 * (k - 16));
+            mask |= isn << k;
+        }
+    }
+    codes[2 * b] = lo;
+    codes[2 * b + 1] = hi;
+    nmask[b] = mask;
+}
+
+// Parity accessor: packed -> int8 codes laid out like the ASCII input.
+__global__ void __launch_bounds__(256)
+unpack_codes_kernel(SeqView S, const int64_t *__restrict__ seq_off, int8_t *__restrict__ out) {
+    int64_t p = (int64_t) blockIdx.x * blockDim.x + threadIdx.x;
+    if (p >= S.total_packed) return;
+    int64_t s = find_seq(S.poff, S.n_seqs, p);
+    int64_t j = p - S.poff[s];
+    if (j < S.len[s]) out[seq_off[s] + j] = (int8_t) base_code(S, p);
+}
+
+// ---------------------------------------------------------------------------------------------
+// prefilter.
+//
+// Work unit: a warp chunk of 32*W consecutive packed positions; lane l owns the W window
+// starts p0 .. p0+W-1 with p0 = chunk*32*W + l*W.  A thread keeps the pre-scaled 2-mer index of
+// every offset it can need (W + 2*(kMaxGroups-1) registers), so the per-motif inner loop is
+// one LDS [idx + motif_base + imm] plus a third of an IADD3 per 2 PWM columns of BOTH strands:
+// a table entry packs (forward sum << 16) + reverse sum of its two columns in 16-bit fixed
+// point, pre-biased so that bit 31 / bit 15 of the final sum is the "forward / reverse score
+// may reach the cutoff" flag.  Entries of one group are 16 consecutive words = 16 banks, lanes
+// that read the same word are broadcast: conflict-free by construction.
+// ---------------------------------------------------------------------------------------------
+template <int W> struct PF {
+    static constexpr int kIdx = W + 2 * (kMaxGroups - 1);  // 2-mer offsets a thread may use
+    static constexpr int kThreads = 512;
+    static constexpr int kChunk = 32 * W;
+};
+
+template <int G, int W>
+__device__ __forceinline__ uint32_t score_motif(const unsigned char *__restrict__ tab,
+                                                const uint32_t (&idx)[PF<W>::kIdx],
+                                                uint32_t (&acc)[W]) {
+    uint32_t any = 0;
+#pragma unroll
+    for (int w = 0; w < W; w++) {
+        uint32_t a = 0;
+#pragma unroll
+        for (int g = 0; g < G; g++)
+            a += *reinterpret_cast<const uint32_t *>(tab + g * kGroupBytes + idx[w + 2 * g]);
+        acc[w] = a;
+        any |= a;
+    }
+    return any & 0x80008000u;
+}
+
+template <int W>
+__device__ __forceinline__ void emit_candidates(const PrefilterParams &P,
+                                                const uint32_t (&acc)[W], uint32_t live,
+                                                uint32_t sorted_idx, int64_t p0, int32_t j0,
+                                                int32_t slen) {
+    int32_t L = __ldg(P.mlen + __ldg(P.order + sorted_idx));
+#pragma unroll
+    for (int w = 0; w < W; w++) {
+        uint32_t f = acc[w] & 0x80008000u;
+        if (f == 0 || !((live >> w) & 1u)) continue;
+        if (j0 + w + L > slen) continue;  // window runs past the sequence (cscore.c:340)
+        if (f & 0x80000000u) {
+            unsigned long long slot = atomicAdd(P.counters + 0, 1ull);
+            if ((int64_t) slot < P.cand_cap) P.cand[slot] = make_key(sorted_idx, p0 + w, 0);
+        }
+        if (f & 0x00008000u) {
+            unsigned long long slot = atomicAdd(P.counters + 0, 1ull);
+            if ((int64_t) slot < P.cand_cap) P.cand[slot] = make_key(sorted_idx, p0 + w, 1);
+        }
+    }
+}
+
+template <int G, int W>
+__device__ __forceinline__ void run_group(const PrefilterParams &P,
+                                          const unsigned char *__restrict__ &tab,
+                                          uint32_t &sorted_idx,
+                                          const uint32_t (&idx)[PF<W>::kIdx], uint32_t live,
+                                          int64_t p0, int32_t j0, int32_t slen) {
+    const int cnt = P.batch.g_count[G];
+    for (int i = 0; i < cnt; i++) {
+        uint32_t acc[W];
+        if (score_motif<G, W>(tab, idx, acc))
+            emit_candidates<W>(P, acc, live, sorted_idx, p0, j0, slen);
+        tab += G * kGroupBytes;
+        sorted_idx++;
+    }
+}
+
+template <int G, int W> struct GroupLoop {
+    static __device__ __forceinline__ void run(const PrefilterParams &P,
+                                               const unsigned char *__restrict__ &tab,
+                                               uint32_t &sorted_idx,
+                                               const uint32_t (&idx)[PF<W>::kIdx],
+                                               uint32_t live, int64_t p0, int32_t j0,
+                                               int32_t slen) {
+        GroupLoop<G - 1, W>::run(P, tab, sorted_idx, idx, live, p0, j0, slen);
+        run_group<G, W>(P, tab, sorted_idx, idx, live, p0, j0, slen);
+    }
+};
+template <int W> struct GroupLoop<0, W> {
+    static __device__ __forceinline__ void run(const PrefilterParams &, const unsigned char *__restrict__ &,
+                                               uint32_t &, const uint32_t (&)[PF<W>::kIdx],
+                                               uint32_t, int64_t, int32_t, int32_t) {}
+};
+
+template <int W>
+__global__ void __launch_bounds__(PF<W>::kThreads, 1)
+prefilter_kernel(const __grid_constant__ PrefilterParams P) {
+    extern __shared__ __align__(16) unsigned char s_tab[];
+    {
+        const uint4 *src = reinterpret_cast<const uint4 *>(P.tab + P.batch.tab_word_off);
+        uint4 *dst = reinterpret_cast<uint4 *>(s_tab);
+        const uint32_t n4 = P.batch.tab_words >> 2;
+        for (uint32_t i = threadIdx.x; i < n4; i += blockDim.x) dst[i] = __ldg(src + i);
+    }
+    __syncthreads();
+
+    const SeqView &S = P.seq;
+    const int lane = threadIdx.x & 31;
+    const int64_t warps_total = (int64_t) gridDim.x * (blockDim.x >> 5);
+    const int64_t warp_global = (int64_t) blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    const int64_t n_chunks = (S.total_packed + PF<W>::kChunk - 1) / PF<W>::kChunk;
+    const uint32_t horizon = P.lmax_all >= 32 ? 0xffffffffu : ((1u << P.lmax_all) - 1u);
+
+    for (int64_t chunk = warp_global; chunk < n_chunks; chunk += warps_total) {
+        const int64_t p0 = chunk * PF<W>::kChunk + (int64_t) lane * W;
+        if (p0 >= S.total_packed) continue;
+        const int64_t s = find_seq(S.poff, S.n_seqs, p0);
+        const int32_t j0 = (int32_t) (p0 - __ldg(S.poff + s));
+        const int32_t slen = __ldg(S.len + s);
+        if (j0 >= slen) continue;  // padding behind the sequence's last base
+
+        // N mask of [p0, p0 + W + 31): window w is "dirty" if any base in its horizon is N.
+        const uint32_t *mp = S.nmask + (p0 >> 5);
+        const uint64_t m64 = (((uint64_t) __ldg(mp + 1) << 32) | __ldg(mp)) >> (p0 & 31);
+        uint32_t live = 0;  // windows this thread scores with the table path
+#pragma unroll
+        for (int w = 0; w < W; w++) {
+            const uint32_t bits = (uint32_t) (m64 >> w) & horizon;
+            if (j0 + w < slen) {
+                if (bits == 0) {
+                    live |= 1u << w;
+                } else if (P.emit_dirty && !(bits == horizon && !P.any_zero_hit)) {
+                    // Touches an N: scored exactly by exact_dirty_kernel.  A window whose whole
+                    // horizon is N scores 0 for every motif and is dropped when no motif's
+                    // cutoff admits a zero score.
+                    unsigned long long slot = atomicAdd(P.counters + 1, 1ull);
+                    if ((int64_t) slot < P.dirty_cap) P.dirty[slot] = p0 + w;
+                }
+            }
+        }
+        if (live == 0) continue;
+
+        // 2-bit codes of [p0, p0 + 48 - (p0 & 15)) aligned to bit 0.
+        const uint32_t *cp = S.codes + (p0 >> 4);
+        const uint32_t sh = (uint32_t) (p0 & 15) * 2;
+        const uint32_t r0 = __ldg(cp), r1 = __ldg(cp + 1), r2 = __ldg(cp + 2);
+        uint32_t cw[4];
+        cw[0] = __funnelshift_r(r0, r1, sh);
+        cw[1] = __funnelshift_r(r1, r2, sh);
+        cw[2] = r2 >> sh;
+        cw[3] = 0;
+        uint32_t idx[PF<W>::kIdx];
+#pragma unroll
+        for (int k = 0; k < PF<W>::kIdx; k++) {
+            const uint32_t v = __funnelshift_r(cw[(2 * k) >> 5], cw[((2 * k) >> 5) + 1], (2 * k) & 31);
+            idx[k] = (v & 0xFu) << 2;
+        }
+
+        const unsigned char *tab = s_tab;
+        uint32_t sorted_idx = P.batch.first_sorted;
+        GroupLoop<kMaxGroups, W>::run(P, tab, sorted_idx, idx, live, p0, j0, slen);
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// exact stage: the reference's arithmetic, verbatim (cscore.c:341-389).
+// ---------------------------------------------------------------------------------------------
+struct ExactParams {
+    SeqView seq;
+    MotifView mot;
+    int strand;
+    uint64_t *hit_key;    // motif id in the motif field
+    double *hit_score;
+    int64_t hit_cap;
+    unsigned long long *counters;  // [2] hits
+};
+
+// Raw score of one strand of window [p, p+L): double accumulation in ascending column order,
+// non-ACGT bases skipped.  No multiply on the path, so the sum is the reference's bit for bit.
+__device__ __forceinline__ double exact_raw(const SeqView &S, const double *__restrict__ pw, int L,
+                                            int64_t p, int rev) {
+    double acc = 0.0;
+    for (int c = 0; c < L; c++) {
+        const int row = base_code(S, p + c);
+        if (row >= 0) {
+            const double v = rev ? __ldg(pw + 4 * (L - 1 - c) + (3 - row)) : __ldg(pw + 4 * c + row);
+            acc = __dadd_rn(acc, v);
+        }
+    }
+    return acc;
+}
+
+__device__ __forceinline__ void test_and_emit(const ExactParams &E, uint32_t m, int64_t p, int rev,
+                                              double raw) {
+    const double score = __ddiv_rn(raw, __ldg(E.mot.max_raw + m));       // cscore.c:357,374
+    if (__dsub_rn(score, __ldg(E.mot.cutoff + m)) >= -1e-10) {           // cscore.c:358,375
+        unsigned long long slot = atomicAdd(E.counters + 2, 1ull);
+        if ((int64_t) slot < E.hit_cap) {
+            E.hit_key[slot] = make_key(m, p, (uint32_t) rev);
+            E.hit_score[slot] = score;
+        }
+    }
+}
+
+__global__ void __launch_bounds__(256)
+exact_candidates_kernel(ExactParams E, const uint64_t *__restrict__ cand, int64_t n_cand,
+                        const int32_t *__restrict__ order) {
+    int64_t i = (int64_t) blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n_cand) return;
+    const uint64_t k = cand[i];
+    const uint32_t m = (uint32_t) __ldg(order + key_motif(k));
+    const int64_t p = key_pos(k);
+    const int rev = (int) key_rev(k);
+    const int L = __ldg(E.mot.len + m);
+    const double *pw = E.mot.pwm + 4 * (int64_t) __ldg(E.mot.col_off + m);
+    test_and_emit(E, m, p, rev, exact_raw(E.seq, pw, L, p, rev));
+}
+
+// One thread per (listed position, motif); consecutive threads take consecutive motifs of the
+// same position.  `motif_ids` == nullptr means all motifs.
+__global__ void __launch_bounds__(256)
+exact_positions_kernel(ExactParams E, const int64_t *__restrict__ pos, int64_t n_pos,
+                       const int32_t *__restrict__ motif_ids, int32_t n_ids) {
+    const int64_t t = (int64_t) blockIdx.x * blockDim.x + threadIdx.x;
+    const int64_t d = t / n_ids;
+    if (d >= n_pos) return;
+    const uint32_t m = motif_ids ? (uint32_t) __ldg(motif_ids + (t - d * n_ids)) : (uint32_t) (t - d * n_ids);
+    const int64_t p = pos ? __ldg(pos + d) : d;
+    if (p >= E.seq.total_packed) return;
+    const int64_t s = find_seq(E.seq.poff, E.seq.n_seqs, p);
+    const int64_t j = p - __ldg(E.seq.poff + s);
+    const int L = __ldg(E.mot.len + m);
+    const int64_t slen = __ldg(E.seq.len + s);
+    if (j >= slen || j + L > slen) return;   // cscore.c:337,340
+    const double *pw = E.mot.pwm + 4 * (int64_t) __ldg(E.mot.col_off + m);
+    if (E.strand & 1) test_and_emit(E, m, p, 0, exact_raw(E.seq, pw, L, p, 0));
+    if (E.strand & 2) test_and_emit(E, m, p, 1, exact_raw(E.seq, pw, L, p, 1));
+}
+
+__global__ void __launch_bounds__(256)
+decode_sites_kernel(SeqView S, const uint64_t *__restrict__ key, int64_t n,
+                    int32_t *__restrict__ seq_idx, int32_t *__restrict__ start,
+                    int8_t *__restrict__ strand, unsigned long long *__restrict__ counts) {
+    int64_t i = (int64_t) blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const uint64_t k = key[i];
+    const int64_t p = key_pos(k);
+    const int64_t s = find_seq(S.poff, S.n_seqs, p);
+    seq_idx[i] = (int32_t) s;
+    start[i] = (int32_t) (p - __ldg(S.poff + s));
+    strand[i] = (int8_t) (key_rev(k) + 1);  // 1 forward, 2 reverse (cscore.c:359,376)
+    atomicAdd(counts + key_motif(k), 1ull);
+}
+
+// ---------------------------------------------------------------------------------------------
+// c_score: offset-0 window of every sequence (cscore.c:191-223).  One thread per sequence,
+// looping over a slice of motifs; out[m * n_seqs + i].
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+score0_kernel(SeqView S, MotifView M, int strand, int32_t m_begin, int32_t m_end, int64_t out_stride,
+              double *__restrict__ out) {
+    const int64_t i = (int64_t) blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= S.n_seqs) return;
+    const int64_t p = __ldg(S.poff + i);
+    for (int32_t m = m_begin + (int32_t) blockIdx.y; m < m_end; m += (int32_t) gridDim.y) {
+        const int L = __ldg(M.len + m);
+        const double *pw = M.pwm + 4 * (int64_t) __ldg(M.col_off + m);
+        double f = 0.0, r = 0.0;
+        for (int c = 0; c < L; c++) {
+            const int row = base_code(S, p + c);
+            if (row >= 0) {
+                if (strand & 1) f = __dadd_rn(f, __ldg(pw + 4 * c + row));
+                if (strand & 2) r = __dadd_rn(r, __ldg(pw + 4 * (L - 1 - c) + (3 - row)));
+            }
+        }
+        double sc = 0.0;
+        if (strand == 1) sc = f;
+        else if (strand == 2) sc = r;
+        else if (strand == 3) sc = (f > r) ? f : r;  // cscore.c:215-221
+        out[(int64_t) (m - m_begin) * out_stride + i] = __ddiv_rn(sc, __ldg(M.max_raw + m));
+    }
+}
+
+__global__ void __launch_bounds__(256)
+gather_ranks_kernel(const double *__restrict__ sorted, int64_t n_seqs, int32_t n_motifs_chunk,
+                    const int64_t *__restrict__ ranks, int32_t n_ranks, double *__restrict__ out) {
+    const int t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= n_motifs_chunk * n_ranks) return;
+    const int m = t / n_ranks, k = t - m * n_ranks;
+    out[t] = sorted[(int64_t) m * n_seqs + ranks[k]];
+}
+
+}  // namespace msb

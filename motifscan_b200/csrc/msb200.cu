@@ -1,0 +1,1059 @@
+// msb200.cu -- host side of libmsb200.so: the C ABI declared in include/msb200.h.
+//
+// Replaces the reference's native extension motifscan/motif/cscore.c for the scan path:
+//   convert_args/convert_pwm/convert_seq (cscore.c:50-151)  -> msb_motifs_create, msb_seqs_from_ascii
+//   scan_motif_thread/scan_motif         (cscore.c:317-476) -> msb_scan
+//   motif_score_thread/motif_score       (cscore.c:174-302) -> msb_score, msb_score_select
+// There is no CPU implementation in this library: without a CUDA device every entry point that
+// computes returns MSB_ECUDA.
+#include <cub/cub.cuh>
+
+#include <algorithm>
+#include <cmath>
+#include <cstring>
+#include <limits>
+#include <mutex>
+#include <new>
+#include <numeric>
+
+#include "kernels.cuh"
+
+namespace msb {
+
+static thread_local std::string g_err;
+void set_error(const std::string &msg) { g_err = msg; }
+int cuda_fail(cudaError_t e, const char *what, const char *file, int line) {
+    g_err = std::string("CUDA error: ") + cudaGetErrorString(e) + " in " + what + " (" + file + ":" +
+            std::to_string(line) + ")";
+    cudaGetLastError();  // clear the sticky-less error state
+    return e == cudaErrorMemoryAllocation ? MSB_ENOMEM : MSB_ECUDA;
+}
+
+int DevBuf::ensure(size_t bytes) {
+    if (bytes <= cap) return MSB_OK;
+    size_t want = std::max(bytes, cap + cap / 2);
+    void *np = nullptr;
+    if (p) { cudaFree(p); p = nullptr; cap = 0; }
+    cudaError_t e = cudaMalloc(&np, want);
+    if (e != cudaSuccess && want > bytes) e = cudaMalloc(&np, want = bytes);
+    if (e != cudaSuccess) return cuda_fail(e, "cudaMalloc", __FILE__, __LINE__);
+    p = np;
+    cap = want;
+    return MSB_OK;
+}
+void DevBuf::release() {
+    if (p) cudaFree(p);
+    p = nullptr;
+    cap = 0;
+}
+
+struct PinnedBlock {
+    void *p = nullptr;
+    size_t cap = 0;
+};
+
+}  // namespace msb
+
+using namespace msb;
+
+// ------------------------------------------------------------------------------------------------
+struct msb_ctx {
+    int device = 0;
+    cudaStream_t stream = nullptr;
+    bool own_stream = false;
+    int sm_count = 0;
+    size_t smem_optin = 0;
+    cudaEvent_t ev[8] = {};
+    double t[MSB_T_COUNT] = {};
+    int64_t c[MSB_C_COUNT] = {};
+    // scratch (grow-only, reused across calls)
+    DevBuf ascii, seq_off, cand, dirty, hit_key, hit_score, key_alt, score_alt, sort_tmp, counters;
+    DevBuf out_seq, out_start, out_strand, out_counts, scores, scores_sorted, seg_off, ranks, sel;
+    unsigned long long *h_counters = nullptr;  // pinned, 4 entries
+    std::vector<PinnedBlock> pinned_free;
+    std::mutex pinned_mu;
+    // results of the last msb_scan_device, still on the device
+    int64_t last_sites = 0;
+    int32_t last_n_motifs = 0;
+};
+
+struct TableSet {
+    bool valid = false;
+    int strand = 0;
+    uint64_t cutoff_version = 0;
+    size_t smem_budget = 0;
+    std::vector<int32_t> order;       // sorted index -> motif id (fast motifs only)
+    std::vector<int32_t> slow;        // motif ids scored by the exact kernel everywhere
+    std::vector<BatchDesc> batches;
+    int32_t lmax_fast = 0;
+    int any_zero_hit = 0;
+    DevBuf d_tab, d_order, d_slow;
+};
+
+struct msb_motifs {
+    msb_ctx *ctx = nullptr;
+    int32_t n = 0;
+    std::vector<int32_t> lens, col_off;
+    std::vector<int64_t> mat_off;
+    std::vector<double> mats;     // row-major 4 x L per motif, as given
+    std::vector<double> cutoffs, max_raw;
+    uint64_t cutoff_version = 1;
+    int32_t lmax = 0;
+    DevBuf d_pwm, d_col_off, d_len, d_cutoff, d_max_raw;
+    TableSet tables[4];
+    MotifView view() const {
+        MotifView v;
+        v.pwm = d_pwm.as<double>();
+        v.col_off = d_col_off.as<int32_t>();
+        v.len = d_len.as<int32_t>();
+        v.cutoff = d_cutoff.as<double>();
+        v.max_raw = d_max_raw.as<double>();
+        v.n_motifs = n;
+        return v;
+    }
+};
+
+struct msb_seqs {
+    msb_ctx *ctx = nullptr;
+    int64_t n = 0, total_bp = 0, total_packed = 0;
+    int32_t min_len = 0;
+    std::vector<int64_t> seq_off, poff;
+    DevBuf d_codes, d_nmask, d_poff, d_len, d_seq_off;
+    SeqView view() const {
+        SeqView v;
+        v.codes = d_codes.as<uint32_t>();
+        v.nmask = d_nmask.as<uint32_t>();
+        v.poff = d_poff.as<int64_t>();
+        v.len = d_len.as<int32_t>();
+        v.n_seqs = n;
+        v.total_packed = total_packed;
+        return v;
+    }
+};
+
+struct msb_result {
+    msb_ctx *ctx = nullptr;
+    int64_t n_sites = 0;
+    int32_t n_motifs = 0;
+    PinnedBlock block;
+    int32_t *seq_idx = nullptr;
+    int32_t *start = nullptr;
+    double *score = nullptr;
+    int8_t *strand = nullptr;
+    std::vector<int64_t> counts;
+};
+
+// ------------------------------------------------------------------------------------------------
+static int pinned_get(msb_ctx *ctx, size_t bytes, PinnedBlock *out) {
+    {
+        std::lock_guard<std::mutex> g(ctx->pinned_mu);
+        int best = -1;
+        for (size_t i = 0; i < ctx->pinned_free.size(); i++)
+            if (ctx->pinned_free[i].cap >= bytes &&
+                (best < 0 || ctx->pinned_free[i].cap < ctx->pinned_free[best].cap))
+                best = (int) i;
+        if (best >= 0) {
+            *out = ctx->pinned_free[best];
+            ctx->pinned_free.erase(ctx->pinned_free.begin() + best);
+            return MSB_OK;
+        }
+    }
+    size_t cap = std::max<size_t>(bytes, 4096);
+    void *p = nullptr;
+    MSB_CUDA(cudaHostAlloc(&p, cap, cudaHostAllocDefault));
+    out->p = p;
+    out->cap = cap;
+    return MSB_OK;
+}
+static void pinned_put(msb_ctx *ctx, PinnedBlock b) {
+    if (!b.p) return;
+    std::lock_guard<std::mutex> g(ctx->pinned_mu);
+    if (ctx->pinned_free.size() < 8) ctx->pinned_free.push_back(b);
+    else cudaFreeHost(b.p);
+}
+
+static inline float ev_ms(cudaEvent_t a, cudaEvent_t b) {
+    float ms = 0;
+    cudaEventElapsedTime(&ms, a, b);
+    return ms;
+}
+
+// ------------------------------------------------------------------------------------------------
+extern "C" {
+
+const char *msb_last_error(void) { return g_err.c_str(); }
+int msb_version(void) { return 100; }
+
+int msb_device_count(int *count) {
+    if (!count) { set_error("msb_device_count: null"); return MSB_EINVAL; }
+    int n = 0;
+    cudaError_t e = cudaGetDeviceCount(&n);
+    if (e != cudaSuccess) { cudaGetLastError(); n = 0; }
+    *count = n;
+    return MSB_OK;
+}
+
+int msb_pinned_alloc(int64_t bytes, void **ptr) {
+    if (!ptr || bytes < 0) { set_error("msb_pinned_alloc: bad argument"); return MSB_EINVAL; }
+    MSB_CUDA(cudaHostAlloc(ptr, (size_t) std::max<int64_t>(bytes, 1), cudaHostAllocDefault));
+    return MSB_OK;
+}
+int msb_pinned_free(void *ptr) {
+    if (ptr) MSB_CUDA(cudaFreeHost(ptr));
+    return MSB_OK;
+}
+
+int msb_ctx_create(int device, void *stream, msb_ctx **out) {
+    if (!out) { set_error("msb_ctx_create: null out"); return MSB_EINVAL; }
+    *out = nullptr;
+    int n = 0;
+    cudaError_t e = cudaGetDeviceCount(&n);
+    if (e != cudaSuccess || n == 0) {
+        cudaGetLastError();
+        set_error("no CUDA device available: libmsb200 has no CPU path");
+        return MSB_ECUDA;
+    }
+    if (device < 0 || device >= n) { set_error("msb_ctx_create: device out of range"); return MSB_EINVAL; }
+    MSB_CUDA(cudaSetDevice(device));
+    cudaDeviceProp prop;
+    MSB_CUDA(cudaGetDeviceProperties(&prop, device));
+    if (prop.major != 10) {
+        set_error("libmsb200 is built for sm_100a (B200) only; device is sm_" + std::to_string(prop.major) +
+                  std::to_string(prop.minor));
+        return MSB_ECUDA;
+    }
+    msb_ctx *ctx = new (std::nothrow) msb_ctx();
+    if (!ctx) { set_error("out of host memory"); return MSB_ENOMEM; }
+    ctx->device = device;
+    ctx->sm_count = prop.multiProcessorCount;
+    ctx->smem_optin = prop.sharedMemPerBlockOptin;
+    if (stream) {
+        ctx->stream = (cudaStream_t) stream;
+    } else {
+        cudaError_t se = cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking);
+        if (se != cudaSuccess) { delete ctx; return cuda_fail(se, "cudaStreamCreate", __FILE__, __LINE__); }
+        ctx->own_stream = true;
+    }
+    for (auto &evt : ctx->ev) cudaEventCreate(&evt);
+    cudaHostAlloc((void **) &ctx->h_counters, 4 * sizeof(unsigned long long), cudaHostAllocDefault);
+    if (ctx->counters.ensure(4 * sizeof(unsigned long long)) != MSB_OK || !ctx->h_counters) {
+        msb_ctx_destroy(ctx);
+        return MSB_ENOMEM;
+    }
+    cudaFuncSetAttribute(prefilter_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) ctx->smem_optin);
+    cudaFuncSetAttribute(prefilter_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) ctx->smem_optin);
+    *out = ctx;
+    return MSB_OK;
+}
+
+int msb_ctx_destroy(msb_ctx *ctx) {
+    if (!ctx) return MSB_OK;
+    cudaSetDevice(ctx->device);
+    cudaStreamSynchronize(ctx->stream);
+    for (DevBuf *b : {&ctx->ascii, &ctx->seq_off, &ctx->cand, &ctx->dirty, &ctx->hit_key, &ctx->hit_score,
+                      &ctx->key_alt, &ctx->score_alt, &ctx->sort_tmp, &ctx->counters, &ctx->out_seq,
+                      &ctx->out_start, &ctx->out_strand, &ctx->out_counts, &ctx->scores,
+                      &ctx->scores_sorted, &ctx->seg_off, &ctx->ranks, &ctx->sel})
+        b->release();
+    for (auto &b : ctx->pinned_free) cudaFreeHost(b.p);
+    if (ctx->h_counters) cudaFreeHost(ctx->h_counters);
+    for (auto &evt : ctx->ev) if (evt) cudaEventDestroy(evt);
+    if (ctx->own_stream) cudaStreamDestroy(ctx->stream);
+    delete ctx;
+    return MSB_OK;
+}
+
+int msb_ctx_sync(msb_ctx *ctx) {
+    if (!ctx) { set_error("null ctx"); return MSB_EINVAL; }
+    MSB_CUDA(cudaStreamSynchronize(ctx->stream));
+    return MSB_OK;
+}
+
+int msb_ctx_timings(const msb_ctx *ctx, double *ms, int n) {
+    if (!ctx || !ms) { set_error("msb_ctx_timings: null"); return MSB_EINVAL; }
+    for (int i = 0; i < n && i < MSB_T_COUNT; i++) ms[i] = ctx->t[i];
+    return MSB_OK;
+}
+int msb_ctx_counters(const msb_ctx *ctx, int64_t *v, int n) {
+    if (!ctx || !v) { set_error("msb_ctx_counters: null"); return MSB_EINVAL; }
+    for (int i = 0; i < n && i < MSB_C_COUNT; i++) v[i] = ctx->c[i];
+    return MSB_OK;
+}
+
+// ---- motifs ------------------------------------------------------------------------------------
+int msb_motifs_create(msb_ctx *ctx, int32_t n, const int32_t *lens, const double *mats,
+                      const int64_t *mat_off, const double *cutoffs, msb_motifs **out) {
+    if (!ctx || !out || n < 0 || (n > 0 && (!lens || !mats || !mat_off))) {
+        set_error("msb_motifs_create: bad argument");
+        return MSB_EINVAL;
+    }
+    *out = nullptr;
+    if ((uint64_t) n >= (1ull << (64 - kMotifShift))) { set_error("too many motifs"); return MSB_EINVAL; }
+    for (int32_t m = 0; m < n; m++)
+        if (lens[m] < 0 || mat_off[m] < 0) { set_error("msb_motifs_create: negative length/offset"); return MSB_EINVAL; }
+    MSB_CUDA(cudaSetDevice(ctx->device));
+    msb_motifs *M = new (std::nothrow) msb_motifs();
+    if (!M) { set_error("out of host memory"); return MSB_ENOMEM; }
+    M->ctx = ctx;
+    M->n = n;
+    M->lens.assign(lens, lens + n);
+    M->col_off.resize(n + 1);
+    M->mat_off.resize(n);
+    M->cutoffs.resize(n);
+    M->max_raw.resize(n);
+    int64_t total_cols = 0;
+    for (int32_t m = 0; m < n; m++) {
+        M->col_off[m] = (int32_t) total_cols;
+        total_cols += lens[m];
+        M->lmax = std::max(M->lmax, lens[m]);
+    }
+    M->col_off[n] = (int32_t) total_cols;
+    M->mats.resize((size_t) total_cols * 4);
+    std::vector<double> dev_pwm((size_t) total_cols * 4);  // [motif][col][row]
+    for (int32_t m = 0; m < n; m++) {
+        const int L = lens[m];
+        const double *src = mats + mat_off[m];
+        double *dst = M->mats.data() + 4 * (size_t) M->col_off[m];
+        M->mat_off[m] = 4 * (int64_t) M->col_off[m];
+        std::memcpy(dst, src, sizeof(double) * 4 * (size_t) L);
+        // get_max_raw_score, cscore.c:36-48: column maximum floored at 0, summed ascending.
+        double max_raw = 0;
+        for (int j = 0; j < L; j++) {
+            double col_max = 0;
+            for (int r = 0; r < 4; r++) {
+                const double v = src[(size_t) r * L + j];
+                if (v > col_max) col_max = v;
+                dev_pwm[4 * ((size_t) M->col_off[m] + j) + r] = v;
+            }
+            max_raw += col_max;
+        }
+        M->max_raw[m] = max_raw;
+        M->cutoffs[m] = cutoffs ? cutoffs[m] : 1.0;  // cscore.c:71-75
+    }
+    int rc = MSB_OK;
+    auto up = [&](DevBuf &b, const void *src, size_t bytes) {
+        if (rc != MSB_OK) return;
+        rc = b.ensure(std::max<size_t>(bytes, 16));
+        if (rc == MSB_OK && bytes) {
+            cudaError_t e = cudaMemcpyAsync(b.p, src, bytes, cudaMemcpyHostToDevice, ctx->stream);
+            if (e != cudaSuccess) rc = cuda_fail(e, "cudaMemcpyAsync", __FILE__, __LINE__);
+        }
+    };
+    up(M->d_pwm, dev_pwm.data(), dev_pwm.size() * sizeof(double));
+    up(M->d_col_off, M->col_off.data(), M->col_off.size() * sizeof(int32_t));
+    up(M->d_len, M->lens.data(), (size_t) n * sizeof(int32_t));
+    up(M->d_cutoff, M->cutoffs.data(), (size_t) n * sizeof(double));
+    up(M->d_max_raw, M->max_raw.data(), (size_t) n * sizeof(double));
+    if (rc == MSB_OK) {
+        cudaError_t e = cudaStreamSynchronize(ctx->stream);
+        if (e != cudaSuccess) rc = cuda_fail(e, "cudaStreamSynchronize", __FILE__, __LINE__);
+    }
+    if (rc != MSB_OK) { msb_motifs_destroy(M); return rc; }
+    *out = M;
+    return MSB_OK;
+}
+
+int msb_motifs_set_cutoffs(msb_motifs *M, const double *cutoffs) {
+    if (!M) { set_error("null motifs"); return MSB_EINVAL; }
+    MSB_CUDA(cudaSetDevice(M->ctx->device));
+    for (int32_t m = 0; m < M->n; m++) M->cutoffs[m] = cutoffs ? cutoffs[m] : 1.0;
+    M->cutoff_version++;
+    if (M->n)
+        MSB_CUDA(cudaMemcpyAsync(M->d_cutoff.p, M->cutoffs.data(), (size_t) M->n * sizeof(double),
+                                 cudaMemcpyHostToDevice, M->ctx->stream));
+    MSB_CUDA(cudaStreamSynchronize(M->ctx->stream));
+    return MSB_OK;
+}
+
+int msb_motifs_count(const msb_motifs *M, int32_t *n) {
+    if (!M || !n) { set_error("null"); return MSB_EINVAL; }
+    *n = M->n;
+    return MSB_OK;
+}
+int msb_motifs_max_raw(const msb_motifs *M, double *out) {
+    if (!M || !out) { set_error("null"); return MSB_EINVAL; }
+    std::copy(M->max_raw.begin(), M->max_raw.end(), out);
+    return MSB_OK;
+}
+int msb_motifs_destroy(msb_motifs *M) {
+    if (!M) return MSB_OK;
+    cudaSetDevice(M->ctx->device);
+    cudaStreamSynchronize(M->ctx->stream);
+    for (DevBuf *b : {&M->d_pwm, &M->d_col_off, &M->d_len, &M->d_cutoff, &M->d_max_raw}) b->release();
+    for (auto &t : M->tables) { t.d_tab.release(); t.d_order.release(); t.d_slow.release(); }
+    delete M;
+    return MSB_OK;
+}
+
+// ---- sequences ---------------------------------------------------------------------------------
+int msb_seqs_from_ascii(msb_ctx *ctx, int64_t n_seqs, const char *bytes, const int64_t *seq_off,
+                        msb_seqs **out) {
+    if (!ctx || !out || n_seqs < 0 || !seq_off || (seq_off[n_seqs] > 0 && !bytes)) {
+        set_error("msb_seqs_from_ascii: bad argument");
+        return MSB_EINVAL;
+    }
+    *out = nullptr;
+    if (seq_off[0] != 0) { set_error("seq_off[0] must be 0"); return MSB_EINVAL; }
+    for (int64_t i = 0; i < n_seqs; i++) {
+        const int64_t len = seq_off[i + 1] - seq_off[i];
+        if (len < 0 || len > (int64_t) 0x7fffffff - 64) {
+            set_error("msb_seqs_from_ascii: sequence offsets not ascending or sequence >= 2^31 bases");
+            return MSB_EINVAL;
+        }
+    }
+    MSB_CUDA(cudaSetDevice(ctx->device));
+    msb_seqs *S = new (std::nothrow) msb_seqs();
+    if (!S) { set_error("out of host memory"); return MSB_ENOMEM; }
+    S->ctx = ctx;
+    S->n = n_seqs;
+    S->total_bp = seq_off[n_seqs];
+    S->seq_off.assign(seq_off, seq_off + n_seqs + 1);
+    S->poff.resize(n_seqs + 1);
+    std::vector<int32_t> lens((size_t) std::max<int64_t>(n_seqs, 1));
+    int64_t at = 0;
+    int32_t min_len = n_seqs ? std::numeric_limits<int32_t>::max() : 0;
+    for (int64_t i = 0; i < n_seqs; i++) {
+        const int64_t len = seq_off[i + 1] - seq_off[i];
+        S->poff[i] = at;
+        lens[i] = (int32_t) len;
+        min_len = std::min<int32_t>(min_len, (int32_t) len);
+        at += (len + kPadBases - 1) / kPadBases * kPadBases;
+    }
+    S->poff[n_seqs] = at;
+    S->total_packed = at;
+    S->min_len = min_len;
+    if ((uint64_t) at >= (1ull << kPosBits)) { delete S; set_error("sequence set too large"); return MSB_EINVAL; }
+
+    int rc = MSB_OK;
+    const int64_t n_blocks = at / kPadBases;
+    // +8 / +4 words of zero padding: the prefilter reads up to 3 code words / 2 mask words
+    // starting at the word of a thread's first window.
+    if ((rc = S->d_codes.ensure((size_t) (2 * n_blocks + 8) * 4)) != MSB_OK ||
+        (rc = S->d_nmask.ensure((size_t) (n_blocks + 4) * 4)) != MSB_OK ||
+        (rc = S->d_poff.ensure((size_t) (n_seqs + 1) * 8)) != MSB_OK ||
+        (rc = S->d_len.ensure((size_t) std::max<int64_t>(n_seqs, 1) * 4)) != MSB_OK ||
+        (rc = S->d_seq_off.ensure((size_t) (n_seqs + 1) * 8)) != MSB_OK ||
+        (rc = ctx->ascii.ensure((size_t) std::max<int64_t>(S->total_bp, 16))) != MSB_OK) {
+        msb_seqs_destroy(S);
+        return rc;
+    }
+    cudaStream_t st = ctx->stream;
+    cudaError_t e = cudaSuccess;
+    auto step = [&](cudaError_t x) { if (e == cudaSuccess) e = x; };
+    step(cudaEventRecord(ctx->ev[0], st));
+    step(cudaMemsetAsync(S->d_codes.p, 0, (size_t) (2 * n_blocks + 8) * 4, st));
+    step(cudaMemsetAsync(S->d_nmask.p, 0, (size_t) (n_blocks + 4) * 4, st));
+    step(cudaMemcpyAsync(S->d_poff.p, S->poff.data(), (size_t) (n_seqs + 1) * 8, cudaMemcpyHostToDevice, st));
+    step(cudaMemcpyAsync(S->d_seq_off.p, S->seq_off.data(), (size_t) (n_seqs + 1) * 8, cudaMemcpyHostToDevice, st));
+    if (n_seqs) step(cudaMemcpyAsync(S->d_len.p, lens.data(), (size_t) n_seqs * 4, cudaMemcpyHostToDevice, st));
+    if (S->total_bp) step(cudaMemcpyAsync(ctx->ascii.p, bytes, (size_t) S->total_bp, cudaMemcpyHostToDevice, st));
+    step(cudaEventRecord(ctx->ev[1], st));
+    if (e == cudaSuccess && n_blocks > 0) {
+        const int64_t grid = (n_blocks + 255) / 256;
+        encode_pack_kernel<<<(unsigned) grid, 256, 0, st>>>(
+            ctx->ascii.as<uint8_t>(), S->d_seq_off.as<int64_t>(), S->d_poff.as<int64_t>(), S->d_len.as<int32_t>(),
+            n_seqs, n_blocks, S->d_codes.as<uint32_t>(), S->d_nmask.as<uint32_t>());
+        step(cudaGetLastError());
+    }
+    step(cudaEventRecord(ctx->ev[2], st));
+    step(cudaStreamSynchronize(st));  // `bytes` and `lens` may go away after return
+    if (e != cudaSuccess) {
+        msb_seqs_destroy(S);
+        return cuda_fail(e, "msb_seqs_from_ascii", __FILE__, __LINE__);
+    }
+    ctx->t[MSB_T_H2D] = ev_ms(ctx->ev[0], ctx->ev[1]);
+    ctx->t[MSB_T_ENCODE] = ev_ms(ctx->ev[1], ctx->ev[2]);
+    *out = S;
+    return MSB_OK;
+}
+
+int msb_seqs_count(const msb_seqs *S, int64_t *n_seqs, int64_t *total_bp) {
+    if (!S) { set_error("null seqs"); return MSB_EINVAL; }
+    if (n_seqs) *n_seqs = S->n;
+    if (total_bp) *total_bp = S->total_bp;
+    return MSB_OK;
+}
+
+int msb_seqs_codes(msb_ctx *ctx, const msb_seqs *S, int8_t *codes) {
+    if (!ctx || !S || (!codes && S->total_bp)) { set_error("msb_seqs_codes: null"); return MSB_EINVAL; }
+    if (S->total_bp == 0) return MSB_OK;
+    MSB_CUDA(cudaSetDevice(ctx->device));
+    DevBuf tmp;
+    MSB_TRY(tmp.ensure((size_t) S->total_bp));
+    const int64_t grid = (S->total_packed + 255) / 256;
+    unpack_codes_kernel<<<(unsigned) grid, 256, 0, ctx->stream>>>(S->view(), S->d_seq_off.as<int64_t>(), tmp.as<int8_t>());
+    cudaError_t e = cudaGetLastError();
+    if (e == cudaSuccess) e = cudaMemcpyAsync(codes, tmp.p, (size_t) S->total_bp, cudaMemcpyDeviceToHost, ctx->stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
+    tmp.release();
+    if (e != cudaSuccess) return cuda_fail(e, "msb_seqs_codes", __FILE__, __LINE__);
+    return MSB_OK;
+}
+
+int msb_seqs_destroy(msb_seqs *S) {
+    if (!S) return MSB_OK;
+    cudaSetDevice(S->ctx->device);
+    cudaStreamSynchronize(S->ctx->stream);
+    for (DevBuf *b : {&S->d_codes, &S->d_nmask, &S->d_poff, &S->d_len, &S->d_seq_off}) b->release();
+    delete S;
+    return MSB_OK;
+}
+
+}  // extern "C"
+
+// ------------------------------------------------------------------------------------------------
+// Prefilter tables.
+//
+// For motif m (length L, G = ceil(L/2) groups) and 2-mer index i = b0 + 4*b1 of the bases at
+// window offsets 2g, 2g+1:
+//     f_g(i) = M[b0][2g] + M[b1][2g+1]                 forward   (cscore.c:348)
+//     r_g(i) = M[3-b0][L-1-2g] + M[3-b1][L-2-2g]       reverse   (cscore.c:351)
+// (second term dropped when 2g+1 == L).  With scale s, per-group minima and the real-valued
+// threshold T below, the stored 16-bit quantities are ceil((f_g - min f_g) * s), so that
+//     sum_g q_g  >=  s * (raw - sum_g min f_g)        for every window,
+// and a window is a candidate iff  sum_g q_g >= Qthr = floor(s * (T - sum_g min f_g)) - 1.
+// T is a strict under-estimate of the smallest exact raw score the reference could accept:
+//     score/max_raw - cutoff >= -1e-10  (evaluated in double, cscore.c:357-358)
+//     =>  raw >= max_raw * (cutoff - 1e-10) - 1e-12 * (max_raw * (|cutoff| + 1) + sum_c max_b |M[b][c]|)
+// (the 1e-12 term is > 1000x the worst-case rounding of the L-term double sum, the division
+// and the subtraction).  Hence candidates are a superset of the reference's hits; the exact
+// stage removes the rest.  Group 0 also carries the bias 32768 - Qthr, so bit 15 of the 16-bit
+// sum is the candidate flag; the forward quantity lives in bits 16..31 of the entry, the
+// reverse one in bits 0..15, and one 32-bit add accumulates both.
+// ------------------------------------------------------------------------------------------------
+namespace msb {
+
+static bool motif_is_fast(const msb_motifs *M, int32_t m) {
+    const int L = M->lens[m];
+    if (L < 1 || L > kMaxFastLen) return false;
+    const double *mat = M->mats.data() + M->mat_off[m];
+    for (int k = 0; k < 4 * L; k++)
+        if (!std::isfinite(mat[k])) return false;
+    return true;
+}
+
+static void build_motif_table(const msb_motifs *M, int32_t m, int strand, uint32_t *out /* G*16 words */) {
+    const int L = M->lens[m];
+    const int G = (L + 1) / 2;
+    const double *mat = M->mats.data() + M->mat_off[m];
+    auto at = [&](int row, int col) { return mat[(size_t) row * L + col]; };
+    const double max_raw = M->max_raw[m];
+    const double cutoff = M->cutoffs[m];
+    std::fill(out, out + (size_t) G * kGroupWords, 0u);
+    // Motifs that can never produce a site keep all-zero tables (flag bits never set):
+    // max_raw == 0 gives score = raw/0 = -inf or NaN; cutoff NaN / +inf fail the predicate.
+    if (!(max_raw > 0) || std::isnan(cutoff) || (std::isinf(cutoff) && cutoff > 0)) return;
+
+    double f[kMaxGroups][16], r[kMaxGroups][16];
+    double fmin_sum = 0, fmax_sum = 0, rmin_sum = 0, rmax_sum = 0, abs_sum = 0;
+    double fmin[kMaxGroups], rmin[kMaxGroups];
+    for (int c = 0; c < L; c++) {
+        double a = 0;
+        for (int row = 0; row < 4; row++) a = std::max(a, std::fabs(at(row, c)));
+        abs_sum += a;
+    }
+    for (int g = 0; g < G; g++) {
+        const int c0 = 2 * g, c1 = 2 * g + 1;
+        double fmn = INFINITY, fmx = -INFINITY, rmn = INFINITY, rmx = -INFINITY;
+        for (int i = 0; i < 16; i++) {
+            const int b0 = i & 3, b1 = i >> 2;
+            double fv = at(b0, c0), rv = at(3 - b0, L - 1 - c0);
+            if (c1 < L) { fv += at(b1, c1); rv += at(3 - b1, L - 1 - c1); }
+            f[g][i] = fv;
+            r[g][i] = rv;
+            fmn = std::min(fmn, fv); fmx = std::max(fmx, fv);
+            rmn = std::min(rmn, rv); rmx = std::max(rmx, rv);
+        }
+        fmin[g] = fmn; rmin[g] = rmn;
+        fmin_sum += fmn; fmax_sum += fmx; rmin_sum += rmn; rmax_sum += rmx;
+    }
+    double T;
+    if (std::isinf(cutoff)) {  // -inf: every window with a finite score is a site
+        T = std::min(fmin_sum, rmin_sum) - 1.0;
+    } else {
+        T = max_raw * (cutoff - 1e-10) - 1e-12 * (max_raw * (std::fabs(cutoff) + 1.0) + abs_sum);
+    }
+    const double lo = std::min(fmin_sum, rmin_sum), hi = std::max(fmax_sum, rmax_sum);
+    double range = std::max(std::max(hi - T, T - lo), 0.0);
+    double s = range > 0 ? 32000.0 / range : 1.0;
+    if (!(s < 1e9)) s = 1e9;
+    for (int dir = 0; dir < 2; dir++) {
+        if (!(strand & (dir ? 2 : 1))) continue;
+        const double (*v)[16] = dir ? r : f;
+        const double *vmin = dir ? rmin : fmin;
+        const double min_sum = dir ? rmin_sum : fmin_sum;
+        double qthr_d = std::floor(s * (T - min_sum)) - 1.0;
+        qthr_d = std::max(qthr_d, -32000.0 - 64.0);  // T below every score: all windows flagged
+        const int64_t bias = 32768 - (int64_t) qthr_d;
+        for (int g = 0; g < G; g++)
+            for (int i = 0; i < 16; i++) {
+                int64_t q = (int64_t) std::ceil((v[g][i] - vmin[g]) * s);
+                if (g == 0) q += bias;
+                // linear packing: sum of entries == (sum fwd) * 65536 + (sum rev)  (mod 2^32)
+                out[(size_t) g * kGroupWords + i] += dir ? (uint32_t) q : (uint32_t) (q << 16);
+            }
+    }
+}
+
+static int ensure_tables(msb_ctx *ctx, msb_motifs *M, int strand, TableSet **out) {
+    TableSet &T = M->tables[strand];
+    const size_t budget = ctx->smem_optin;
+    if (T.valid && T.cutoff_version == M->cutoff_version && T.smem_budget == budget) { *out = &T; return MSB_OK; }
+    T.valid = false;
+    T.order.clear();
+    T.slow.clear();
+    T.batches.clear();
+    T.lmax_fast = 0;
+    T.any_zero_hit = 0;
+    std::vector<int32_t> fast;
+    for (int32_t m = 0; m < M->n; m++) {
+        if (motif_is_fast(M, m)) fast.push_back(m);
+        else if (M->lens[m] >= 1) T.slow.push_back(m);  // L == 0: score is 0/0 = NaN, never a site
+    }
+    std::stable_sort(fast.begin(), fast.end(), [&](int32_t a, int32_t b) {
+        return (M->lens[a] + 1) / 2 < (M->lens[b] + 1) / 2;
+    });
+    T.order = fast;
+    std::vector<uint32_t> tab;
+    size_t total_words = 0;
+    for (int32_t m : fast) total_words += (size_t) ((M->lens[m] + 1) / 2) * kGroupWords;
+    tab.resize(total_words + 4);
+    size_t at = 0;
+    BatchDesc cur;
+    std::memset(&cur, 0, sizeof(cur));
+    auto flush = [&]() {
+        if (cur.tab_words) {
+            cur.tab_words = (cur.tab_words + 3) & ~3u;
+            T.batches.push_back(cur);
+        }
+    };
+    for (size_t k = 0; k < fast.size(); k++) {
+        const int32_t m = fast[k];
+        const int G = (M->lens[m] + 1) / 2;
+        const uint32_t words = (uint32_t) G * kGroupWords;
+        if (((size_t) cur.tab_words + words) * 4 > budget || cur.g_count[G] == 0xffff) {
+            flush();
+            std::memset(&cur, 0, sizeof(cur));
+        }
+        if (cur.tab_words == 0) {
+            cur.tab_word_off = (uint32_t) at;
+            cur.first_sorted = (uint32_t) k;
+        }
+        build_motif_table(M, m, strand, tab.data() + at);
+        at += words;
+        cur.tab_words += words;
+        cur.g_count[G]++;
+        T.lmax_fast = std::max(T.lmax_fast, M->lens[m]);
+        // all-N window: score = 0 / max_raw (cscore.c:342-357 with every base skipped)
+        const double z = 0.0 / M->max_raw[m];
+        if (z - M->cutoffs[m] >= -1e-10) T.any_zero_hit = 1;
+    }
+    flush();
+    MSB_TRY(T.d_tab.ensure(std::max<size_t>(tab.size() * 4, 16)));
+    MSB_TRY(T.d_order.ensure(std::max<size_t>(fast.size() * 4, 16)));
+    MSB_TRY(T.d_slow.ensure(std::max<size_t>(T.slow.size() * 4, 16)));
+    MSB_CUDA(cudaMemcpyAsync(T.d_tab.p, tab.data(), tab.size() * 4, cudaMemcpyHostToDevice, ctx->stream));
+    if (!fast.empty())
+        MSB_CUDA(cudaMemcpyAsync(T.d_order.p, fast.data(), fast.size() * 4, cudaMemcpyHostToDevice, ctx->stream));
+    if (!T.slow.empty())
+        MSB_CUDA(cudaMemcpyAsync(T.d_slow.p, T.slow.data(), T.slow.size() * 4, cudaMemcpyHostToDevice, ctx->stream));
+    MSB_CUDA(cudaStreamSynchronize(ctx->stream));  // host vectors go out of scope
+    T.strand = strand;
+    T.cutoff_version = M->cutoff_version;
+    T.smem_budget = budget;
+    T.valid = true;
+    *out = &T;
+    return MSB_OK;
+}
+
+static int read_counters(msb_ctx *ctx) {
+    MSB_CUDA(cudaMemcpyAsync(ctx->h_counters, ctx->counters.p, 4 * sizeof(unsigned long long),
+                             cudaMemcpyDeviceToHost, ctx->stream));
+    MSB_CUDA(cudaStreamSynchronize(ctx->stream));
+    return MSB_OK;
+}
+
+static int launch_positions(msb_ctx *ctx, const ExactParams &E, const int64_t *pos, int64_t n_pos,
+                            const int32_t *ids, int32_t n_ids) {
+    // one thread per (position, motif); split so that a launch stays below 2^31 blocks
+    if (n_pos <= 0 || n_ids <= 0) return MSB_OK;
+    const int64_t max_threads = (int64_t) 1 << 38;
+    const int64_t pos_per_launch = std::max<int64_t>(1, max_threads / n_ids);
+    for (int64_t at = 0; at < n_pos; at += pos_per_launch) {
+        const int64_t cnt = std::min(pos_per_launch, n_pos - at);
+        const int64_t threads = cnt * n_ids;
+        ExactParams e2 = E;
+        if (pos) {
+            exact_positions_kernel<<<(unsigned) ((threads + 255) / 256), 256, 0, ctx->stream>>>(e2, pos + at, cnt, ids, n_ids);
+        } else {
+            // pos == nullptr: the kernel takes the thread's position index as the packed position.
+            // Only one slice is supported (needs total_packed * n_ids <= 2^38 threads).
+            if (at != 0) { set_error("sequence set too large for the slow-motif path"); return MSB_EINVAL; }
+            exact_positions_kernel<<<(unsigned) ((threads + 255) / 256), 256, 0, ctx->stream>>>(e2, nullptr, cnt, ids, n_ids);
+        }
+        MSB_CUDA(cudaGetLastError());
+        ctx->c[MSB_C_LAUNCHES]++;
+    }
+    return MSB_OK;
+}
+
+static int g_prefilter_w = 4;  // windows per thread (4 or 8); overridable for experiments
+
+static int scan_device(msb_ctx *ctx, msb_motifs *M, const msb_seqs *S, int strand) {
+    if (!ctx || !M || !S) { set_error("msb_scan: null argument"); return MSB_EINVAL; }
+    if (strand < 1 || strand > 3) { set_error("msb_scan: strand must be 1, 2 or 3"); return MSB_EINVAL; }
+    if (M->ctx != ctx || S->ctx != ctx) { set_error("msb_scan: motifs/seqs belong to another context"); return MSB_EINVAL; }
+    MSB_CUDA(cudaSetDevice(ctx->device));
+    TableSet *T = nullptr;
+    MSB_TRY(ensure_tables(ctx, M, strand, &T));
+    cudaStream_t st = ctx->stream;
+    std::fill(ctx->c, ctx->c + MSB_C_COUNT, 0);
+    ctx->last_sites = 0;
+    ctx->last_n_motifs = M->n;
+    MSB_TRY(ctx->out_counts.ensure(std::max<size_t>((size_t) M->n * 8, 16)));
+    MSB_CUDA(cudaMemsetAsync(ctx->out_counts.p, 0, std::max<size_t>((size_t) M->n * 8, 16), st));
+    if (M->n == 0 || S->total_packed == 0) {
+        MSB_CUDA(cudaStreamSynchronize(st));
+        return MSB_OK;
+    }
+    const SeqView sv = S->view();
+    const MotifView mv = M->view();
+
+    // ---- stage 1: prefilter ------------------------------------------------------------------
+    const double cells = (double) S->total_packed * (double) std::max<size_t>(T->order.size(), 1);
+    int64_t cand_cap = (int64_t) std::min<double>(std::max<double>(cells / 512.0, 1 << 20), (double) (1ll << 30));
+    int64_t dirty_cap = std::max<int64_t>(1 << 16, S->total_packed / 64);
+    if (ctx->cand.cap / 8 > (size_t) cand_cap) cand_cap = (int64_t) (ctx->cand.cap / 8);
+    if (ctx->dirty.cap / 8 > (size_t) dirty_cap) dirty_cap = (int64_t) (ctx->dirty.cap / 8);
+    int64_t n_cand = 0, n_dirty = 0;
+    MSB_CUDA(cudaEventRecord(ctx->ev[0], st));
+    for (int attempt = 0;; attempt++) {
+        MSB_TRY(ctx->cand.ensure((size_t) cand_cap * 8));
+        MSB_TRY(ctx->dirty.ensure((size_t) dirty_cap * 8));
+        MSB_CUDA(cudaMemsetAsync(ctx->counters.p, 0, 4 * sizeof(unsigned long long), st));
+        PrefilterParams P;
+        P.seq = sv;
+        P.tab = T->d_tab.as<uint32_t>();
+        P.order = T->d_order.as<int32_t>();
+        P.mlen = mv.len;
+        P.lmax_all = std::max(T->lmax_fast, 1);
+        P.any_zero_hit = T->any_zero_hit;
+        P.cand = ctx->cand.as<uint64_t>();
+        P.cand_cap = cand_cap;
+        P.dirty = ctx->dirty.as<int64_t>();
+        P.dirty_cap = dirty_cap;
+        P.counters = ctx->counters.as<unsigned long long>();
+        for (size_t b = 0; b < T->batches.size(); b++) {
+            P.batch = T->batches[b];
+            P.emit_dirty = (b == 0);
+            const size_t smem = (size_t) P.batch.tab_words * 4;
+            if (g_prefilter_w == 8)
+                prefilter_kernel<8><<<ctx->sm_count, PF<8>::kThreads, smem, st>>>(P);
+            else
+                prefilter_kernel<4><<<ctx->sm_count, PF<4>::kThreads, smem, st>>>(P);
+            MSB_CUDA(cudaGetLastError());
+            ctx->c[MSB_C_LAUNCHES]++;
+            ctx->c[MSB_C_PREFILTER_LAUNCHES]++;
+        }
+        MSB_CUDA(cudaEventRecord(ctx->ev[1], st));
+        MSB_TRY(read_counters(ctx));
+        n_cand = (int64_t) ctx->h_counters[0];
+        n_dirty = (int64_t) ctx->h_counters[1];
+        if (n_cand <= cand_cap && n_dirty <= dirty_cap) break;
+        if (attempt >= 2) { set_error("msb_scan: candidate buffers kept overflowing"); return MSB_ENOMEM; }
+        ctx->c[MSB_C_RETRIES]++;
+        cand_cap = std::max(cand_cap, n_cand + n_cand / 16 + 1024);
+        dirty_cap = std::max(dirty_cap, n_dirty + n_dirty / 16 + 1024);
+        MSB_CUDA(cudaEventRecord(ctx->ev[0], st));
+    }
+    ctx->c[MSB_C_CANDIDATES] = n_cand;
+    ctx->c[MSB_C_DIRTY] = n_dirty;
+
+    // ---- stage 2: exact fp64 re-score ----------------------------------------------------------
+    const int32_t n_fast = (int32_t) T->order.size(), n_slow = (int32_t) T->slow.size();
+    int64_t hit_cap = std::max<int64_t>(n_cand + 1024, 1 << 16);
+    if (n_dirty) hit_cap += std::min<int64_t>(n_dirty * 2 * std::max(n_fast, 1), 1 << 24);
+    if (n_slow) hit_cap += 1 << 20;
+    if (ctx->hit_key.cap / 8 > (size_t) hit_cap) hit_cap = (int64_t) (ctx->hit_key.cap / 8);
+    int64_t n_hits = 0;
+    for (int attempt = 0;; attempt++) {
+        MSB_TRY(ctx->hit_key.ensure((size_t) hit_cap * 8));
+        MSB_TRY(ctx->hit_score.ensure((size_t) hit_cap * 8));
+        MSB_CUDA(cudaMemsetAsync(ctx->counters.as<unsigned long long>() + 2, 0, sizeof(unsigned long long), st));
+        ExactParams E;
+        E.seq = sv;
+        E.mot = mv;
+        E.strand = strand;
+        E.hit_key = ctx->hit_key.as<uint64_t>();
+        E.hit_score = ctx->hit_score.as<double>();
+        E.hit_cap = hit_cap;
+        E.counters = ctx->counters.as<unsigned long long>();
+        if (n_cand) {
+            exact_candidates_kernel<<<(unsigned) ((n_cand + 255) / 256), 256, 0, st>>>(
+                E, ctx->cand.as<uint64_t>(), n_cand, T->d_order.as<int32_t>());
+            MSB_CUDA(cudaGetLastError());
+            ctx->c[MSB_C_LAUNCHES]++;
+        }
+        if (n_dirty && n_fast)
+            MSB_TRY(launch_positions(ctx, E, ctx->dirty.as<int64_t>(), n_dirty, T->d_order.as<int32_t>(), n_fast));
+        if (n_slow)
+            MSB_TRY(launch_positions(ctx, E, nullptr, S->total_packed, T->d_slow.as<int32_t>(), n_slow));
+        MSB_CUDA(cudaEventRecord(ctx->ev[2], st));
+        MSB_TRY(read_counters(ctx));
+        n_hits = (int64_t) ctx->h_counters[2];
+        if (n_hits <= hit_cap) break;
+        if (attempt >= 2) { set_error("msb_scan: hit buffers kept overflowing"); return MSB_ENOMEM; }
+        ctx->c[MSB_C_RETRIES]++;
+        hit_cap = n_hits + 1024;
+    }
+    ctx->c[MSB_C_HITS] = n_hits;
+
+    // ---- stage 3: order (motif, sequence, start, fwd < rev) and decode --------------------------
+    if (n_hits) {
+        MSB_TRY(ctx->key_alt.ensure((size_t) n_hits * 8));
+        MSB_TRY(ctx->score_alt.ensure((size_t) n_hits * 8));
+        MSB_TRY(ctx->out_seq.ensure((size_t) n_hits * 4));
+        MSB_TRY(ctx->out_start.ensure((size_t) n_hits * 4));
+        MSB_TRY(ctx->out_strand.ensure((size_t) n_hits));
+        int motif_bits = 1;
+        while ((1ll << motif_bits) < (int64_t) M->n) motif_bits++;
+        const int end_bit = std::min(64, kMotifShift + motif_bits);
+        size_t tmp_bytes = 0;
+        MSB_CUDA(cub::DeviceRadixSort::SortPairs(nullptr, tmp_bytes, ctx->hit_key.as<uint64_t>(), ctx->key_alt.as<uint64_t>(),
+                                                 ctx->hit_score.as<double>(), ctx->score_alt.as<double>(), n_hits, 0, end_bit, st));
+        MSB_TRY(ctx->sort_tmp.ensure(std::max<size_t>(tmp_bytes, 16)));
+        MSB_CUDA(cub::DeviceRadixSort::SortPairs(ctx->sort_tmp.p, tmp_bytes, ctx->hit_key.as<uint64_t>(), ctx->key_alt.as<uint64_t>(),
+                                                 ctx->hit_score.as<double>(), ctx->score_alt.as<double>(), n_hits, 0, end_bit, st));
+        decode_sites_kernel<<<(unsigned) ((n_hits + 255) / 256), 256, 0, st>>>(
+            sv, ctx->key_alt.as<uint64_t>(), n_hits, ctx->out_seq.as<int32_t>(), ctx->out_start.as<int32_t>(),
+            ctx->out_strand.as<int8_t>(), ctx->out_counts.as<unsigned long long>());
+        MSB_CUDA(cudaGetLastError());
+        ctx->c[MSB_C_LAUNCHES] += 2;  // sort (several CUB kernels, counted once) + decode
+    }
+    MSB_CUDA(cudaEventRecord(ctx->ev[3], st));
+    MSB_CUDA(cudaStreamSynchronize(st));
+    ctx->t[MSB_T_PREFILTER] = ev_ms(ctx->ev[0], ctx->ev[1]);
+    ctx->t[MSB_T_EXACT] = ev_ms(ctx->ev[1], ctx->ev[2]);
+    ctx->t[MSB_T_ORDER] = ev_ms(ctx->ev[2], ctx->ev[3]);
+    ctx->t[MSB_T_D2H] = 0;
+    ctx->last_sites = n_hits;
+    return MSB_OK;
+}
+
+}  // namespace msb
+
+extern "C" {
+
+int msb_set_option(const char *name, int value) {
+    if (name && !std::strcmp(name, "prefilter_w") && (value == 4 || value == 8)) { g_prefilter_w = value; return MSB_OK; }
+    set_error("msb_set_option: unknown option or value");
+    return MSB_EINVAL;
+}
+
+int msb_scan_device(msb_ctx *ctx, const msb_motifs *M, const msb_seqs *S, int strand, int64_t *n_sites) {
+    MSB_TRY(scan_device(ctx, const_cast<msb_motifs *>(M), S, strand));
+    if (n_sites) *n_sites = ctx->last_sites;
+    return MSB_OK;
+}
+
+int msb_scan(msb_ctx *ctx, const msb_motifs *M, const msb_seqs *S, int strand, msb_result **out) {
+    if (!out) { set_error("msb_scan: null out"); return MSB_EINVAL; }
+    *out = nullptr;
+    MSB_TRY(scan_device(ctx, const_cast<msb_motifs *>(M), S, strand));
+    msb_result *R = new (std::nothrow) msb_result();
+    if (!R) { set_error("out of host memory"); return MSB_ENOMEM; }
+    R->ctx = ctx;
+    R->n_sites = ctx->last_sites;
+    R->n_motifs = M->n;
+    R->counts.assign((size_t) M->n, 0);
+    const int64_t n = R->n_sites;
+    // one pinned block: score (8n) | seq_idx (4n) | start (4n) | strand (n)
+    int rc = pinned_get(ctx, (size_t) std::max<int64_t>(17 * n, 64), &R->block);
+    if (rc != MSB_OK) { delete R; return rc; }
+    char *base = (char *) R->block.p;
+    R->score = (double *) base;
+    R->seq_idx = (int32_t *) (base + 8 * n);
+    R->start = (int32_t *) (base + 12 * n);
+    R->strand = (int8_t *) (base + 16 * n);
+    cudaStream_t st = ctx->stream;
+    cudaError_t e = cudaEventRecord(ctx->ev[4], st);
+    auto step = [&](cudaError_t x) { if (e == cudaSuccess) e = x; };
+    if (n) {
+        step(cudaMemcpyAsync(R->score, ctx->score_alt.p, (size_t) n * 8, cudaMemcpyDeviceToHost, st));
+        step(cudaMemcpyAsync(R->seq_idx, ctx->out_seq.p, (size_t) n * 4, cudaMemcpyDeviceToHost, st));
+        step(cudaMemcpyAsync(R->start, ctx->out_start.p, (size_t) n * 4, cudaMemcpyDeviceToHost, st));
+        step(cudaMemcpyAsync(R->strand, ctx->out_strand.p, (size_t) n, cudaMemcpyDeviceToHost, st));
+    }
+    if (M->n) step(cudaMemcpyAsync(R->counts.data(), ctx->out_counts.p, (size_t) M->n * 8, cudaMemcpyDeviceToHost, st));
+    step(cudaEventRecord(ctx->ev[5], st));
+    step(cudaStreamSynchronize(st));
+    if (e != cudaSuccess) { msb_result_destroy(R); return cuda_fail(e, "msb_scan D2H", __FILE__, __LINE__); }
+    ctx->t[MSB_T_D2H] = ev_ms(ctx->ev[4], ctx->ev[5]);
+    *out = R;
+    return MSB_OK;
+}
+
+int msb_result_total(const msb_result *R, int64_t *n) {
+    if (!R || !n) { set_error("null"); return MSB_EINVAL; }
+    *n = R->n_sites;
+    return MSB_OK;
+}
+int msb_result_counts(const msb_result *R, int64_t *counts) {
+    if (!R || (!counts && R->n_motifs)) { set_error("null"); return MSB_EINVAL; }
+    std::copy(R->counts.begin(), R->counts.end(), counts);
+    return MSB_OK;
+}
+int msb_result_arrays(const msb_result *R, const int32_t **seq_idx, const int32_t **start,
+                      const double **score, const int8_t **strand) {
+    if (!R) { set_error("null result"); return MSB_EINVAL; }
+    if (seq_idx) *seq_idx = R->seq_idx;
+    if (start) *start = R->start;
+    if (score) *score = R->score;
+    if (strand) *strand = R->strand;
+    return MSB_OK;
+}
+int msb_result_destroy(msb_result *R) {
+    if (!R) return MSB_OK;
+    if (R->ctx) pinned_put(R->ctx, R->block);
+    else if (R->block.p) cudaFreeHost(R->block.p);
+    delete R;
+    return MSB_OK;
+}
+
+// ---- c_score -----------------------------------------------------------------------------------
+static int check_score_args(msb_ctx *ctx, const msb_motifs *M, const msb_seqs *S, int strand) {
+    if (!ctx || !M || !S) { set_error("msb_score: null argument"); return MSB_EINVAL; }
+    if (strand < 1 || strand > 3) { set_error("msb_score: strand must be 1, 2 or 3"); return MSB_EINVAL; }
+    if (M->ctx != ctx || S->ctx != ctx) { set_error("msb_score: motifs/seqs belong to another context"); return MSB_EINVAL; }
+    if (S->n > 0 && M->n > 0 && S->min_len < M->lmax) {
+        // the reference reads lens[m] bases without a length check (cscore.c:195): undefined there
+        set_error("msb_score: a sequence is shorter than the longest motif");
+        return MSB_ESHORT;
+    }
+    return MSB_OK;
+}
+
+static int launch_score0(msb_ctx *ctx, const msb_motifs *M, const msb_seqs *S, int strand, int32_t m0,
+                         int32_t m1, double *d_out) {
+    dim3 grid((unsigned) ((S->n + 255) / 256), (unsigned) std::min<int32_t>(m1 - m0, 1024));
+    score0_kernel<<<grid, 256, 0, ctx->stream>>>(S->view(), M->view(), strand, m0, m1, S->n, d_out);
+    MSB_CUDA(cudaGetLastError());
+    return MSB_OK;
+}
+
+int msb_score(msb_ctx *ctx, const msb_motifs *M, const msb_seqs *S, int strand, double *out) {
+    MSB_TRY(check_score_args(ctx, M, S, strand));
+    if (M->n == 0 || S->n == 0) return MSB_OK;
+    if (!out) { set_error("msb_score: null out"); return MSB_EINVAL; }
+    MSB_CUDA(cudaSetDevice(ctx->device));
+    // motif slices bound the device buffer (n_motifs x n_seqs doubles can exceed HBM)
+    const int64_t max_elems = (int64_t) 1 << 29;  // 4 GiB of doubles per slice
+    const int32_t per = (int32_t) std::max<int64_t>(1, std::min<int64_t>(M->n, max_elems / std::max<int64_t>(S->n, 1)));
+    MSB_TRY(ctx->scores.ensure((size_t) per * (size_t) S->n * 8));
+    double total_ms = 0;
+    for (int32_t m0 = 0; m0 < M->n; m0 += per) {
+        const int32_t m1 = std::min(M->n, m0 + per);
+        MSB_CUDA(cudaEventRecord(ctx->ev[0], ctx->stream));
+        MSB_TRY(launch_score0(ctx, M, S, strand, m0, m1, ctx->scores.as<double>()));
+        MSB_CUDA(cudaEventRecord(ctx->ev[1], ctx->stream));
+        MSB_CUDA(cudaMemcpyAsync(out + (size_t) m0 * S->n, ctx->scores.p, (size_t) (m1 - m0) * S->n * 8,
+                                 cudaMemcpyDeviceToHost, ctx->stream));
+        MSB_CUDA(cudaStreamSynchronize(ctx->stream));
+        total_ms += ev_ms(ctx->ev[0], ctx->ev[1]);
+    }
+    ctx->t[MSB_T_SCORE] = total_ms;
+    return MSB_OK;
+}
+
+int msb_score_select(msb_ctx *ctx, const msb_motifs *M, const msb_seqs *S, int strand, int32_t n_ranks,
+                     const int64_t *ranks, double *out) {
+    MSB_TRY(check_score_args(ctx, M, S, strand));
+    if (n_ranks < 0 || (n_ranks > 0 && (!ranks || !out))) { set_error("msb_score_select: bad ranks"); return MSB_EINVAL; }
+    for (int32_t k = 0; k < n_ranks; k++)
+        if (ranks[k] < 0 || ranks[k] >= S->n) { set_error("msb_score_select: rank out of range"); return MSB_EINVAL; }
+    if (M->n == 0 || n_ranks == 0) return MSB_OK;
+    MSB_CUDA(cudaSetDevice(ctx->device));
+    cudaStream_t st = ctx->stream;
+    const int64_t max_elems = (int64_t) 1 << 28;  // 2 GiB of doubles per slice, twice (in + sorted)
+    const int32_t per = (int32_t) std::max<int64_t>(1, std::min<int64_t>(M->n, max_elems / std::max<int64_t>(S->n, 1)));
+    MSB_TRY(ctx->scores.ensure((size_t) per * (size_t) S->n * 8));
+    MSB_TRY(ctx->scores_sorted.ensure((size_t) per * (size_t) S->n * 8));
+    MSB_TRY(ctx->seg_off.ensure((size_t) (per + 1) * 8));
+    MSB_TRY(ctx->ranks.ensure((size_t) n_ranks * 8));
+    MSB_TRY(ctx->sel.ensure((size_t) per * (size_t) n_ranks * 8));
+    std::vector<int64_t> seg((size_t) per + 1);
+    for (int32_t k = 0; k <= per; k++) seg[k] = (int64_t) k * S->n;
+    MSB_CUDA(cudaMemcpyAsync(ctx->seg_off.p, seg.data(), seg.size() * 8, cudaMemcpyHostToDevice, st));
+    MSB_CUDA(cudaMemcpyAsync(ctx->ranks.p, ranks, (size_t) n_ranks * 8, cudaMemcpyHostToDevice, st));
+    double score_ms = 0, select_ms = 0;
+    for (int32_t m0 = 0; m0 < M->n; m0 += per) {
+        const int32_t m1 = std::min(M->n, m0 + per), cnt = m1 - m0;
+        MSB_CUDA(cudaEventRecord(ctx->ev[0], st));
+        MSB_TRY(launch_score0(ctx, M, S, strand, m0, m1, ctx->scores.as<double>()));
+        MSB_CUDA(cudaEventRecord(ctx->ev[1], st));
+        size_t tmp_bytes = 0;
+        const int64_t total = (int64_t) cnt * S->n;
+        MSB_CUDA(cub::DeviceSegmentedRadixSort::SortKeysDescending(
+            nullptr, tmp_bytes, ctx->scores.as<double>(), ctx->scores_sorted.as<double>(), total, cnt,
+            ctx->seg_off.as<int64_t>(), ctx->seg_off.as<int64_t>() + 1, 0, 64, st));
+        MSB_TRY(ctx->sort_tmp.ensure(std::max<size_t>(tmp_bytes, 16)));
+        MSB_CUDA(cub::DeviceSegmentedRadixSort::SortKeysDescending(
+            ctx->sort_tmp.p, tmp_bytes, ctx->scores.as<double>(), ctx->scores_sorted.as<double>(), total, cnt,
+            ctx->seg_off.as<int64_t>(), ctx->seg_off.as<int64_t>() + 1, 0, 64, st));
+        gather_ranks_kernel<<<(cnt * n_ranks + 255) / 256, 256, 0, st>>>(
+            ctx->scores_sorted.as<double>(), S->n, cnt, ctx->ranks.as<int64_t>(), n_ranks, ctx->sel.as<double>());
+        MSB_CUDA(cudaGetLastError());
+        MSB_CUDA(cudaEventRecord(ctx->ev[2], st));
+        MSB_CUDA(cudaMemcpyAsync(out + (size_t) m0 * n_ranks, ctx->sel.p, (size_t) cnt * n_ranks * 8, cudaMemcpyDeviceToHost, st));
+        MSB_CUDA(cudaStreamSynchronize(st));
+        score_ms += ev_ms(ctx->ev[0], ctx->ev[1]);
+        select_ms += ev_ms(ctx->ev[1], ctx->ev[2]);
+    }
+    ctx->t[MSB_T_SCORE] = score_ms;
+    ctx->t[MSB_T_SELECT] = select_ms;
+    return MSB_OK;
+}
+
+// ---- one-shot mirrors --------------------------------------------------------------------------
+static std::mutex g_default_mu;
+static msb_ctx *g_default_ctx[64] = {};
+
+static int default_ctx(int device, msb_ctx **out) {
+    if (device < 0 || device >= 64) { set_error("device out of range"); return MSB_EINVAL; }
+    if (!g_default_ctx[device]) MSB_TRY(msb_ctx_create(device, nullptr, &g_default_ctx[device]));
+    *out = g_default_ctx[device];
+    return MSB_OK;
+}
+
+int msb_c_scan_motif(int device, int32_t n_motifs, const int32_t *lens, const double *mats,
+                     const int64_t *mat_off, const double *cutoffs, int64_t n_seqs, const char *seq_bytes,
+                     const int64_t *seq_off, int strand, msb_result **out) {
+    std::lock_guard<std::mutex> g(g_default_mu);
+    msb_ctx *ctx = nullptr;
+    MSB_TRY(default_ctx(device, &ctx));
+    msb_motifs *M = nullptr;
+    msb_seqs *S = nullptr;
+    int rc = msb_motifs_create(ctx, n_motifs, lens, mats, mat_off, cutoffs, &M);
+    if (rc == MSB_OK) rc = msb_seqs_from_ascii(ctx, n_seqs, seq_bytes, seq_off, &S);
+    if (rc == MSB_OK) rc = msb_scan(ctx, M, S, strand, out);
+    msb_seqs_destroy(S);
+    msb_motifs_destroy(M);
+    return rc;
+}
+
+int msb_c_score(int device, int32_t n_motifs, const int32_t *lens, const double *mats, const int64_t *mat_off,
+                int64_t n_seqs, const char *seq_bytes, const int64_t *seq_off, int strand, double *out) {
+    std::lock_guard<std::mutex> g(g_default_mu);
+    msb_ctx *ctx = nullptr;
+    MSB_TRY(default_ctx(device, &ctx));
+    msb_motifs *M = nullptr;
+    msb_seqs *S = nullptr;
+    int rc = msb_motifs_create(ctx, n_motifs, lens, mats, mat_off, nullptr, &M);
+    if (rc == MSB_OK) rc = msb_seqs_from_ascii(ctx, n_seqs, seq_bytes, seq_off, &S);
+    if (rc == MSB_OK) rc = msb_score(ctx, M, S, strand, out);
+    msb_seqs_destroy(S);
+    msb_motifs_destroy(M);
+    return rc;
+}
+
+}  // extern "C"

@@ -1,0 +1,218 @@
+"""Handle classes over the C ABI (include/msb200.h): Context, MotifSet, SequenceSet, ScanResult.
+
+These are the array-native entry points the host code (Scanner, cutoff builder, bench) uses; the
+list-of-lists mirrors of the reference's extension methods live in motifscan_b200/motif/cscore.py.
+"""
+import ctypes
+import threading
+
+import numpy as np
+
+from . import _lib
+from ._lib import check, ptr
+
+_default = {}
+_default_lock = threading.Lock()
+
+
+class Context:
+    """One device, one stream, reusable scratch (msb_ctx)."""
+
+    def __init__(self, device=0, stream=None):
+        self._lib = _lib.load()
+        self._h = ctypes.c_void_p()
+        check(self._lib.msb_ctx_create(int(device), ctypes.c_void_p(stream or 0), ctypes.byref(self._h)))
+        self.device = int(device)
+
+    def close(self):
+        if self._h:
+            self._lib.msb_ctx_destroy(self._h)
+            self._h = ctypes.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def sync(self):
+        check(self._lib.msb_ctx_sync(self._h))
+
+    def timings(self):
+        """Device milliseconds per phase of the last call (CUDA events on the context's stream)."""
+        a = np.zeros(len(_lib.T_NAMES), dtype=np.float64)
+        check(self._lib.msb_ctx_timings(self._h, ptr(a, ctypes.c_double), len(a)))
+        return dict(zip(_lib.T_NAMES, a.tolist()))
+
+    def counters(self):
+        a = np.zeros(len(_lib.C_NAMES), dtype=np.int64)
+        check(self._lib.msb_ctx_counters(self._h, ptr(a, ctypes.c_int64), len(a)))
+        return dict(zip(_lib.C_NAMES, a.tolist()))
+
+
+def default_context(device=0):
+    with _default_lock:
+        if device not in _default:
+            _default[device] = Context(device)
+        return _default[device]
+
+
+class MotifSet:
+    """Device-resident PWMs + cutoffs (msb_motifs)."""
+
+    def __init__(self, ctx, pwms, cutoffs=None):
+        self.ctx = ctx
+        self._lib = ctx._lib
+        lens, mats, mat_off = _lib.flatten_pwms(pwms)
+        self.lengths = lens
+        self.n = len(lens)
+        cut = None
+        if cutoffs is not None:
+            cut = np.ascontiguousarray(np.asarray(cutoffs, dtype=np.float64))
+            if cut.shape != (self.n,):
+                raise ValueError("cutoffs must have one entry per PWM")
+        self._h = ctypes.c_void_p()
+        check(self._lib.msb_motifs_create(ctx._h, self.n, ptr(lens, ctypes.c_int32), ptr(mats, ctypes.c_double),
+                                          ptr(mat_off, ctypes.c_int64),
+                                          ptr(cut, ctypes.c_double) if cut is not None else None,
+                                          ctypes.byref(self._h)))
+
+    def set_cutoffs(self, cutoffs):
+        cut = np.ascontiguousarray(np.asarray(cutoffs, dtype=np.float64))
+        if cut.shape != (self.n,):
+            raise ValueError("cutoffs must have one entry per PWM")
+        check(self._lib.msb_motifs_set_cutoffs(self._h, ptr(cut, ctypes.c_double)))
+
+    def max_raw(self):
+        out = np.zeros(max(self.n, 1), dtype=np.float64)
+        check(self._lib.msb_motifs_max_raw(self._h, ptr(out, ctypes.c_double)))
+        return out[:self.n]
+
+    def close(self):
+        if self._h:
+            self._lib.msb_motifs_destroy(self._h)
+            self._h = ctypes.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+class SequenceSet:
+    """Device-resident packed sequences (msb_seqs): 2-bit codes + N mask."""
+
+    def __init__(self, ctx, seqs=None, blob=None, seq_off=None):
+        self.ctx = ctx
+        self._lib = ctx._lib
+        if seqs is not None:
+            blob, seq_off = _lib.flatten_seqs(seqs)
+        blob = np.ascontiguousarray(blob, dtype=np.uint8) if not isinstance(blob, np.ndarray) else blob
+        seq_off = np.ascontiguousarray(seq_off, dtype=np.int64)
+        self.n = len(seq_off) - 1
+        self.total_bp = int(seq_off[-1])
+        self.seq_off = seq_off
+        self._h = ctypes.c_void_p()
+        data = blob.ctypes.data if blob.size else None
+        check(self._lib.msb_seqs_from_ascii(ctx._h, self.n, ctypes.c_void_p(data), ptr(seq_off, ctypes.c_int64),
+                                            ctypes.byref(self._h)))
+
+    def codes(self):
+        """Parity accessor: the reference's int8 codes (cscore.c:81-114) decoded from the device."""
+        out = np.empty(max(self.total_bp, 1), dtype=np.int8)
+        check(self._lib.msb_seqs_codes(self.ctx._h, self._h, ptr(out, ctypes.c_int8)))
+        return out[:self.total_bp]
+
+    def close(self):
+        if self._h:
+            self._lib.msb_seqs_destroy(self._h)
+            self._h = ctypes.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+class ScanResult:
+    """Sites of one scan in the reference's order (motif-major; sequence, start ascending;
+    forward before reverse).  Arrays are views into pinned memory owned by the result."""
+
+    def __init__(self, ctx, handle, n_motifs):
+        self.ctx = ctx
+        self._lib = ctx._lib
+        self._h = handle
+        n = ctypes.c_int64(0)
+        check(self._lib.msb_result_total(self._h, ctypes.byref(n)))
+        self.n_sites = n.value
+        self.counts = np.zeros(max(n_motifs, 1), dtype=np.int64)
+        check(self._lib.msb_result_counts(self._h, ptr(self.counts, ctypes.c_int64)))
+        self.counts = self.counts[:n_motifs]
+        self.offsets = np.zeros(n_motifs + 1, dtype=np.int64)
+        np.cumsum(self.counts, out=self.offsets[1:])
+        p_seq, p_start = _lib.c_i32p(), _lib.c_i32p()
+        p_score, p_strand = _lib.c_f64p(), _lib.c_i8p()
+        check(self._lib.msb_result_arrays(self._h, ctypes.byref(p_seq), ctypes.byref(p_start),
+                                          ctypes.byref(p_score), ctypes.byref(p_strand)))
+        if self.n_sites:
+            shape = (self.n_sites,)
+            self.seq_idx = np.ctypeslib.as_array(p_seq, shape=shape)
+            self.start = np.ctypeslib.as_array(p_start, shape=shape)
+            self.score = np.ctypeslib.as_array(p_score, shape=shape)
+            self.strand = np.ctypeslib.as_array(p_strand, shape=shape)
+        else:
+            self.seq_idx = np.zeros(0, dtype=np.int32)
+            self.start = np.zeros(0, dtype=np.int32)
+            self.score = np.zeros(0, dtype=np.float64)
+            self.strand = np.zeros(0, dtype=np.int8)
+
+    def detach(self):
+        """Copy the arrays out of the pinned block and release it."""
+        self.seq_idx = self.seq_idx.copy()
+        self.start = self.start.copy()
+        self.score = self.score.copy()
+        self.strand = self.strand.copy()
+        self.close()
+        return self
+
+    def close(self):
+        if self._h:
+            self._lib.msb_result_destroy(self._h)
+            self._h = ctypes.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+def scan(ctx, motifs, seqs, strand):
+    h = ctypes.c_void_p()
+    check(ctx._lib.msb_scan(ctx._h, motifs._h, seqs._h, int(strand), ctypes.byref(h)))
+    return ScanResult(ctx, h, motifs.n)
+
+
+def scan_device(ctx, motifs, seqs, strand):
+    """Kernels only (results stay on the device); returns the number of sites."""
+    n = ctypes.c_int64(0)
+    check(ctx._lib.msb_scan_device(ctx._h, motifs._h, seqs._h, int(strand), ctypes.byref(n)))
+    return n.value
+
+
+def score(ctx, motifs, seqs, strand):
+    out = np.empty((motifs.n, seqs.n), dtype=np.float64)
+    buf = out if out.size else np.zeros(1, dtype=np.float64)
+    check(ctx._lib.msb_score(ctx._h, motifs._h, seqs._h, int(strand), ptr(buf, ctypes.c_double)))
+    return out
+
+
+def score_select(ctx, motifs, seqs, strand, ranks):
+    ranks = np.ascontiguousarray(np.asarray(ranks, dtype=np.int64))
+    out = np.empty((motifs.n, len(ranks)), dtype=np.float64)
+    buf = out if out.size else np.zeros(1, dtype=np.float64)
+    check(ctx._lib.msb_score_select(ctx._h, motifs._h, seqs._h, int(strand), len(ranks),
+                                    ptr(ranks, ctypes.c_int64), ptr(buf, ctypes.c_double)))
+    return out

@@ -1,0 +1,298 @@
+"""GPU parity tests: the CUDA path (through the C ABI) against the oracle and the golden fixtures.
+
+Bar: bit-exact -- identical site lists (motif, sequence, start, strand, in order) and identical
+doubles for every score.  No tolerance anywhere in this file.
+"""
+import numpy as np
+import pytest
+
+import oracle
+
+pytestmark = pytest.mark.gpu
+
+KAT_M = [[[1.35, 0.21, -5.23], [0.07, -0.21, 0.6], [2.15, 2.22, -0.84], [-2.64, -1.89, 5.47]]]
+
+
+@pytest.fixture(scope="module")
+def cs():
+    from motifscan_b200.motif import cscore
+    return cscore
+
+
+@pytest.fixture(scope="module")
+def eng():
+    from motifscan_b200 import engine
+    return engine
+
+
+def synth_pwms(rng, n, lmin=6, lmax=30, bg=(0.295, 0.205, 0.205, 0.295)):
+    """Production-shaped PWMs: PFM -> PPM (pseudo 0.001) -> log-odds rounded to 5 dp."""
+    out = []
+    for _ in range(n):
+        L = int(rng.integers(lmin, lmax + 1))
+        depth = int(np.exp(rng.uniform(np.log(20), np.log(5000))))
+        pfm = np.round(depth * rng.dirichlet([0.3] * 4, size=L).T).astype(np.int64)
+        pfm[0, pfm.sum(axis=0) == 0] = 1
+        out.append(oracle.pfm_to_pwm(pfm, dict(zip("ACGT", bg))).tolist())
+    return out
+
+
+def synth_seqs(rng, n, lo, hi, p_n=0.0, p_lower=0.3, n_blocks=False):
+    alphabet = np.frombuffer(b"ACGT", dtype=np.uint8)
+    out = []
+    for _ in range(n):
+        L = int(rng.integers(lo, hi + 1))
+        s = alphabet[rng.choice(4, size=L, p=[0.295, 0.205, 0.205, 0.295])].copy()
+        low = rng.random(L) < p_lower
+        s[low] |= 0x20
+        if p_n > 0:
+            s[rng.random(L) < p_n] = ord("N")
+        if n_blocks and L > 200:
+            a = int(rng.integers(0, L - 100))
+            s[a:a + int(rng.integers(1, 100))] = ord("N")
+            s[:int(rng.integers(0, 40))] = ord("n")
+        out.append(bytes(s).decode())
+    return out
+
+
+def cutoffs_for(pwms, seqs, rate):
+    """Score cutoffs putting roughly `rate` of the windows above the cutoff (from the oracle's
+    offset-0 scores of random sub-windows; only a way to pick realistic thresholds)."""
+    rng = np.random.default_rng(1)
+    lmax = max(len(p[0]) for p in pwms)
+    pool = [s for s in seqs if len(s) >= lmax + 1]
+    samples = []
+    for _ in range(4000):
+        s = pool[int(rng.integers(len(pool)))]
+        a = int(rng.integers(0, len(s) - lmax + 1))
+        samples.append(s[a:a + lmax].upper().replace("N", "A"))
+    sc = oracle.score_arrays(pwms, samples, 3)
+    k = max(int(len(samples) * rate), 1)
+    return [float(np.sort(row)[::-1][k]) for row in sc]
+
+
+def assert_scan_equal(res, expect):
+    counts, seq_idx, start, score, strand = expect
+    assert np.array_equal(res.counts, counts)
+    assert np.array_equal(res.seq_idx, seq_idx.astype(np.int32))
+    assert np.array_equal(res.start, start.astype(np.int32))
+    assert np.array_equal(res.strand, strand)
+    # bit-exact doubles (also distinguishes -0.0 / 0.0 and NaN payloads)
+    assert np.array_equal(res.score.view(np.uint64), score.view(np.uint64))
+
+
+def test_kat_c_score(cs):
+    # reference tests/test_motif_score.py:6-20
+    seqs = ['NNN', 'AGT', 'ANT', 'CTA']
+    assert cs.c_score(KAT_M, seqs, 1, 1)[0] == pytest.approx(
+        [0.0, 0.9186991869918698, 0.693089430894309, -0.7164634146341464])
+    assert cs.c_score(KAT_M, seqs, 2, 1)[0] == pytest.approx(
+        [0.0, 0.6717479674796748, 0.693089430894309, -0.3323170731707317])
+    assert cs.c_score(KAT_M, seqs, 3, 1)[0] == pytest.approx(
+        [0.0, 0.9186991869918698, 0.693089430894309, -0.3323170731707317])
+
+
+def test_kat_c_scan_motif(cs):
+    # reference tests/test_motif_score.py:23-32
+    motif_sites = cs.c_scan_motif(KAT_M, [0.2], ['NNNAG', 'TANTCTA'], 3, 1)
+    assert len(motif_sites) == 1
+    assert len(motif_sites[0]) == 4
+    assert motif_sites[0][0] == pytest.approx([1, 1, 0.693089430894309, 1])
+    assert motif_sites[0][1] == pytest.approx([1, 1, 0.693089430894309, 2])
+    assert motif_sites[0][2] == pytest.approx([1, 2, 0.23983739837398374, 2])
+    assert motif_sites[0][3] == pytest.approx([1, 3, 0.266260162601626, 1])
+
+
+def test_golden_cases_bit_exact(cs, cscore_cases):
+    """Fixtures produced by the unmodified reference extension (tests/golden/make_golden.py)."""
+    for c in cscore_cases:
+        got = cs.c_scan_motif(c["pwms"], c["cutoffs"], c["seqs"], c["strand"], 1)
+        assert got == c["scan"], c["name"]
+        if c["score_seqs"]:
+            assert cs.c_score(c["pwms"], c["score_seqs"], c["strand"], 1) == c["score"], c["name"]
+
+
+def test_encoding_bit_exact(eng):
+    """2-bit + mask packing decodes to exactly the reference's int8 codes (cscore.c:81-114)."""
+    rng = np.random.default_rng(3)
+    every_byte = bytes(range(1, 128)).decode("ascii")
+    seqs = [every_byte, "", "A", "acgtn" * 13, "N" * 70] + synth_seqs(rng, 40, 0, 700, p_n=0.05, n_blocks=True)
+    seqs.append("ACGTé中acgt")  # multi-byte UTF-8: every byte of it is "N" (cscore.c:83)
+    ctx = eng.default_context(0)
+    sset = eng.SequenceSet(ctx, seqs)
+    blob = "".join(seqs).encode("utf-8")
+    assert np.array_equal(sset.codes(), oracle.encode(blob))
+    sset.close()
+
+
+@pytest.mark.parametrize("strand", [1, 2, 3])
+def test_random_production_shape(eng, strand):
+    rng = np.random.default_rng(100 + strand)
+    pwms = synth_pwms(rng, 60)
+    seqs = synth_seqs(rng, 300, 900, 1100)
+    cutoffs = cutoffs_for(pwms, seqs, 2e-3)
+    ctx = eng.default_context(0)
+    motifs = eng.MotifSet(ctx, pwms, cutoffs)
+    sset = eng.SequenceSet(ctx, seqs)
+    res = eng.scan(ctx, motifs, sset, strand)
+    assert_scan_equal(res, oracle.scan_arrays(pwms, cutoffs, seqs, strand, n_threads=8))
+    assert res.n_sites > 100
+    res.close(), sset.close(), motifs.close()
+
+
+def test_n_blocks_lowercase_and_ragged(eng):
+    rng = np.random.default_rng(7)
+    pwms = synth_pwms(rng, 40, lmin=1, lmax=32)
+    seqs = synth_seqs(rng, 120, 0, 1500, p_n=0.01, n_blocks=True)
+    seqs += ["", "A", "N", "ACGTACGTAC", "n" * 100, "NNNNNNNNNNNNNNNNNNNNNNNNNNNNNNNNNNNNACGTACGTTTGACCA"]
+    cutoffs = cutoffs_for(pwms, seqs, 5e-3)
+    ctx = eng.default_context(0)
+    motifs = eng.MotifSet(ctx, pwms, cutoffs)
+    sset = eng.SequenceSet(ctx, seqs)
+    for strand in (3, 1, 2):
+        res = eng.scan(ctx, motifs, sset, strand)
+        assert_scan_equal(res, oracle.scan_arrays(pwms, cutoffs, seqs, strand, n_threads=8))
+        res.close()
+    sset.close(), motifs.close()
+
+
+def test_zero_score_windows_hit_when_cutoff_allows(eng):
+    """All-N windows score exactly 0 and are sites when cutoff <= 1e-10 (cscore.c:358)."""
+    rng = np.random.default_rng(8)
+    pwms = synth_pwms(rng, 5, lmin=4, lmax=12)
+    seqs = ["N" * 80, "ACGT" * 10 + "N" * 50 + "ACGT" * 10, "n" * 33]
+    cutoffs = [0.0, 1e-10, 1e-9, -0.5, 0.7]
+    ctx = eng.default_context(0)
+    motifs = eng.MotifSet(ctx, pwms, cutoffs)
+    sset = eng.SequenceSet(ctx, seqs)
+    res = eng.scan(ctx, motifs, sset, 3)
+    assert_scan_equal(res, oracle.scan_arrays(pwms, cutoffs, seqs, 3))
+    assert res.counts[0] > 100
+    res.close(), sset.close(), motifs.close()
+
+
+def test_many_motifs_multiple_batches(eng):
+    """More motifs than fit one shared-memory batch (tables > 227 KB)."""
+    rng = np.random.default_rng(11)
+    pwms = synth_pwms(rng, 900, lmin=6, lmax=30)
+    seqs = synth_seqs(rng, 24, 400, 600)
+    cutoffs = cutoffs_for(pwms, seqs, 1e-3)
+    ctx = eng.default_context(0)
+    motifs = eng.MotifSet(ctx, pwms, cutoffs)
+    sset = eng.SequenceSet(ctx, seqs)
+    res = eng.scan(ctx, motifs, sset, 3)
+    assert ctx.counters()["prefilter_launches"] >= 2
+    assert_scan_equal(res, oracle.scan_arrays(pwms, cutoffs, seqs, 3, n_threads=8))
+    res.close(), sset.close(), motifs.close()
+
+
+def test_arbitrary_float_int_and_degenerate_pwms(eng):
+    rng = np.random.default_rng(12)
+    pwms = [rng.normal(0, 2, size=(4, int(rng.integers(1, 33)))).tolist() for _ in range(20)]
+    pwms += [rng.integers(-3, 4, size=(4, int(rng.integers(2, 10)))).astype(float).tolist() for _ in range(10)]
+    pwms.append((-np.abs(rng.normal(0, 1, size=(4, 7))) - 0.1).tolist())  # max_raw == 0: never a site
+    pwms.append(np.zeros((4, 5)).tolist())                                   # 0/0 = NaN: never a site
+    pwms.append(np.full((4, 6), 2.5).tolist())                               # constant: every window 1.0
+    pwms.append(rng.normal(0, 2, size=(4, 45)).tolist())                     # L > 32: exact path
+    pwms.append(rng.normal(0, 2, size=(4, 33)).tolist())
+    seqs = synth_seqs(rng, 30, 0, 400, p_n=0.02, n_blocks=True)
+    cutoffs = [float(rng.uniform(0.1, 0.7)) for _ in pwms]
+    cutoffs[3] = float("nan")
+    cutoffs[4] = float("inf")
+    cutoffs[5] = float("-inf")
+    cutoffs[6] = -2.0   # everything is a site
+    cutoffs[7] = 5.0    # nothing is
+    ctx = eng.default_context(0)
+    motifs = eng.MotifSet(ctx, pwms, cutoffs)
+    sset = eng.SequenceSet(ctx, seqs)
+    for strand in (3, 1, 2):
+        res = eng.scan(ctx, motifs, sset, strand)
+        assert_scan_equal(res, oracle.scan_arrays(pwms, cutoffs, seqs, strand, n_threads=8))
+        res.close()
+    sset.close(), motifs.close()
+
+
+def test_dense_hits_overflow_retry(eng):
+    """Cutoffs so low that candidates overflow the first buffers: results must not change."""
+    rng = np.random.default_rng(13)
+    pwms = synth_pwms(rng, 30, lmin=6, lmax=12)
+    seqs = synth_seqs(rng, 100, 1900, 2100)
+    cutoffs = [-5.0] * len(pwms)
+    ctx = eng.Context(0)  # fresh context: scratch starts at its minimum size
+    motifs = eng.MotifSet(ctx, pwms, cutoffs)
+    sset = eng.SequenceSet(ctx, seqs)
+    res = eng.scan(ctx, motifs, sset, 3)
+    assert ctx.counters()["retries"] >= 1
+    assert_scan_equal(res, oracle.scan_arrays(pwms, cutoffs, seqs, 3, n_threads=8))
+    res.close(), sset.close(), motifs.close(), ctx.close()
+
+
+def test_set_cutoffs_rebuilds_tables(eng):
+    rng = np.random.default_rng(14)
+    pwms = synth_pwms(rng, 12)
+    seqs = synth_seqs(rng, 50, 500, 600)
+    ctx = eng.default_context(0)
+    motifs = eng.MotifSet(ctx, pwms, [0.9] * 12)
+    sset = eng.SequenceSet(ctx, seqs)
+    for cut in (0.9, 0.6, 0.75):
+        motifs.set_cutoffs([cut] * 12)
+        res = eng.scan(ctx, motifs, sset, 3)
+        assert_scan_equal(res, oracle.scan_arrays(pwms, [cut] * 12, seqs, 3, n_threads=8))
+        res.close()
+    sset.close(), motifs.close()
+
+
+def test_prefilter_w8_same_sites(eng):
+    """The 8-windows-per-thread prefilter variant yields the same sites."""
+    from motifscan_b200 import _lib
+    rng = np.random.default_rng(15)
+    pwms = synth_pwms(rng, 50)
+    seqs = synth_seqs(rng, 100, 900, 1100, p_n=0.001)
+    cutoffs = cutoffs_for(pwms, seqs, 2e-3)
+    ctx = eng.default_context(0)
+    motifs = eng.MotifSet(ctx, pwms, cutoffs)
+    sset = eng.SequenceSet(ctx, seqs)
+    expect = oracle.scan_arrays(pwms, cutoffs, seqs, 3, n_threads=8)
+    try:
+        _lib.check(_lib.load().msb_set_option(b"prefilter_w", 8))
+        res = eng.scan(ctx, motifs, sset, 3)
+        assert_scan_equal(res, expect)
+        res.close()
+    finally:
+        _lib.check(_lib.load().msb_set_option(b"prefilter_w", 4))
+    sset.close(), motifs.close()
+
+
+def test_score_matches_oracle_bit_exact(eng):
+    rng = np.random.default_rng(16)
+    pwms = synth_pwms(rng, 70, lmin=1, lmax=30)
+    pwms.append(rng.normal(0, 2, size=(4, 40)).tolist())
+    seqs = synth_seqs(rng, 3000, 40, 60, p_n=0.01)
+    ctx = eng.default_context(0)
+    motifs = eng.MotifSet(ctx, pwms)
+    sset = eng.SequenceSet(ctx, seqs)
+    for strand in (1, 2, 3):
+        got = eng.score(ctx, motifs, sset, strand)
+        want = oracle.score_arrays(pwms, seqs, strand)
+        assert np.array_equal(got.view(np.uint64), want.view(np.uint64))
+    with pytest.raises(ValueError):
+        short = eng.SequenceSet(ctx, ["ACGTACGT"])
+        eng.score(ctx, motifs, short, 3)
+    sset.close(), motifs.close()
+
+
+def test_score_select_matches_sorted_order_statistics(eng):
+    """Fused score + order statistics == sorting the oracle's scores (motif/__init__.py:396-399)."""
+    rng = np.random.default_rng(17)
+    pwms = synth_pwms(rng, 25)
+    seqs = synth_seqs(rng, 20000, 30, 30)
+    n = len(seqs)
+    ranks = [int(n * 0.1 ** e) - 1 for e in range(2, min(len(str(n)), 7))]
+    ctx = eng.default_context(0)
+    motifs = eng.MotifSet(ctx, pwms)
+    sset = eng.SequenceSet(ctx, seqs)
+    got = eng.score_select(ctx, motifs, sset, 3, ranks)
+    want = oracle.score_arrays(pwms, seqs, 3)
+    want = np.sort(want, axis=1)[:, ::-1][:, ranks]
+    assert np.array_equal(got.view(np.uint64), np.ascontiguousarray(want).view(np.uint64))
+    sset.close(), motifs.close()
