@@ -1,0 +1,451 @@
+#!/usr/bin/env python3
+"""bench.py -- throughput of the motif-scan hot path on B200, next to the reference CPU path.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W]            our arm (CUDA, C ABI)
+    python bench.py --impl reference [--gpus N] [--steps K] ...    the reference's CPU extension
+
+Metric (BASELINE.json): motif*bp scored per second, both strands.  Workload at every N:
+BASELINE.json configs[1] per GPU -- a JASPAR-2020-vertebrates-shaped set of 750 PWMs (length
+6-30) against 50,000 synthetic 1 kb peaks, cutoffs at p = 1e-4 -- so N GPUs scan N x 50,000 peaks
+(weak scaling; regions are sharded, there is no collective on the data path).
+
+One "step" = one pass of the hot path over the rank's batch of peaks:
+  value  inputs (packed 2-bit sequence + N mask, motif tables) already resident in HBM;
+         prefilter + exact fp64 re-score + ordering, timed with CUDA events on the launch stream.
+  e2e    the same through the C-ABI calls a binding makes, from HOST buffers: H2D of the ASCII
+         bytes from pinned memory, encode/pack, scan, D2H of the sites (msb_seqs_from_ascii +
+         msb_scan).
+Prints ONE JSON line on rank 0.
+"""
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import tempfile
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+METRIC = "motif_bp_scored_per_sec_both_strands"
+UNIT = "motif*bp/s"
+N_MOTIFS = 750
+N_REGIONS = 50000
+REGION_BP = 1000
+P_VALUE = "1e-4"
+N_BACKGROUND = 100000
+
+
+def workload_name():
+    return (f"configs[1]: {N_MOTIFS} JASPAR-2020-vertebrates-shaped PWMs (len 6-30) x {N_REGIONS} "
+            f"synthetic {REGION_BP} bp peaks per GPU, both strands, cutoffs p={P_VALUE}")
+
+
+def load_peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        with open(path) as fh:
+            return json.load(fh), "measured (MEASURED_PEAKS.json)"
+    return {"hbm_gbs": 6650.0, "sm_max_mhz": 1965.0}, "fallback (B200_PROFILING.md)"
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled every 200 ms during the timed region."""
+    FIELDS = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+              "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+              "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index = index
+        self.proc = None
+        self.path = None
+
+    def start(self):
+        try:
+            fd, self.path = tempfile.mkstemp(suffix=".csv")
+            os.close(fd)
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.FIELDS}",
+                 "--format=csv,noheader,nounits", "-lms", "200"],
+                stdout=open(self.path, "w"), stderr=subprocess.DEVNULL)
+        except Exception:
+            self.proc = None
+
+    def stop(self):
+        out = {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
+        if self.proc is None:
+            return out
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        names = ("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap")
+        try:
+            for line in open(self.path):
+                parts = [p.strip() for p in line.split(",")]
+                if len(parts) < 7:
+                    continue
+                try:
+                    sm.append(float(parts[0]))
+                    mx.append(float(parts[1]))
+                except ValueError:
+                    continue
+                for name, flag in zip(names, parts[3:7]):
+                    if flag.lower().startswith("active"):
+                        reasons.add(name)
+            os.unlink(self.path)
+        except Exception:
+            pass
+        if sm:
+            out.update(sm_mhz=statistics.median(sm), sm_max_mhz=max(mx), reasons=sorted(reasons),
+                       samples=len(sm))
+        return out
+
+
+def algorithmic_adds(pwm_lens, seq_lens_hist):
+    """OPS = 2 * sum_seqs sum_m max(len_i - L_m + 1, 0) * L_m -- one add
+    per PWM column per strand per window, the reference's inner loop (cscore.c:344-354)."""
+    total = 0
+    for length, count in seq_lens_hist.items():
+        w = np.maximum(length - pwm_lens + 1, 0)
+        total += 2 * int((w * pwm_lens).sum()) * count
+    return total
+
+
+def make_workload(rank):
+    from motifscan_b200 import synth
+    _, pwms, _ = synth.motif_set(N_MOTIFS, seed=2020)
+    blob, seq_off = synth.peak_set(N_REGIONS, REGION_BP, seed=50 + rank)
+    return pwms, blob, seq_off
+
+
+def build_cutoffs(engine, ctx, motifs, lmax):
+    """motif --build arithmetic (cli/motif.py:129-153) on the device: background samples of the
+    longest motif's length, strand 3, order statistic int(n * 1e-4) - 1, rounded to 8 decimals."""
+    from motifscan_b200 import synth
+    blob, off = synth.background_samples(N_BACKGROUND, lmax, seed=1)
+    bg = engine.SequenceSet(ctx, blob=blob, seq_off=off)
+    rank = int(N_BACKGROUND * 0.1 ** 4) - 1
+    cut = engine.score_select(ctx, motifs, bg, 3, [rank])[:, 0]
+    bg.close()
+    return np.around(cut, 8)
+
+
+# ------------------------------------------------------------------------------------------------
+# CPU side: the reference's own extension (oracle/_ref) or, if it never compiled, the oracle port.
+# ------------------------------------------------------------------------------------------------
+def cpu_scanner():
+    import oracle
+    ref = oracle.load_reference_cscore()
+    if ref is not None:
+        return "reference", ref.c_scan_motif
+    return "port", oracle.c_scan_motif
+
+
+def cpu_time_sample(fn, matrices, cutoffs, seqs, n_threads):
+    t0 = time.perf_counter()
+    sites = fn(matrices, cutoffs, seqs, 3, n_threads)
+    return time.perf_counter() - t0, sites
+
+
+def cpu_pick_sample(fn, matrices, cutoffs, all_seqs, n_threads, target_s):
+    """Choose how many sequences (all motifs) give about `target_s` seconds of CPU work:
+    a tiny probe, then a ~2 s probe (thread start-up dominates the tiny one)."""
+    n = max(8, n_threads // 4)
+    for goal in (2.0, target_s):
+        probe = all_seqs[:n]
+        dt, _ = cpu_time_sample(fn, matrices, cutoffs, probe, n_threads)
+        rate = len(probe) / max(dt, 1e-6)
+        n = int(min(len(all_seqs), max(len(probe), rate * goal)))
+    return n
+
+
+def blob_to_strs(blob, seq_off, n):
+    raw = blob.tobytes() if isinstance(blob, np.ndarray) else bytes(blob)
+    return [raw[seq_off[i]:seq_off[i + 1]].decode("ascii") for i in range(n)]
+
+
+def run_reference(args, rank, world):
+    if rank != 0:
+        return 0
+    pwms, blob, seq_off = make_workload(0)
+    kind, fn = cpu_scanner()
+    n_threads = os.cpu_count() or 1
+    matrices = [p.tolist() for p in pwms]
+    # cutoffs: the same rule as our arm, computed on the CPU by sorting oracle scores is far too
+    # slow at 750 x 1e5; the benchmark's hit rate only needs realistic thresholds, so reuse the
+    # cached device-built cutoffs when the GPU arm left them, else derive them from a sample.
+    cutoffs = reference_cutoffs(pwms)
+    budget_s = 150.0
+    per_step = max(budget_s / (args.steps + args.warmup), 2.0)
+    all_seqs = blob_to_strs(blob, seq_off, min(N_REGIONS, 20000))
+    n = cpu_pick_sample(fn, matrices, cutoffs, all_seqs, n_threads, per_step)
+    seqs = all_seqs[:n]
+    units = N_MOTIFS * sum(len(s) for s in seqs)
+    for _ in range(args.warmup):
+        cpu_time_sample(fn, matrices, cutoffs, seqs, n_threads)
+    times = []
+    for _ in range(args.steps):
+        dt, sites = cpu_time_sample(fn, matrices, cutoffs, seqs, n_threads)
+        times.append(dt)
+    ms = 1e3 * sum(times) / len(times)
+    value = units / (ms / 1e3)
+    sample = f"first {n} of {N_REGIONS} peaks x all {N_MOTIFS} motifs per step"
+    line = {
+        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": {"workload": workload_name(), "sample": sample, "n_threads": n_threads},
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": n_threads, "kind": kind, "sample": sample},
+        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line))
+    return 0
+
+
+def reference_cutoffs(pwms):
+    """p = 1e-4 cutoffs for the CPU arm without a GPU: per motif, the order statistic of the
+    oracle's scores over 20,000 background samples (rank int(n * 1e-4) - 1 = 1)."""
+    import oracle
+    from motifscan_b200 import synth
+    lmax = max(p.shape[1] for p in pwms)
+    n = 20000
+    blob, off = synth.background_samples(n, lmax, seed=1)
+    raw = blob.tobytes()
+    seqs = [raw[off[i]:off[i + 1]].decode("ascii") for i in range(n)]
+    sc = oracle.score_arrays([p.tolist() for p in pwms], seqs, 3)
+    rank = int(n * 0.1 ** 4) - 1
+    return np.around(-np.sort(-sc, axis=1)[:, rank], 8).tolist()
+
+
+# ------------------------------------------------------------------------------------------------
+def compare_sites(res, ref_sites, n_seq_sample):
+    """GPU result restricted to the first n sequences vs the CPU extension's per-motif lists."""
+    off = res.offsets
+    mismatches = 0
+    total = 0
+    for m, lst in enumerate(ref_sites):
+        a, b = off[m], off[m + 1]
+        keep = res.seq_idx[a:b] < n_seq_sample
+        g_seq, g_start = res.seq_idx[a:b][keep], res.start[a:b][keep]
+        g_score, g_strand = res.score[a:b][keep], res.strand[a:b][keep]
+        total += len(lst)
+        if len(lst) != len(g_seq):
+            mismatches += 1
+            continue
+        if lst:
+            arr = np.array(lst, dtype=np.float64)
+            ok = (np.array_equal(arr[:, 0].astype(np.int64), g_seq) and np.array_equal(arr[:, 1].astype(np.int64), g_start)
+                  and np.array_equal(arr[:, 3].astype(np.int64), g_strand)
+                  and np.array_equal(arr[:, 2].view(np.uint64), np.ascontiguousarray(g_score).view(np.uint64)))
+            mismatches += 0 if ok else 1
+    return total, mismatches
+
+
+def run_ours(args, rank, local_rank, world):
+    import ctypes
+    import torch
+    from motifscan_b200 import _lib, engine
+
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device -- the scan path has no CPU fallback")
+    torch.cuda.set_device(local_rank)
+    dist = None
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+
+    def barrier():
+        torch.cuda.synchronize()
+        if dist is not None:
+            dist.barrier()
+
+    stream = torch.cuda.Stream()
+    ctx = engine.Context(local_rank, stream=stream.cuda_stream)
+    lib = _lib.load()
+
+    pwms, blob, seq_off = make_workload(rank)
+    pwm_lens = np.array([p.shape[1] for p in pwms], dtype=np.int64)
+    motifs = engine.MotifSet(ctx, pwms)
+    cutoffs = build_cutoffs(engine, ctx, motifs, int(pwm_lens.max()))
+    motifs.set_cutoffs(cutoffs)
+
+    # pinned host copy of the ASCII input (the e2e leg copies from it every step)
+    pinned = ctypes.c_void_p()
+    _lib.check(lib.msb_pinned_alloc(int(blob.size), ctypes.byref(pinned)))
+    host_blob = np.ctypeslib.as_array(ctypes.cast(pinned, ctypes.POINTER(ctypes.c_uint8)), shape=(blob.size,))
+    host_blob[:] = blob
+
+    units = int(N_MOTIFS) * int(seq_off[-1])             # motif*bp per step per rank
+    adds = algorithmic_adds(pwm_lens, {REGION_BP: N_REGIONS})
+    resident = engine.SequenceSet(ctx, blob=host_blob, seq_off=seq_off)
+    flush = torch.empty(512 << 20, dtype=torch.uint8, device="cuda")
+
+    def flush_l2():
+        with torch.cuda.stream(stream):
+            flush.fill_(1)
+
+    # ---- device-resident leg ---------------------------------------------------------------------
+    n_sites = 0
+    for _ in range(args.warmup):
+        n_sites = engine.scan_device(ctx, motifs, resident, 3)
+    sampler = ClockSampler(local_rank)
+    step_ms, phase = [], {"prefilter": [], "exact": [], "order": []}
+    launches = 0
+    barrier()
+    sampler.start()
+    t_wall0 = time.perf_counter()
+    for _ in range(args.steps):
+        flush_l2()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(stream)
+        n_sites = engine.scan_device(ctx, motifs, resident, 3)
+        e1.record(stream)
+        e1.synchronize()
+        step_ms.append(e0.elapsed_time(e1))
+        t = ctx.timings()
+        for k in phase:
+            phase[k].append(t[k])
+        launches += ctx.counters()["launches"]
+    barrier()
+    wall_ms = 1e3 * (time.perf_counter() - t_wall0) / args.steps
+    counters = ctx.counters()
+    ms_per_step = sum(step_ms) / len(step_ms)
+
+    # ---- end-to-end leg: host buffers in, host arrays out ---------------------------------------
+    e2e_steps = max(1, min(args.steps, 5))
+    res = None
+    for _ in range(min(args.warmup, 2)):
+        s = engine.SequenceSet(ctx, blob=host_blob, seq_off=seq_off)
+        res = engine.scan(ctx, motifs, s, 3)
+        res.close(), s.close()
+    barrier()
+    e2e_ms = []
+    h2d_bytes = int(blob.size + seq_off.nbytes * 2 + 4 * N_REGIONS)
+    d2h_bytes = 0
+    for k in range(e2e_steps):
+        flush_l2()
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        s = engine.SequenceSet(ctx, blob=host_blob, seq_off=seq_off)
+        res = engine.scan(ctx, motifs, s, 3)
+        total_sites = int(res.counts.sum())  # the result is on the host here
+        e2e_ms.append(1e3 * (time.perf_counter() - t0))
+        d2h_bytes = 17 * total_sites + 8 * N_MOTIFS
+        s.close()
+        if k + 1 < e2e_steps:
+            res.close()
+    clocks = sampler.stop()
+    barrier()
+    e2e_ms_step = sum(e2e_ms) / len(e2e_ms)
+
+    # ---- reduce over ranks: the slowest rank defines the step ------------------------------------
+    if dist is not None:
+        tt = torch.tensor([ms_per_step, e2e_ms_step, wall_ms], device="cuda", dtype=torch.float64)
+        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+        ms_per_step, e2e_ms_step, wall_ms = tt.tolist()
+        ll = torch.tensor([launches, n_sites], device="cuda", dtype=torch.int64)
+        dist.all_reduce(ll, op=dist.ReduceOp.SUM)
+        launches, n_sites_all = ll.tolist()
+    else:
+        n_sites_all = n_sites
+
+    if rank == 0:
+        peaks, peaks_src = load_peaks()
+        pre_ms = sum(phase["prefilter"]) / len(phase["prefilter"])
+        n_pre = max(counters["prefilter_launches"], 1)
+        sm_count = torch.cuda.get_device_properties(local_rank).multi_processor_count
+        issue_peak = sm_count * 128 * peaks.get("sm_max_mhz", 1965.0) * 1e6 / 1e12   # T adds/s
+        achieved = adds / (pre_ms / 1e3) / 1e12
+        seq_bytes = 0.375 * float(seq_off[-1]) * n_pre      # 2-bit codes + 1-bit mask, read once per batch launch
+        hit_bytes = 8.0 * counters["candidates"]
+        traffic = None
+        tpath = os.path.join(ROOT, "profiles", "prefilter_traffic.json")
+        if os.path.exists(tpath):
+            try:
+                traffic = json.load(open(tpath)).get("dram_bytes_per_launch")
+            except Exception:
+                traffic = None
+        roofline = {
+            "bound": "issue", "kernel": "prefilter_kernel<4>",
+            "achieved": achieved, "peak": issue_peak, "unit": "Tadd/s", "frac": achieved / issue_peak,
+            "peak_source": f"{sm_count} SMs x 128 lanes x sm_max_mhz from {peaks_src}",
+            "algorithmic_adds_per_launch": adds / n_pre, "launches_per_step": n_pre,
+            "launch_ms": pre_ms / n_pre, "traffic": traffic,
+            "hbm": {"algorithmic_bytes_per_step": seq_bytes + hit_bytes,
+                    "achieved_gbs": (seq_bytes + hit_bytes) / (pre_ms / 1e3) / 1e9,
+                    "peak_gbs": peaks.get("hbm_gbs"), "note": "not the binding resource"},
+        }
+        cpu = None
+        if world == 1 and not args.no_cpu:
+            kind, fn = cpu_scanner()
+            n_threads = os.cpu_count() or 1
+            matrices = [p.tolist() for p in pwms]
+            all_seqs = blob_to_strs(blob, seq_off, min(N_REGIONS, 20000))
+            n = cpu_pick_sample(fn, matrices, cutoffs.tolist(), all_seqs, n_threads, 15.0)
+            dt, ref_sites = cpu_time_sample(fn, matrices, cutoffs.tolist(), all_seqs[:n], n_threads)
+            total, bad = compare_sites(res, ref_sites, n)
+            cpu = {"value": N_MOTIFS * n * REGION_BP / dt, "unit": UNIT, "cores": n_threads, "kind": kind,
+                   "sample": f"first {n} of {N_REGIONS} peaks x all {N_MOTIFS} motifs, {dt:.1f} s",
+                   "parity": {"sites_compared": total, "motifs_with_any_difference": bad,
+                              "bar": "identical (seq, start, strand) lists and bit-identical scores"}}
+        line = {
+            "metric": METRIC, "value": world * units / (ms_per_step / 1e3), "unit": UNIT, "n_gpus": world,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_per_step,
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "i16x2 prefilter + f64 exact", "data": "synthetic",
+            "config": {"workload": workload_name(), "n_motifs": N_MOTIFS, "n_regions_per_gpu": N_REGIONS,
+                       "region_bp": REGION_BP, "strand": "both", "p_value": P_VALUE,
+                       "l2": "flushed between timed steps (512 MiB device write)",
+                       "parallelism": f"regions sharded over {world} GPU(s), no collective"},
+            "phase_ms": {k: sum(v) / len(v) for k, v in phase.items()},
+            "wall_ms_per_step": wall_ms,
+            "sites_per_step": int(n_sites_all), "candidates_per_step_rank0": counters["candidates"],
+            "e2e": {"value": world * units / (e2e_ms_step / 1e3), "unit": UNIT, "ms_per_step": e2e_ms_step,
+                    "steps": e2e_steps, "h2d_bytes_per_step": h2d_bytes, "d2h_bytes_per_step": d2h_bytes},
+            "gpu_launches": int(launches),
+            "gpu_launches_note": "own kernels; the CUB radix sort of the sites is counted as one launch",
+            "roofline": roofline, "clocks": clocks,
+        }
+        if cpu is not None:
+            line["cpu_baseline"] = cpu
+        print(json.dumps(line))
+    if res is not None:
+        res.close()
+    resident.close()
+    motifs.close()
+    lib.msb_pinned_free(pinned)
+    if dist is not None:
+        dist.barrier()
+        dist.destroy_process_group()
+    return 0
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    if args.impl == "reference":
+        return run_reference(args, rank, world)
+    return run_ours(args, rank, local_rank, world)
+
+
+if __name__ == "__main__":
+    sys.exit(main())
