@@ -98,9 +98,16 @@ int msb_seqs_destroy(msb_seqs *seqs);
  * doubles bit for bit; the hit predicate is score - cutoff >= -1e-10. */
 int msb_scan(msb_ctx *ctx, const msb_motifs *motifs, const msb_seqs *seqs, int strand,
              msb_result **out);
+/* The same with flags.  MSB_SCAN_DEDUP additionally applies the reference's adjacent-site
+ * de-duplication (deduplicate_motif_sites, scanner.py:156-193) on the device: per (motif,
+ * sequence) and per strand, a site closer than the motif length to the previous survivor
+ * replaces it only if it scores strictly higher. */
+#define MSB_SCAN_DEDUP 1
+int msb_scan_ex(msb_ctx *ctx, const msb_motifs *motifs, const msb_seqs *seqs, int strand,
+                int flags, msb_result **out);
 /* Device-only variant for measurement: same kernels, results left on the device, no D2H. */
 int msb_scan_device(msb_ctx *ctx, const msb_motifs *motifs, const msb_seqs *seqs, int strand,
-                    int64_t *n_sites);
+                    int flags, int64_t *n_sites);
 int msb_result_total(const msb_result *res, int64_t *n_sites);
 int msb_result_counts(const msb_result *res, int64_t *counts /* n_motifs */);
 /* Borrowed pointers into the result (valid until msb_result_destroy): n_sites entries each. */

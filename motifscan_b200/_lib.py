@@ -12,6 +12,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libmsb200.so")
 
 MSB_OK, MSB_EINVAL, MSB_ENOMEM, MSB_ECUDA, MSB_ESHORT = 0, -1, -2, -3, -4
+MSB_SCAN_DEDUP = 1
 T_NAMES = ("h2d", "encode", "prefilter", "exact", "order", "d2h", "score", "select")
 C_NAMES = ("candidates", "dirty", "hits", "launches", "retries", "prefilter_launches")
 
@@ -45,7 +46,8 @@ SIGNATURES = {
     "msb_seqs_codes": (ctypes.c_int, [c_vp, c_vp, c_i8p]),
     "msb_seqs_destroy": (ctypes.c_int, [c_vp]),
     "msb_scan": (ctypes.c_int, [c_vp, c_vp, c_vp, ctypes.c_int, ctypes.POINTER(c_vp)]),
-    "msb_scan_device": (ctypes.c_int, [c_vp, c_vp, c_vp, ctypes.c_int, c_i64p]),
+    "msb_scan_ex": (ctypes.c_int, [c_vp, c_vp, c_vp, ctypes.c_int, ctypes.c_int, ctypes.POINTER(c_vp)]),
+    "msb_scan_device": (ctypes.c_int, [c_vp, c_vp, c_vp, ctypes.c_int, ctypes.c_int, c_i64p]),
     "msb_result_total": (ctypes.c_int, [c_vp, c_i64p]),
     "msb_result_counts": (ctypes.c_int, [c_vp, c_i64p]),
     "msb_result_arrays": (ctypes.c_int, [c_vp, ctypes.POINTER(c_i32p), ctypes.POINTER(c_i32p),

@@ -7,7 +7,8 @@
 //                           order + the reference's hit predicate       (cscore.c:344-389)
 //   exact_dirty_kernel      the same for windows that touch a non-ACGT base
 //   exact_slow_kernel       the same for motifs the table path cannot take (L > 32, non-finite)
-//   decode_sites_kernel     sorted keys -> (seq_idx, start, strand) + per-motif counts
+//   decode_sites_kernel     sorted keys -> (seq_idx, start, strand); motif_offsets_kernel: CSR
+//   dedup_flags_kernel      adjacent-site de-duplication              (scanner.py:156-193)
 //   score0_kernel           offset-0 window score of every sequence     (cscore.c:191-223)
 #pragma once
 #include "common.cuh"
@@ -317,7 +318,7 @@ exact_positions_kernel(ExactParams E, const int64_t *__restrict__ pos, int64_t n
 __global__ void __launch_bounds__(256)
 decode_sites_kernel(SeqView S, const uint64_t *__restrict__ key, int64_t n,
                     int32_t *__restrict__ seq_idx, int32_t *__restrict__ start,
-                    int8_t *__restrict__ strand, unsigned long long *__restrict__ counts) {
+                    int8_t *__restrict__ strand) {
     int64_t i = (int64_t) blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
     const uint64_t k = key[i];
@@ -326,7 +327,73 @@ decode_sites_kernel(SeqView S, const uint64_t *__restrict__ key, int64_t n,
     seq_idx[i] = (int32_t) s;
     start[i] = (int32_t) (p - __ldg(S.poff + s));
     strand[i] = (int8_t) (key_rev(k) + 1);  // 1 forward, 2 reverse (cscore.c:359,376)
-    atomicAdd(counts + key_motif(k), 1ull);
+}
+
+// offsets[m] = first sorted site whose motif id is >= m  (m = 0..n_motifs): CSR over motifs.
+__global__ void __launch_bounds__(256)
+motif_offsets_kernel(const uint64_t *__restrict__ key, int64_t n, int32_t n_motifs,
+                     int64_t *__restrict__ offsets) {
+    const int32_t m = blockIdx.x * blockDim.x + threadIdx.x;
+    if (m > n_motifs) return;
+    int64_t lo = 0, hi = n;  // first i with key_motif(key[i]) >= m
+    while (lo < hi) {
+        const int64_t mid = (lo + hi) >> 1;
+        if ((int64_t) key_motif(__ldg(key + mid)) < (int64_t) m) lo = mid + 1; else hi = mid;
+    }
+    offsets[m] = lo;
+}
+
+// ---------------------------------------------------------------------------------------------
+// De-duplication of adjacent sites (scanner.py:156-193), on the sorted site list.
+// Per (motif, sequence) segment and per strand separately, walking sites by ascending start with
+// one "current survivor": a site closer than the motif length to the survivor replaces it only
+// if its score is strictly higher (`curr.score >= next.score` keeps curr, scanner.py:163).
+// The surviving forward and reverse sites keep their (start, forward-first) order, which is the
+// reference's `fwd + rev` followed by a stable sort on start (scanner.py:190-191).
+// One thread per segment head walks its (short) segment.
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+dedup_flags_kernel(const uint64_t *__restrict__ key, const int32_t *__restrict__ seq_idx,
+                   const int32_t *__restrict__ start, const int8_t *__restrict__ strand,
+                   const double *__restrict__ score, int64_t n, const int32_t *__restrict__ mlen,
+                   int32_t *__restrict__ keep) {
+    const int64_t i = (int64_t) blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const uint32_t m = key_motif(key[i]);
+    const int32_t s = seq_idx[i];
+    if (i > 0 && key_motif(key[i - 1]) == m && seq_idx[i - 1] == s) return;  // not a segment head
+    int64_t e = i + 1;
+    while (e < n && key_motif(key[e]) == m && seq_idx[e] == s) e++;
+    const int32_t L = __ldg(mlen + m);
+    for (int8_t which = 1; which <= 2; which++) {
+        int64_t cur = -1;
+        for (int64_t t = i; t < e; t++) {
+            if (strand[t] != which) continue;
+            if (cur >= 0 && start[t] - start[cur] < L) {
+                if (score[cur] >= score[t]) { keep[t] = 0; continue; }
+                keep[cur] = 0;
+            }
+            keep[t] = 1;
+            cur = t;
+        }
+    }
+}
+
+__global__ void __launch_bounds__(256)
+scatter_kept_kernel(const int32_t *__restrict__ keep, const int64_t *__restrict__ dst, int64_t n,
+                    const uint64_t *__restrict__ key, const double *__restrict__ score,
+                    const int32_t *__restrict__ seq_idx, const int32_t *__restrict__ start,
+                    const int8_t *__restrict__ strand, uint64_t *__restrict__ o_key,
+                    double *__restrict__ o_score, int32_t *__restrict__ o_seq,
+                    int32_t *__restrict__ o_start, int8_t *__restrict__ o_strand) {
+    const int64_t i = (int64_t) blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n || !keep[i]) return;
+    const int64_t j = dst[i];
+    o_key[j] = key[i];
+    o_score[j] = score[i];
+    o_seq[j] = seq_idx[i];
+    o_start[j] = start[i];
+    o_strand[j] = strand[i];
 }
 
 // ---------------------------------------------------------------------------------------------

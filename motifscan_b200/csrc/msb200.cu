@@ -69,6 +69,12 @@ struct msb_ctx {
     // scratch (grow-only, reused across calls)
     DevBuf ascii, seq_off, cand, dirty, hit_key, hit_score, key_alt, score_alt, sort_tmp, counters;
     DevBuf out_seq, out_start, out_strand, out_counts, scores, scores_sorted, seg_off, ranks, sel;
+    DevBuf keep, keep_pos, out2_seq, out2_start, out2_strand;
+    // final site arrays of the last scan (point into the buffers above)
+    uint64_t *fin_key = nullptr;
+    double *fin_score = nullptr;
+    int32_t *fin_seq = nullptr, *fin_start = nullptr;
+    int8_t *fin_strand = nullptr;
     unsigned long long *h_counters = nullptr;  // pinned, 4 entries
     std::vector<PinnedBlock> pinned_free;
     std::mutex pinned_mu;
@@ -253,7 +259,8 @@ int msb_ctx_destroy(msb_ctx *ctx) {
     for (DevBuf *b : {&ctx->ascii, &ctx->seq_off, &ctx->cand, &ctx->dirty, &ctx->hit_key, &ctx->hit_score,
                       &ctx->key_alt, &ctx->score_alt, &ctx->sort_tmp, &ctx->counters, &ctx->out_seq,
                       &ctx->out_start, &ctx->out_strand, &ctx->out_counts, &ctx->scores,
-                      &ctx->scores_sorted, &ctx->seg_off, &ctx->ranks, &ctx->sel})
+                      &ctx->scores_sorted, &ctx->seg_off, &ctx->ranks, &ctx->sel, &ctx->keep, &ctx->keep_pos,
+                      &ctx->out2_seq, &ctx->out2_start, &ctx->out2_strand})
         b->release();
     for (auto &b : ctx->pinned_free) cudaFreeHost(b.p);
     if (ctx->h_counters) cudaFreeHost(ctx->h_counters);
@@ -699,7 +706,7 @@ static int launch_positions(msb_ctx *ctx, const ExactParams &E, const int64_t *p
 
 static int g_prefilter_w = 4;  // windows per thread (4 or 8); overridable for experiments
 
-static int scan_device(msb_ctx *ctx, msb_motifs *M, const msb_seqs *S, int strand) {
+static int scan_device(msb_ctx *ctx, msb_motifs *M, const msb_seqs *S, int strand, int flags) {
     if (!ctx || !M || !S) { set_error("msb_scan: null argument"); return MSB_EINVAL; }
     if (strand < 1 || strand > 3) { set_error("msb_scan: strand must be 1, 2 or 3"); return MSB_EINVAL; }
     if (M->ctx != ctx || S->ctx != ctx) { set_error("msb_scan: motifs/seqs belong to another context"); return MSB_EINVAL; }
@@ -710,8 +717,8 @@ static int scan_device(msb_ctx *ctx, msb_motifs *M, const msb_seqs *S, int stran
     std::fill(ctx->c, ctx->c + MSB_C_COUNT, 0);
     ctx->last_sites = 0;
     ctx->last_n_motifs = M->n;
-    MSB_TRY(ctx->out_counts.ensure(std::max<size_t>((size_t) M->n * 8, 16)));
-    MSB_CUDA(cudaMemsetAsync(ctx->out_counts.p, 0, std::max<size_t>((size_t) M->n * 8, 16), st));
+    MSB_TRY(ctx->out_counts.ensure((size_t) (M->n + 1) * 8));  // CSR offsets over motifs
+    MSB_CUDA(cudaMemsetAsync(ctx->out_counts.p, 0, (size_t) (M->n + 1) * 8, st));
     if (M->n == 0 || S->total_packed == 0) {
         MSB_CUDA(cudaStreamSynchronize(st));
         return MSB_OK;
@@ -808,7 +815,9 @@ static int scan_device(msb_ctx *ctx, msb_motifs *M, const msb_seqs *S, int stran
     }
     ctx->c[MSB_C_HITS] = n_hits;
 
-    // ---- stage 3: order (motif, sequence, start, fwd < rev) and decode --------------------------
+    // ---- stage 3: order (motif, sequence, start, fwd < rev), decode, optional de-duplication ----
+    ctx->fin_key = nullptr;
+    int64_t n_final = n_hits;
     if (n_hits) {
         MSB_TRY(ctx->key_alt.ensure((size_t) n_hits * 8));
         MSB_TRY(ctx->score_alt.ensure((size_t) n_hits * 8));
@@ -824,11 +833,54 @@ static int scan_device(msb_ctx *ctx, msb_motifs *M, const msb_seqs *S, int stran
         MSB_TRY(ctx->sort_tmp.ensure(std::max<size_t>(tmp_bytes, 16)));
         MSB_CUDA(cub::DeviceRadixSort::SortPairs(ctx->sort_tmp.p, tmp_bytes, ctx->hit_key.as<uint64_t>(), ctx->key_alt.as<uint64_t>(),
                                                  ctx->hit_score.as<double>(), ctx->score_alt.as<double>(), n_hits, 0, end_bit, st));
-        decode_sites_kernel<<<(unsigned) ((n_hits + 255) / 256), 256, 0, st>>>(
-            sv, ctx->key_alt.as<uint64_t>(), n_hits, ctx->out_seq.as<int32_t>(), ctx->out_start.as<int32_t>(),
-            ctx->out_strand.as<int8_t>(), ctx->out_counts.as<unsigned long long>());
+        const unsigned grid = (unsigned) ((n_hits + 255) / 256);
+        decode_sites_kernel<<<grid, 256, 0, st>>>(sv, ctx->key_alt.as<uint64_t>(), n_hits, ctx->out_seq.as<int32_t>(),
+                                                  ctx->out_start.as<int32_t>(), ctx->out_strand.as<int8_t>());
         MSB_CUDA(cudaGetLastError());
         ctx->c[MSB_C_LAUNCHES] += 2;  // sort (several CUB kernels, counted once) + decode
+        ctx->fin_key = ctx->key_alt.as<uint64_t>();
+        ctx->fin_score = ctx->score_alt.as<double>();
+        ctx->fin_seq = ctx->out_seq.as<int32_t>();
+        ctx->fin_start = ctx->out_start.as<int32_t>();
+        ctx->fin_strand = ctx->out_strand.as<int8_t>();
+        if (flags & MSB_SCAN_DEDUP) {
+            // scanner.py:171-193 on the device: keep flags, exclusive scan, scatter.
+            MSB_TRY(ctx->keep.ensure((size_t) n_hits * 4));
+            MSB_TRY(ctx->keep_pos.ensure((size_t) n_hits * 8));
+            MSB_TRY(ctx->out2_seq.ensure((size_t) n_hits * 4));
+            MSB_TRY(ctx->out2_start.ensure((size_t) n_hits * 4));
+            MSB_TRY(ctx->out2_strand.ensure((size_t) n_hits));
+            dedup_flags_kernel<<<grid, 256, 0, st>>>(ctx->fin_key, ctx->fin_seq, ctx->fin_start, ctx->fin_strand, ctx->fin_score,
+                                                     n_hits, mv.len, ctx->keep.as<int32_t>());
+            MSB_CUDA(cudaGetLastError());
+            size_t scan_bytes = 0;
+            MSB_CUDA(cub::DeviceScan::ExclusiveSum(nullptr, scan_bytes, ctx->keep.as<int32_t>(), ctx->keep_pos.as<int64_t>(), n_hits, st));
+            MSB_TRY(ctx->sort_tmp.ensure(std::max<size_t>(scan_bytes, 16)));
+            MSB_CUDA(cub::DeviceScan::ExclusiveSum(ctx->sort_tmp.p, scan_bytes, ctx->keep.as<int32_t>(), ctx->keep_pos.as<int64_t>(), n_hits, st));
+            // hit_key / hit_score are free again after the sort: reuse them as the compacted output
+            scatter_kept_kernel<<<grid, 256, 0, st>>>(ctx->keep.as<int32_t>(), ctx->keep_pos.as<int64_t>(), n_hits, ctx->fin_key,
+                                                      ctx->fin_score, ctx->fin_seq, ctx->fin_start, ctx->fin_strand,
+                                                      ctx->hit_key.as<uint64_t>(), ctx->hit_score.as<double>(),
+                                                      ctx->out2_seq.as<int32_t>(), ctx->out2_start.as<int32_t>(),
+                                                      ctx->out2_strand.as<int8_t>());
+            MSB_CUDA(cudaGetLastError());
+            ctx->c[MSB_C_LAUNCHES] += 3;
+            int32_t last_keep = 0;
+            int64_t last_pos = 0;
+            MSB_CUDA(cudaMemcpyAsync(&last_keep, ctx->keep.as<int32_t>() + (n_hits - 1), 4, cudaMemcpyDeviceToHost, st));
+            MSB_CUDA(cudaMemcpyAsync(&last_pos, ctx->keep_pos.as<int64_t>() + (n_hits - 1), 8, cudaMemcpyDeviceToHost, st));
+            MSB_CUDA(cudaStreamSynchronize(st));
+            n_final = last_pos + last_keep;
+            ctx->fin_key = ctx->hit_key.as<uint64_t>();
+            ctx->fin_score = ctx->hit_score.as<double>();
+            ctx->fin_seq = ctx->out2_seq.as<int32_t>();
+            ctx->fin_start = ctx->out2_start.as<int32_t>();
+            ctx->fin_strand = ctx->out2_strand.as<int8_t>();
+        }
+        motif_offsets_kernel<<<(unsigned) ((M->n + 1 + 255) / 256), 256, 0, st>>>(ctx->fin_key, n_final, M->n,
+                                                                                  ctx->out_counts.as<int64_t>());
+        MSB_CUDA(cudaGetLastError());
+        ctx->c[MSB_C_LAUNCHES] += 1;
     }
     MSB_CUDA(cudaEventRecord(ctx->ev[3], st));
     MSB_CUDA(cudaStreamSynchronize(st));
@@ -836,7 +888,7 @@ static int scan_device(msb_ctx *ctx, msb_motifs *M, const msb_seqs *S, int stran
     ctx->t[MSB_T_EXACT] = ev_ms(ctx->ev[1], ctx->ev[2]);
     ctx->t[MSB_T_ORDER] = ev_ms(ctx->ev[2], ctx->ev[3]);
     ctx->t[MSB_T_D2H] = 0;
-    ctx->last_sites = n_hits;
+    ctx->last_sites = n_final;
     return MSB_OK;
 }
 
@@ -850,22 +902,23 @@ int msb_set_option(const char *name, int value) {
     return MSB_EINVAL;
 }
 
-int msb_scan_device(msb_ctx *ctx, const msb_motifs *M, const msb_seqs *S, int strand, int64_t *n_sites) {
-    MSB_TRY(scan_device(ctx, const_cast<msb_motifs *>(M), S, strand));
+int msb_scan_device(msb_ctx *ctx, const msb_motifs *M, const msb_seqs *S, int strand, int flags, int64_t *n_sites) {
+    MSB_TRY(scan_device(ctx, const_cast<msb_motifs *>(M), S, strand, flags));
     if (n_sites) *n_sites = ctx->last_sites;
     return MSB_OK;
 }
 
-int msb_scan(msb_ctx *ctx, const msb_motifs *M, const msb_seqs *S, int strand, msb_result **out) {
+int msb_scan_ex(msb_ctx *ctx, const msb_motifs *M, const msb_seqs *S, int strand, int flags, msb_result **out) {
     if (!out) { set_error("msb_scan: null out"); return MSB_EINVAL; }
     *out = nullptr;
-    MSB_TRY(scan_device(ctx, const_cast<msb_motifs *>(M), S, strand));
+    MSB_TRY(scan_device(ctx, const_cast<msb_motifs *>(M), S, strand, flags));
     msb_result *R = new (std::nothrow) msb_result();
     if (!R) { set_error("out of host memory"); return MSB_ENOMEM; }
     R->ctx = ctx;
     R->n_sites = ctx->last_sites;
     R->n_motifs = M->n;
     R->counts.assign((size_t) M->n, 0);
+    std::vector<int64_t> offsets((size_t) M->n + 1, 0);
     const int64_t n = R->n_sites;
     // one pinned block: score (8n) | seq_idx (4n) | start (4n) | strand (n)
     int rc = pinned_get(ctx, (size_t) std::max<int64_t>(17 * n, 64), &R->block);
@@ -879,18 +932,23 @@ int msb_scan(msb_ctx *ctx, const msb_motifs *M, const msb_seqs *S, int strand, m
     cudaError_t e = cudaEventRecord(ctx->ev[4], st);
     auto step = [&](cudaError_t x) { if (e == cudaSuccess) e = x; };
     if (n) {
-        step(cudaMemcpyAsync(R->score, ctx->score_alt.p, (size_t) n * 8, cudaMemcpyDeviceToHost, st));
-        step(cudaMemcpyAsync(R->seq_idx, ctx->out_seq.p, (size_t) n * 4, cudaMemcpyDeviceToHost, st));
-        step(cudaMemcpyAsync(R->start, ctx->out_start.p, (size_t) n * 4, cudaMemcpyDeviceToHost, st));
-        step(cudaMemcpyAsync(R->strand, ctx->out_strand.p, (size_t) n, cudaMemcpyDeviceToHost, st));
+        step(cudaMemcpyAsync(R->score, ctx->fin_score, (size_t) n * 8, cudaMemcpyDeviceToHost, st));
+        step(cudaMemcpyAsync(R->seq_idx, ctx->fin_seq, (size_t) n * 4, cudaMemcpyDeviceToHost, st));
+        step(cudaMemcpyAsync(R->start, ctx->fin_start, (size_t) n * 4, cudaMemcpyDeviceToHost, st));
+        step(cudaMemcpyAsync(R->strand, ctx->fin_strand, (size_t) n, cudaMemcpyDeviceToHost, st));
+        step(cudaMemcpyAsync(offsets.data(), ctx->out_counts.p, (size_t) (M->n + 1) * 8, cudaMemcpyDeviceToHost, st));
     }
-    if (M->n) step(cudaMemcpyAsync(R->counts.data(), ctx->out_counts.p, (size_t) M->n * 8, cudaMemcpyDeviceToHost, st));
     step(cudaEventRecord(ctx->ev[5], st));
     step(cudaStreamSynchronize(st));
     if (e != cudaSuccess) { msb_result_destroy(R); return cuda_fail(e, "msb_scan D2H", __FILE__, __LINE__); }
+    for (int32_t m = 0; m < M->n; m++) R->counts[m] = offsets[m + 1] - offsets[m];
     ctx->t[MSB_T_D2H] = ev_ms(ctx->ev[4], ctx->ev[5]);
     *out = R;
     return MSB_OK;
+}
+
+int msb_scan(msb_ctx *ctx, const msb_motifs *M, const msb_seqs *S, int strand, msb_result **out) {
+    return msb_scan_ex(ctx, M, S, strand, 0, out);
 }
 
 int msb_result_total(const msb_result *R, int64_t *n) {

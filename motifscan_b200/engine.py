@@ -189,16 +189,20 @@ class ScanResult:
             pass
 
 
-def scan(ctx, motifs, seqs, strand):
+def scan(ctx, motifs, seqs, strand, remove_dup=False):
+    """Scan; with remove_dup the reference's adjacent-site de-duplication (scanner.py:156-193)
+    runs on the device before the sites are copied back."""
     h = ctypes.c_void_p()
-    check(ctx._lib.msb_scan(ctx._h, motifs._h, seqs._h, int(strand), ctypes.byref(h)))
+    flags = _lib.MSB_SCAN_DEDUP if remove_dup else 0
+    check(ctx._lib.msb_scan_ex(ctx._h, motifs._h, seqs._h, int(strand), flags, ctypes.byref(h)))
     return ScanResult(ctx, h, motifs.n)
 
 
-def scan_device(ctx, motifs, seqs, strand):
+def scan_device(ctx, motifs, seqs, strand, remove_dup=False):
     """Kernels only (results stay on the device); returns the number of sites."""
     n = ctypes.c_int64(0)
-    check(ctx._lib.msb_scan_device(ctx._h, motifs._h, seqs._h, int(strand), ctypes.byref(n)))
+    flags = _lib.MSB_SCAN_DEDUP if remove_dup else 0
+    check(ctx._lib.msb_scan_device(ctx._h, motifs._h, seqs._h, int(strand), flags, ctypes.byref(n)))
     return n.value
 
 

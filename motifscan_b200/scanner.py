@@ -1,0 +1,229 @@
+"""Motif scanner for a list of genomic regions -- the reference's `motifscan.scanner` API
+(scanner.py:16-193) over the CUDA path.
+
+Same constructor arguments, attributes (`sequences`, `seq_starts`, `seq_ends`) and
+`scan_motifs(pwms)` contract; the result indexes like the reference's nested list
+`[pwm][region] -> [MotifSite(start, score, strand), ...]` but is backed by the arrays the device
+returns, so a (motif, region) cell costs nothing until it is looked at (the reference allocates
+one Python list per cell, scanner.py:140-143 -- 3.8e8 lists for configs[4]).
+"""
+import logging
+import os
+from collections import namedtuple
+
+import numpy as np
+
+from . import engine
+
+logger = logging.getLogger(__name__)
+
+MotifSite = namedtuple("MotifSite", ["start", "score", "strand"])  # scanner.py:16
+_STRAND_ARG = {"+": 1, "-": 2, "both": 3}  # scanner.py:118-123
+
+
+class Scanner:
+    def __init__(self, genome, regions, window_size=0, strand="both", p_value="1e-4",
+                 remove_dup=True, n_threads=1, device=None):
+        self.window_size = window_size if window_size > 0 else 0
+        self.extend = window_size // 2
+        if strand not in _STRAND_ARG:
+            raise ValueError(f"invalid strand option: {strand!r}")
+        self.strand = strand
+        self.p_value = p_value
+        self.remove_dup = remove_dup
+        # kept for signature compatibility (scanner.py:56-66); the GPU path has no thread count
+        self.n_threads = max(1, min(int(n_threads), os.cpu_count() or 1))
+        self.device = device
+        self.seq_starts = []
+        self.seq_ends = []
+        self._chunks = []
+        self._sequences = None
+        self._extract_seq(genome, regions)
+
+    def _extract_seq(self, genome, regions):
+        """Forward-strand sequence of every region's scan window (scanner.py:71-87): the whole
+        region, or `window_size` centred on the summit, clipped to [0, chromosome size)."""
+        fetch = getattr(genome, "fetch_bytes", None)
+        sizes = genome.chrom_sizes
+        for region in regions:
+            if self.window_size <= 0:
+                start, end = region.start, region.end
+            else:
+                start = max(region.summit - self.extend, 0)
+                end = min(region.summit + self.extend, sizes[region.chrom])
+            self.seq_starts.append(start)
+            self.seq_ends.append(end)
+            if fetch is not None:
+                self._chunks.append(fetch(region.chrom, start, end))
+            else:
+                self._chunks.append(genome.fetch_sequence(region.chrom, start, end).encode("utf-8"))
+
+    @property
+    def sequences(self):
+        if self._sequences is None:
+            self._sequences = [c.decode("utf-8") for c in self._chunks]
+        return self._sequences
+
+    def _flat(self):
+        off = np.zeros(len(self._chunks) + 1, dtype=np.int64)
+        if self._chunks:
+            np.cumsum([len(c) for c in self._chunks], out=off[1:])
+        return np.frombuffer(b"".join(self._chunks), dtype=np.uint8), off
+
+    def scan_motifs(self, pwms, ctx=None):
+        """Scan for motif occurrences; returns a `MotifSites` (nested-list view, (n_pwms,
+        n_regions, n_sites))."""
+        cutoffs = []
+        for pwm in pwms:
+            try:
+                cutoffs.append(pwm.cutoffs[self.p_value])
+            except (TypeError, KeyError):
+                raise ValueError(f"PWM has no motif score cutoff set for P-value {self.p_value!r}")
+        if ctx is None:
+            dev = self.device
+            if dev is None:
+                dev = int(os.environ.get("MOTIFSCAN_B200_DEVICE", os.environ.get("LOCAL_RANK", "0")))
+            ctx = engine.default_context(dev)
+        matrices = [pwm.matrix for pwm in pwms]
+        lengths = [pwm.length for pwm in pwms]
+        if not matrices:
+            return MotifSites(None, 0, self.seq_starts, lengths)
+        motifs = engine.MotifSet(ctx, matrices, cutoffs)
+        try:
+            blob, off = self._flat()
+            sset = engine.SequenceSet(ctx, blob=blob, seq_off=off)
+            try:
+                res = engine.scan(ctx, motifs, sset, _STRAND_ARG[self.strand], remove_dup=self.remove_dup)
+            finally:
+                sset.close()
+        finally:
+            motifs.close()
+        return MotifSites(res.detach(), len(matrices), self.seq_starts, lengths)
+
+
+class _PerMotif:
+    """`motif_sites[m]`: sequence-indexed view of one motif's sites."""
+
+    def __init__(self, parent, m):
+        self._p = parent
+        self._m = m
+        a, b = parent._off[m], parent._off[m + 1]
+        self._a = a
+        seq = parent._seq_idx[a:b]
+        # sites are sorted by sequence within a motif: CSR over sequences by binary search
+        self._bounds = a + np.searchsorted(seq, np.arange(parent.n_seqs + 1))
+
+    def __len__(self):
+        return self._p.n_seqs
+
+    def __getitem__(self, s):
+        if isinstance(s, slice):
+            return [self[i] for i in range(*s.indices(len(self)))]
+        if s < 0:
+            s += len(self)
+        if not 0 <= s < len(self):
+            raise IndexError("region index out of range")
+        p = self._p
+        a, b = int(self._bounds[s]), int(self._bounds[s + 1])
+        base = p.seq_starts[s]
+        return [MotifSite(start=base + int(p._start[k]), score=float(p._score[k]),
+                          strand="+" if p._strand[k] == 1 else "-") for k in range(a, b)]
+
+    def __iter__(self):
+        return (self[s] for s in range(len(self)))
+
+    def site_counts(self):
+        """Number of sites per region (what motif_sites_number.xls tabulates, io/__init__.py:27)."""
+        return np.diff(self._bounds)
+
+
+class MotifSites:
+    """Nested-list view `[pwm][region] -> [MotifSite]` over the scan's arrays (the shape
+    make_motif_sites returns, scanner.py:135-153).  `start` is genomic: window start + offset."""
+
+    def __init__(self, res, n_pwms, seq_starts, lengths):
+        self.n_pwms = n_pwms
+        self.n_seqs = len(seq_starts)
+        self.seq_starts = list(seq_starts)
+        self.lengths = list(lengths)
+        if res is None:
+            self._off = np.zeros(n_pwms + 1, dtype=np.int64)
+            self._seq_idx = np.zeros(0, dtype=np.int32)
+            self._start = np.zeros(0, dtype=np.int32)
+            self._score = np.zeros(0, dtype=np.float64)
+            self._strand = np.zeros(0, dtype=np.int8)
+        else:
+            self._off, self._seq_idx = res.offsets, res.seq_idx
+            self._start, self._score, self._strand = res.start, res.score, res.strand
+
+    def __len__(self):
+        return self.n_pwms
+
+    def __getitem__(self, m):
+        if isinstance(m, slice):
+            return [self[i] for i in range(*m.indices(len(self)))]
+        if m < 0:
+            m += len(self)
+        if not 0 <= m < len(self):
+            raise IndexError("motif index out of range")
+        return _PerMotif(self, m)
+
+    def __iter__(self):
+        return (self[m] for m in range(len(self)))
+
+    def tolist(self):
+        return [[cell for cell in per] for per in self]
+
+    # -- vectorised summaries (consumers: stats.motif_enrichment, the site tables) --------------
+    def n_sites(self):
+        return np.diff(self._off)
+
+    def regions_with_sites(self):
+        """Per motif, the number of regions with at least one site (stats.py:29-31)."""
+        out = np.zeros(self.n_pwms, dtype=np.int64)
+        for m in range(self.n_pwms):
+            seq = self._seq_idx[self._off[m]:self._off[m + 1]]
+            if len(seq):
+                out[m] = 1 + np.count_nonzero(np.diff(seq))
+        return out
+
+
+# ---- list-based helpers with the reference's signatures (scanner.py:135-193) ---------------------
+def make_motif_sites(sites, seq_starts):
+    """Pooled `c_scan_motif` output -> nested list (n_pwms, n_seqs, n_sites) with genomic starts
+    and '+'/'-' strands (scanner.py:135-153)."""
+    nested = []
+    for per_pwm in sites:
+        cells = [[] for _ in seq_starts]
+        for seq_idx, pos, score, strand in per_pwm:
+            cells[seq_idx].append(MotifSite(seq_starts[seq_idx] + pos, score, "+" if strand == 1 else "-"))
+        nested.append(cells)
+    return nested
+
+
+def _survivors(sites, length):
+    """One strand's sites by ascending start -> survivors of the reference's greedy pass
+    (scanner.py:156-168): a site closer than `length` to the current survivor replaces it only
+    when it scores strictly higher."""
+    kept = []
+    for site in sites:
+        if kept and site.start - kept[-1].start < length:
+            if kept[-1].score >= site.score:
+                continue
+            kept.pop()
+        kept.append(site)
+    return kept
+
+
+def deduplicate_motif_sites(motif_sites, lengths):
+    """Adjacent-site de-duplication (scanner.py:171-193), per strand, then merged by start with
+    '+' first on ties (the reference's stable sort of fwd + rev)."""
+    out = []
+    for per_pwm, length in zip(motif_sites, lengths):
+        cells = []
+        for sites in per_pwm:
+            fwd = _survivors([s for s in sites if s.strand == "+"], length)
+            rev = _survivors([s for s in sites if s.strand != "+"], length)
+            cells.append(sorted(fwd + rev, key=lambda s: s.start))
+        out.append(cells)
+    return out
