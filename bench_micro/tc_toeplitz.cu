@@ -1,0 +1,364 @@
+// Micro-benchmark + correctness probe for the tensor-core prefilter formulation on B200:
+//
+//   D[128 windows x 256 motif-strands] += A[128 x K] * B[256 x K]^T      (tcgen05.mma kind::f8f6f4)
+//
+// A is never materialised: it is the Toeplitz matrix of the one-hot sequence stream.  The stream
+// holds 4 bytes per base (e4m3 1.0 in the byte of its code, all zero for N); row r of A is the
+// stream at byte offset 16*r, i.e. the window that starts 4 bases after row r-1's.  With the
+// no-swizzle K-major canonical layout ((8,m),2):((16 B, SBO),LBO) this is SBO = 128 B, LBO = 16 B:
+// overlapping rows, one descriptor.  Four copies of the stream shifted by 0..3 bases give the
+// windows at every start.  B (PWM tile, e4m3) uses the same canonical layout, chunk-major.
+//
+// The probe checks every accumulator of the first tile of CTA 0 and the per-CTA count of
+// non-negative accumulators against a CPU computation, then times the pipeline.
+#include <cstdio>
+#include <cstdint>
+#include <cstdlib>
+#include <cstring>
+#include <cmath>
+#include <vector>
+#include <cuda_runtime.h>
+
+#define CK(x) do { cudaError_t e_ = (x); if (e_ != cudaSuccess) { printf("CUDA %s at %s:%d\n", cudaGetErrorString(e_), __FILE__, __LINE__); exit(1); } } while (0)
+
+constexpr int kTileBases = 512;                  // window starts per position tile (4 shifts x 128 rows)
+constexpr int kHalo = 32;
+constexpr int kStreamBases = kTileBases + kHalo; // 544
+constexpr int kStreamBytes = kStreamBases * 4;   // 2176 per shifted copy
+constexpr int kSlotBytes = 4 * kStreamBytes;     // 8704
+constexpr int kSlots = 3;
+constexpr int kN = 256;                          // motif-strand columns per B tile
+constexpr int kThreads = 256;                    // warp 0 MMA, 1-3 producers, 4-7 epilogue
+
+__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t) __cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint64_t *bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t *bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "WAIT_%=:\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+        "@p bra DONE_%=;\n\t"
+        "bra WAIT_%=;\n\t"
+        "DONE_%=:\n\t}" ::"r"(smem_u32(bar)), "r"(parity) : "memory");
+}
+__device__ __forceinline__ void umma_commit(uint64_t *bar) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void umma_f8(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t acc) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f8f6f4 [%0], %1, %2, %3, p;\n\t}" ::"r"(d_tmem), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(acc)
+        : "memory");
+}
+// K-major, no swizzle: start address, leading (K-chunk) byte offset, stride (8-row group) byte offset
+__device__ __forceinline__ uint64_t make_desc(uint32_t addr, uint32_t lbo, uint32_t sbo) {
+    return (uint64_t) ((addr & 0x3FFFFu) >> 4) | ((uint64_t) (lbo >> 4) << 16) | ((uint64_t) (sbo >> 4) << 32) | (1ull << 46);
+}
+
+#define LD32(r, addr)                                                                               \
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x32.b32 "                                          \
+                 "{%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,"                          \
+                 "%16,%17,%18,%19,%20,%21,%22,%23,%24,%25,%26,%27,%28,%29,%30,%31}, [%32];"        \
+                 : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),  \
+                   "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), \
+                   "=r"(r[16]), "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), \
+                   "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31]) \
+                 : "r"(addr))
+
+struct Params {
+    const uint32_t *codes;   // 2-bit codes, 16 per word
+    const uint32_t *nmask;   // 1 bit per base
+    const uint8_t *btiles;   // NT tiles, each KS*8192 bytes: [kchunk16][n][16 B]
+    int tiles_per_cta;
+    int nt;
+    unsigned long long *count;   // per CTA: accumulators with sign bit clear
+    float *dump;                 // CTA 0, tile 0: [shift][nt][128][256]
+    int epilogue;                // 0: skip TMEM reads (MMA pace only)
+};
+
+template <int KS>
+__global__ void __launch_bounds__(kThreads, 1) tc_kernel(const Params P) {
+    extern __shared__ __align__(1024) uint8_t smem[];
+    uint8_t *s_stream = smem;                                   // kSlots * kSlotBytes
+    uint8_t *s_b = smem + ((kSlots * kSlotBytes + 1023) & ~1023);  // nt * KS * 8192
+    __shared__ uint64_t bar_stream_full[kSlots], bar_stream_empty[kSlots], bar_tmem_full[2], bar_tmem_empty[2];
+    __shared__ uint32_t s_tmem_base;
+    __shared__ unsigned long long s_count;
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    if (threadIdx.x == 0) {
+        for (int i = 0; i < kSlots; i++) { mbar_init(&bar_stream_full[i], 3); mbar_init(&bar_stream_empty[i], 1); }
+        for (int i = 0; i < 2; i++) { mbar_init(&bar_tmem_full[i], 1); mbar_init(&bar_tmem_empty[i], 4); }
+        s_count = 0;
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 0) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], 512;" ::"r"(smem_u32(&s_tmem_base)));
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
+    }
+    // B tiles -> smem (generic proxy), then make them visible to the async proxy
+    {
+        const uint4 *src = reinterpret_cast<const uint4 *>(P.btiles);
+        uint4 *dst = reinterpret_cast<uint4 *>(s_b);
+        const int n16 = P.nt * KS * 8192 / 16;
+        for (int i = threadIdx.x; i < n16; i += kThreads) dst[i] = src[i];
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;");
+    __syncthreads();
+    asm volatile("tcgen05.fence::after_thread_sync;");
+    const uint32_t tmem = s_tmem_base;
+    const int T = P.tiles_per_cta, NT = P.nt;
+    // idesc: D = F32 (1 << 4), A = B = E4M3 (0), K-major both, N = 256 (>> 3 at bit 17), M = 128 (>> 4 at bit 24)
+    const uint32_t idesc = (1u << 4) | ((uint32_t) (kN >> 3) << 17) | ((uint32_t) (128 >> 4) << 24);
+
+    if (warp == 0) {
+        if (lane == 0) {
+            uint32_t u = 0;
+            for (int it = 0; it < T; it++) {
+                const int slot = it % kSlots;
+                mbar_wait(&bar_stream_full[slot], (it / kSlots) & 1);
+                asm volatile("tcgen05.fence::after_thread_sync;");
+                const uint32_t a_base = smem_u32(s_stream + slot * kSlotBytes);
+                for (int s = 0; s < 4; s++) {
+                    for (int nt = 0; nt < NT; nt++, u++) {
+                        const uint32_t buf = u & 1;
+                        mbar_wait(&bar_tmem_empty[buf], ((u >> 1) & 1) ^ 1);
+                        asm volatile("tcgen05.fence::after_thread_sync;");
+                        const uint32_t b_base = smem_u32(s_b + nt * KS * 8192);
+#pragma unroll
+                        for (int ks = 0; ks < KS; ks++) {
+                            const uint64_t ad = make_desc(a_base + s * kStreamBytes + ks * 32, 16, 128);
+                            const uint64_t bd = make_desc(b_base + ks * 8192, 4096, 128);
+                            umma_f8(tmem + buf * 256, ad, bd, idesc, ks > 0);
+                        }
+                        umma_commit(&bar_tmem_full[buf]);
+                    }
+                }
+                umma_commit(&bar_stream_empty[slot]);
+            }
+        }
+        __syncwarp();
+    } else if (warp < 4) {
+        // producers: expand the packed codes of tile `it` into the 4 shifted one-hot streams
+        const int pw = warp - 1;
+        for (int it = 0; it < T; it++) {
+            const int slot = it % kSlots;
+            mbar_wait(&bar_stream_empty[slot], ((it / kSlots) & 1) ^ 1);
+            const long long tile_start = ((long long) blockIdx.x * T + it) * kTileBases;
+            uint32_t *dst = reinterpret_cast<uint32_t *>(s_stream + slot * kSlotBytes);
+            for (int idx = pw * 32 + lane; idx < 4 * kStreamBases; idx += 96) {
+                const int s = idx / kStreamBases, i = idx - s * kStreamBases;
+                const long long p = tile_start + s + i;
+                const uint32_t code = (__ldg(P.codes + (p >> 4)) >> ((p & 15) * 2)) & 3u;
+                const uint32_t isn = (__ldg(P.nmask + (p >> 5)) >> (p & 31)) & 1u;
+                dst[idx] = isn ? 0u : (0x38u << (8 * code));
+            }
+            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&bar_stream_full[slot]);
+        }
+    } else {
+        // epilogue: warp w reads TMEM lanes 32*(w%4) .. +31 = its 32 windows, all 256 columns
+        const int q = warp & 3;
+        unsigned long long cnt = 0;
+        uint32_t u = 0;
+        for (int it = 0; it < T; it++) {
+            for (int s = 0; s < 4; s++) {
+                for (int nt = 0; nt < NT; nt++, u++) {
+                    const uint32_t buf = u & 1;
+                    mbar_wait(&bar_tmem_full[buf], (u >> 1) & 1);
+                    asm volatile("tcgen05.fence::after_thread_sync;");
+                    if (P.epilogue) {
+                        const uint32_t taddr = tmem + buf * 256 + ((uint32_t) (q * 32) << 16);
+                        const bool dump = (blockIdx.x == 0 && it == 0 && P.dump != nullptr);
+#pragma unroll 1
+                        for (int c = 0; c < 256; c += 64) {
+                            uint32_t r0[32], r1[32];
+                            LD32(r0, taddr + c);
+                            LD32(r1, taddr + c + 32);
+                            asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+                            uint32_t all = 0xffffffffu;
+#pragma unroll
+                            for (int j = 0; j < 32; j += 2) all &= r0[j] & r0[j + 1];
+#pragma unroll
+                            for (int j = 0; j < 32; j += 2) all &= r1[j] & r1[j + 1];
+                            if (!(all & 0x80000000u)) {   // some accumulator is >= 0
+#pragma unroll
+                                for (int j = 0; j < 32; j++) cnt += (r0[j] >> 31) ^ 1u;
+#pragma unroll
+                                for (int j = 0; j < 32; j++) cnt += (r1[j] >> 31) ^ 1u;
+                            }
+                            if (dump) {
+                                float *o = P.dump + (((size_t) (s * NT + nt) * 128) + q * 32 + lane) * 256 + c;
+#pragma unroll
+                                for (int j = 0; j < 32; j++) { o[j] = __uint_as_float(r0[j]); o[32 + j] = __uint_as_float(r1[j]); }
+                            }
+                        }
+                    }
+                    asm volatile("tcgen05.fence::before_thread_sync;");
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive(&bar_tmem_empty[buf]);
+                }
+            }
+        }
+        atomicAdd(&s_count, cnt);
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;");
+    __syncthreads();
+    if (threadIdx.x == 0) P.count[blockIdx.x] = s_count;
+    if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 512;" ::"r"(tmem));
+}
+
+// ---- host -------------------------------------------------------------------------------------
+static float e4m3_decode(uint8_t v) {
+    const int s = v >> 7, e = (v >> 3) & 15, m = v & 7;
+    float mag = e == 0 ? ldexpf((float) m / 8.f, -6) : ldexpf(1.f + (float) m / 8.f, e - 7);
+    return s ? -mag : mag;
+}
+// largest representable value <= x (round toward -inf), finite inputs within +-448
+static uint8_t e4m3_encode_floor(float x) {
+    uint8_t best = 0xFE;  // -448
+    float bestv = -448.f;
+    for (int v = 0; v < 256; v++) {
+        if ((v & 0x7F) == 0x7F) continue;  // NaN
+        const float f = e4m3_decode((uint8_t) v);
+        if (f <= x && f >= bestv) { if (f > bestv || v < 0x80) { best = (uint8_t) v; bestv = f; } }
+    }
+    return best;
+}
+
+template <int KS>
+static void run(int nt, int tiles_per_cta, bool verify, int wmode = 0) {
+    const int L = 8 * KS;
+    const int n_cta = 148;
+    const long long n_bases = (long long) n_cta * tiles_per_cta * kTileBases;
+    const long long padded = n_bases + 1024;
+    std::vector<uint8_t> base(padded);
+    srand(1234 + KS);
+    for (long long i = 0; i < padded; i++) {
+        int r = rand() % 100;
+        base[i] = r < 3 ? 4 : (uint8_t) (rand() & 3);   // 3 % N
+        if (i >= n_bases) base[i] = 4;
+    }
+    std::vector<uint32_t> codes(padded / 16 + 8, 0), nmask(padded / 32 + 8, 0);
+    for (long long i = 0; i < padded; i++) {
+        if (base[i] == 4) nmask[i >> 5] |= 1u << (i & 31);
+        else codes[i >> 4] |= (uint32_t) base[i] << ((i & 15) * 2);
+    }
+    // PWM tiles: W[nt][n][c][b] floats exactly representable in e4m3; mostly negative so that a
+    // non-negative window sum is rare
+    std::vector<float> W((size_t) nt * kN * L * 4);
+    std::vector<uint8_t> bt((size_t) nt * KS * 8192);
+    for (int t = 0; t < nt; t++)
+        for (int n = 0; n < kN; n++)
+            for (int c = 0; c < L; c++) {
+                const int best = rand() & 3;
+                for (int b = 0; b < 4; b++) {
+                    float v = (b == best) ? (float) (rand() % 5) * 0.5f + 1.0f : -(float) (rand() % 40) * 0.25f - 1.0f;
+                    uint8_t q = e4m3_encode_floor(v);
+                    if (wmode == 1) {   // adversarial: any representable magnitude, wide exponent spread
+                        q = (uint8_t) (rand() % 0x7F);               // 0 .. 448
+                        if (b != best) q |= 0x80;
+                        if (b == best && q > 0x60) q -= 0x30;        // keep the positives moderate
+                    }
+                    W[(((size_t) t * kN + n) * L + c) * 4 + b] = e4m3_decode(q);
+                    const int k = 4 * c + b, ks = k / 32, kk = k % 32, chunk = kk / 16, byte = kk % 16;
+                    bt[(size_t) t * KS * 8192 + (size_t) ks * 8192 + (size_t) chunk * 4096 + (size_t) n * 16 + byte] = q;
+                }
+            }
+    uint32_t *d_codes, *d_nmask; uint8_t *d_bt; unsigned long long *d_count; float *d_dump;
+    CK(cudaMalloc(&d_codes, codes.size() * 4)); CK(cudaMalloc(&d_nmask, nmask.size() * 4));
+    CK(cudaMalloc(&d_bt, bt.size())); CK(cudaMalloc(&d_count, n_cta * 8));
+    const size_t dump_elems = (size_t) 4 * nt * 128 * 256;
+    CK(cudaMalloc(&d_dump, dump_elems * 4));
+    CK(cudaMemcpy(d_codes, codes.data(), codes.size() * 4, cudaMemcpyHostToDevice));
+    CK(cudaMemcpy(d_nmask, nmask.data(), nmask.size() * 4, cudaMemcpyHostToDevice));
+    CK(cudaMemcpy(d_bt, bt.data(), bt.size(), cudaMemcpyHostToDevice));
+    CK(cudaMemset(d_dump, 0, dump_elems * 4));
+    Params P{d_codes, d_nmask, d_bt, tiles_per_cta, nt, d_count, verify ? d_dump : nullptr, 1};
+    const size_t smem = ((kSlots * kSlotBytes + 1023) & ~1023) + (size_t) nt * KS * 8192 + 1024;
+    CK(cudaFuncSetAttribute(tc_kernel<KS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem));
+    cudaEvent_t e0, e1; CK(cudaEventCreate(&e0)); CK(cudaEventCreate(&e1));
+    for (int mode = 1; mode >= 0; mode--) {
+        P.epilogue = mode;
+        tc_kernel<KS><<<n_cta, kThreads, smem>>>(P);   // warm-up
+        CK(cudaDeviceSynchronize());
+        CK(cudaEventRecord(e0));
+        tc_kernel<KS><<<n_cta, kThreads, smem>>>(P);
+        CK(cudaEventRecord(e1));
+        CK(cudaDeviceSynchronize());
+        float ms = 0; CK(cudaEventElapsedTime(&ms, e0, e1));
+        const double units = (double) n_cta * tiles_per_cta * 4 * nt;
+        const double macs = units * 128.0 * 256.0 * 32.0 * KS;
+        printf("KS=%d (L=%d) nt=%d tiles/cta=%d epilogue=%d: %.3f ms, %.1f TMAC/s (%.2f PFLOP/s), %.1f ns/unit/SM, "
+               "%.2f G window*motif-strand/s\n", KS, L, nt, tiles_per_cta, mode, ms, macs / ms / 1e9, 2 * macs / ms / 1e12,
+               ms * 1e6 / (units / n_cta), units * 128 * 256 / ms / 1e6);
+    }
+    if (verify) {
+        std::vector<unsigned long long> cnt(n_cta);
+        P.epilogue = 1;
+        tc_kernel<KS><<<n_cta, kThreads, smem>>>(P);
+        CK(cudaDeviceSynchronize());
+        CK(cudaMemcpy(cnt.data(), d_count, n_cta * 8, cudaMemcpyDeviceToHost));
+        std::vector<float> dump(dump_elems);
+        CK(cudaMemcpy(dump.data(), d_dump, dump_elems * 4, cudaMemcpyDeviceToHost));
+        // CPU: exact dump of CTA 0 tile 0, counts of the first 4 CTAs
+        auto score = [&](long long p, int t, int n) {
+            float acc = 0;
+            for (int c = 0; c < L; c++) { const int b = base[p + c]; if (b < 4) acc += W[(((size_t) t * kN + n) * L + c) * 4 + b]; }
+            return acc;
+        };
+        auto score_d = [&](long long p, int t, int n) {
+            double acc = 0;
+            for (int c = 0; c < L; c++) { const int b = base[p + c]; if (b < 4) acc += (double) W[(((size_t) t * kN + n) * L + c) * 4 + b]; }
+            return acc;
+        };
+        double max_pos = 0, max_neg = 0, max_mag = 0; long long inexact = 0;
+        long long bad = 0;
+        for (int s = 0; s < 4; s++) for (int t = 0; t < nt; t++) for (int r = 0; r < 128; r++) for (int n = 0; n < kN; n++) {
+            const float want = score(4 * r + s, t, n), got = dump[(((size_t) (s * nt + t) * 128) + r) * 256 + n];
+            if (wmode == 1) {
+                const double wd = score_d(4 * r + s, t, n);
+                const double err = (double) got - wd;
+                if (err > max_pos) max_pos = err;
+                if (err < max_neg) max_neg = err;
+                if (fabs(wd) > max_mag) max_mag = fabs(wd);
+                if ((double) (float) wd != (double) got) inexact++;
+                continue;
+            }
+            if (want != got) { if (bad < 5) printf("  MISMATCH s=%d t=%d r=%d n=%d want %g got %g\n", s, t, r, n, want, got); bad++; }
+        }
+        printf("  dump check: %lld mismatches of %zu\n", bad, dump_elems);
+        if (wmode == 1) { printf("  adversarial: err range [%g, %g], max |sum| %g, results != RN(exact): %lld\n", max_neg, max_pos, max_mag, inexact); }
+        long long cbad = 0;
+        for (int cta = 0; cta < (wmode ? 0 : 4); cta++) {
+            unsigned long long want = 0;
+            const long long start = (long long) cta * tiles_per_cta * kTileBases;
+            for (long long p = start; p < start + (long long) tiles_per_cta * kTileBases; p++)
+                for (int t = 0; t < nt; t++) for (int n = 0; n < kN; n++) {
+                    const float v = score(p, t, n);
+                    want += !std::signbit(v);
+                }
+            if (want != cnt[cta]) { cbad++; printf("  COUNT MISMATCH cta %d want %llu got %llu\n", cta, want, cnt[cta]); }
+        }
+        printf("  count check: %lld mismatches (cta0 count %llu)\n", cbad, cnt[0]);
+    }
+    cudaFree(d_codes); cudaFree(d_nmask); cudaFree(d_bt); cudaFree(d_count); cudaFree(d_dump);
+}
+
+int main(int argc, char **argv) {
+    run<1>(1, 8, true);
+    run<4>(3, 8, true);
+    run<1>(1, 8, true, 1);
+    run<2>(2, 8, true, 1);
+    run<4>(3, 8, true, 1);
+    return 0;
+}
