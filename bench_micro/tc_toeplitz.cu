@@ -18,6 +18,7 @@
 #include <cmath>
 #include <vector>
 #include <cuda_runtime.h>
+#include <cuda_fp16.h>
 
 #define CK(x) do { cudaError_t e_ = (x); if (e_ != cudaSuccess) { printf("CUDA %s at %s:%d\n", cudaGetErrorString(e_), __FILE__, __LINE__); exit(1); } } while (0)
 
@@ -28,7 +29,7 @@ constexpr int kStreamBytes = kStreamBases * 4;   // 2176 per shifted copy
 constexpr int kSlotBytes = 4 * kStreamBytes;     // 8704
 constexpr int kSlots = 3;
 constexpr int kN = 256;                          // motif-strand columns per B tile
-constexpr int kThreads = 256;                    // warp 0 MMA, 1-3 producers, 4-7 epilogue
+constexpr int kThreads = 384;                    // warp 0 MMA, 1-3 producers, 4-11 epilogue (EW = 4 or 8 of them work)
 
 __device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t) __cvta_generic_to_shared(p); }
 
@@ -72,6 +73,16 @@ __device__ __forceinline__ uint64_t make_desc(uint32_t addr, uint32_t lbo, uint3
                    "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31]) \
                  : "r"(addr))
 
+#define LD32P(r, addr)                                                                              \
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.pack::16b.x32.b32 "                                \
+                 "{%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,"                          \
+                 "%16,%17,%18,%19,%20,%21,%22,%23,%24,%25,%26,%27,%28,%29,%30,%31}, [%32];"        \
+                 : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),  \
+                   "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), \
+                   "=r"(r[16]), "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), \
+                   "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31]) \
+                 : "r"(addr))
+
 struct Params {
     const uint32_t *codes;   // 2-bit codes, 16 per word
     const uint32_t *nmask;   // 1 bit per base
@@ -81,21 +92,23 @@ struct Params {
     unsigned long long *count;   // per CTA: accumulators with sign bit clear
     float *dump;                 // CTA 0, tile 0: [shift][nt][128][256]
     int epilogue;                // 0: skip TMEM reads (MMA pace only)
+    long long *stamp;            // cta 0, units 64..79: [mma issued, epi wait start, epi woke, ld done]
+    long long *prof;             // [cta][8]: mma_wait_empty, mma_issue, epi_wait_full, epi_ld, epi_proc, total
 };
 
-template <int KS>
+template <int KS, int NB, bool H = false>
 __global__ void __launch_bounds__(kThreads, 1) tc_kernel(const Params P) {
     extern __shared__ __align__(1024) uint8_t smem[];
     uint8_t *s_stream = smem;                                   // kSlots * kSlotBytes
     uint8_t *s_b = smem + ((kSlots * kSlotBytes + 1023) & ~1023);  // nt * KS * 8192
-    __shared__ uint64_t bar_stream_full[kSlots], bar_stream_empty[kSlots], bar_tmem_full[2], bar_tmem_empty[2];
+    __shared__ uint64_t bar_stream_full[kSlots], bar_stream_empty[kSlots], bar_tmem_full[8], bar_tmem_empty[8];
     __shared__ uint32_t s_tmem_base;
     __shared__ unsigned long long s_count;
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     if (threadIdx.x == 0) {
         for (int i = 0; i < kSlots; i++) { mbar_init(&bar_stream_full[i], 3); mbar_init(&bar_stream_empty[i], 1); }
-        for (int i = 0; i < 2; i++) { mbar_init(&bar_tmem_full[i], 1); mbar_init(&bar_tmem_empty[i], 4); }
+        for (int i = 0; i < 8; i++) { mbar_init(&bar_tmem_full[i], 1); mbar_init(&bar_tmem_empty[i], NB == 256 ? 8 : 4); }
         s_count = 0;
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
@@ -117,33 +130,43 @@ __global__ void __launch_bounds__(kThreads, 1) tc_kernel(const Params P) {
     const uint32_t tmem = s_tmem_base;
     const int T = P.tiles_per_cta, NT = P.nt;
     // idesc: D = F32 (1 << 4), A = B = E4M3 (0), K-major both, N = 256 (>> 3 at bit 17), M = 128 (>> 4 at bit 24)
-    const uint32_t idesc = (1u << 4) | ((uint32_t) (kN >> 3) << 17) | ((uint32_t) (128 >> 4) << 24);
+    const uint32_t idesc = (H ? 0u : (1u << 4)) | ((uint32_t) (NB >> 3) << 17) | ((uint32_t) (128 >> 4) << 24);
+    constexpr int SUBS = 256 / NB;    // sub-units (TMEM buffers) per 256-column unit
 
     if (warp == 0) {
         if (lane == 0) {
             uint32_t u = 0;
+            long long t_mw = 0, t_sw = 0, t_all = clock64();
             for (int it = 0; it < T; it++) {
                 const int slot = it % kSlots;
+                long long c1 = clock64();
                 mbar_wait(&bar_stream_full[slot], (it / kSlots) & 1);
+                t_sw += clock64() - c1;
                 asm volatile("tcgen05.fence::after_thread_sync;");
                 const uint32_t a_base = smem_u32(s_stream + slot * kSlotBytes);
                 for (int s = 0; s < 4; s++) {
                     for (int nt = 0; nt < NT; nt++, u++) {
-                        const uint32_t buf = u & 1;
-                        mbar_wait(&bar_tmem_empty[buf], ((u >> 1) & 1) ^ 1);
-                        asm volatile("tcgen05.fence::after_thread_sync;");
                         const uint32_t b_base = smem_u32(s_b + nt * KS * 8192);
+                        for (int sub = 0; sub < SUBS; sub++) {
+                            const uint32_t buf = (u & 1) * SUBS + sub;
+                            long long c0 = clock64();
+                            mbar_wait(&bar_tmem_empty[buf], ((u >> 1) & 1) ^ 1);
+                            t_mw += clock64() - c0;
+                            asm volatile("tcgen05.fence::after_thread_sync;");
 #pragma unroll
-                        for (int ks = 0; ks < KS; ks++) {
-                            const uint64_t ad = make_desc(a_base + s * kStreamBytes + ks * 32, 16, 128);
-                            const uint64_t bd = make_desc(b_base + ks * 8192, 4096, 128);
-                            umma_f8(tmem + buf * 256, ad, bd, idesc, ks > 0);
+                            for (int ks = 0; ks < KS; ks++) {
+                                const uint64_t ad = make_desc(a_base + s * kStreamBytes + ks * 32, 16, 128);
+                                const uint64_t bd = make_desc(b_base + ks * 8192 + sub * NB * 16, 4096, 128);
+                                umma_f8(tmem + buf * NB, ad, bd, idesc, ks > 0);
+                            }
+                            umma_commit(&bar_tmem_full[buf]);
+                            if (P.prof && u >= 64 && u < 64 + 16 && sub == 0 && blockIdx.x == 0) P.stamp[(u - 64) * 4 + 0] = clock64();
                         }
-                        umma_commit(&bar_tmem_full[buf]);
                     }
                 }
                 umma_commit(&bar_stream_empty[slot]);
             }
+            if (P.prof) { P.prof[blockIdx.x * 8 + 0] = t_mw; P.prof[blockIdx.x * 8 + 1] = t_sw; P.prof[blockIdx.x * 8 + 5] = clock64() - t_all; }
         }
         __syncwarp();
     } else if (warp < 4) {
@@ -170,46 +193,89 @@ __global__ void __launch_bounds__(kThreads, 1) tc_kernel(const Params P) {
         const int q = warp & 3;
         unsigned long long cnt = 0;
         uint32_t u = 0;
+        long long t_ew = 0, t_ld = 0, t_pr = 0;
         for (int it = 0; it < T; it++) {
             for (int s = 0; s < 4; s++) {
                 for (int nt = 0; nt < NT; nt++, u++) {
-                    const uint32_t buf = u & 1;
-                    mbar_wait(&bar_tmem_full[buf], (u >> 1) & 1);
-                    asm volatile("tcgen05.fence::after_thread_sync;");
-                    if (P.epilogue) {
-                        const uint32_t taddr = tmem + buf * 256 + ((uint32_t) (q * 32) << 16);
-                        const bool dump = (blockIdx.x == 0 && it == 0 && P.dump != nullptr);
+                    const int h = (warp - 4) >> 2;
+                    const bool dump = (blockIdx.x == 0 && it == 0 && P.dump != nullptr);
 #pragma unroll 1
-                        for (int c = 0; c < 256; c += 64) {
-                            uint32_t r0[32], r1[32];
-                            LD32(r0, taddr + c);
-                            LD32(r1, taddr + c + 32);
-                            asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+                    for (int j = 0; j < (NB == 256 ? 1 : 128 / NB); j++) {
+                        const int sub = NB == 256 ? 0 : h * (128 / NB) + j;
+                        const uint32_t buf = (u & 1) * SUBS + sub;
+                        long long c0 = clock64();
+                        mbar_wait(&bar_tmem_full[buf], (u >> 1) & 1);
+                        t_ew += clock64() - c0;
+                        asm volatile("tcgen05.fence::after_thread_sync;");
+                        const uint32_t taddr = tmem + buf * NB + (NB == 256 ? h * 128 : 0) + ((uint32_t) (q * 32) << 16);
+                        const long long c1 = clock64();
+                        uint32_t r0[32], r1[32], r2[32], r3[32];
+                        if (H) {
+                            // f16 accumulators: one 16-bit value per TMEM column, two columns packed per register
+                            LD32P(r0, taddr);
+                            LD32P(r1, taddr + 64);
+                            for (int jj = 0; jj < 32; jj++) { r2[jj] = 0x80008000u; r3[jj] = 0x80008000u; }
+                        } else {
+                        LD32(r0, taddr);
+                        LD32(r1, taddr + 32);
+                        if (NB >= 128) { LD32(r2, taddr + 64); LD32(r3, taddr + 96); }
+                        }
+                        asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+                        // force a true dependency on the loaded data before reading the clock
+                        uint32_t dep = r0[0] ^ r1[31] ^ (NB >= 128 ? (r2[0] ^ r3[31]) : 0u);
+                        asm volatile("" :: "r"(dep) : "memory");
+                        const long long c2 = clock64() + (dep == 0x12345u);
+                        t_ld += c2 - c1;
+                        asm volatile("tcgen05.fence::before_thread_sync;");
+                        __syncwarp();
+                        if (lane == 0) mbar_arrive(&bar_tmem_empty[buf]);
+                        if (warp == 4 && lane == 0 && P.prof && u >= 64 && u < 64 + 16 && j == 0 && blockIdx.x == 0) {
+                            P.stamp[(u - 64) * 4 + 1] = c0; P.stamp[(u - 64) * 4 + 2] = c1; P.stamp[(u - 64) * 4 + 3] = c2; }
+                        if (P.epilogue) {
                             uint32_t all = 0xffffffffu;
 #pragma unroll
-                            for (int j = 0; j < 32; j += 2) all &= r0[j] & r0[j + 1];
+                            for (int jj = 0; jj < 32; jj += 2) all &= r0[jj] & r0[jj + 1];
 #pragma unroll
-                            for (int j = 0; j < 32; j += 2) all &= r1[j] & r1[j + 1];
-                            if (!(all & 0x80000000u)) {   // some accumulator is >= 0
+                            for (int jj = 0; jj < 32; jj += 2) all &= r1[jj] & r1[jj + 1];
+                            if (NB >= 128) {
 #pragma unroll
-                                for (int j = 0; j < 32; j++) cnt += (r0[j] >> 31) ^ 1u;
+                                for (int jj = 0; jj < 32; jj += 2) all &= r2[jj] & r2[jj + 1];
 #pragma unroll
-                                for (int j = 0; j < 32; j++) cnt += (r1[j] >> 31) ^ 1u;
+                                for (int jj = 0; jj < 32; jj += 2) all &= r3[jj] & r3[jj + 1];
+                            }
+                            if ((all & (H ? 0x80008000u : 0x80000000u)) != (H ? 0x80008000u : 0x80000000u)) {   // some accumulator is >= 0
+#pragma unroll
+                                for (int jj = 0; jj < 32; jj++) cnt += ((r0[jj] >> 31) ^ 1u) + ((r1[jj] >> 31) ^ 1u);
+                                if (NB >= 128) {
+#pragma unroll
+                                    for (int jj = 0; jj < 32; jj++) cnt += ((r2[jj] >> 31) ^ 1u) + ((r3[jj] >> 31) ^ 1u);
+                                }
                             }
                             if (dump) {
-                                float *o = P.dump + (((size_t) (s * NT + nt) * 128) + q * 32 + lane) * 256 + c;
+                                float *o = P.dump + (((size_t) (s * NT + nt) * 128) + q * 32 + lane) * 256 + sub * NB + (NB == 256 ? h * 128 : 0);
 #pragma unroll
-                                for (int j = 0; j < 32; j++) { o[j] = __uint_as_float(r0[j]); o[32 + j] = __uint_as_float(r1[j]); }
+                                if (H) {
+                                    for (int jj = 0; jj < 32; jj++) {
+                                        o[2 * jj] = __half2float(__ushort_as_half((unsigned short) (r0[jj] & 0xffff)));
+                                        o[2 * jj + 1] = __half2float(__ushort_as_half((unsigned short) (r0[jj] >> 16)));
+                                        o[64 + 2 * jj] = __half2float(__ushort_as_half((unsigned short) (r1[jj] & 0xffff)));
+                                        o[64 + 2 * jj + 1] = __half2float(__ushort_as_half((unsigned short) (r1[jj] >> 16)));
+                                    }
+                                } else {
+                                for (int jj = 0; jj < 32; jj++) { o[jj] = __uint_as_float(r0[jj]); o[32 + jj] = __uint_as_float(r1[jj]); }
+                                }
+                                if (NB >= 128 && !H) {
+#pragma unroll
+                                    for (int jj = 0; jj < 32; jj++) { o[64 + jj] = __uint_as_float(r2[jj]); o[96 + jj] = __uint_as_float(r3[jj]); }
+                                }
                             }
                         }
                     }
-                    asm volatile("tcgen05.fence::before_thread_sync;");
-                    __syncwarp();
-                    if (lane == 0) mbar_arrive(&bar_tmem_empty[buf]);
                 }
             }
         }
         atomicAdd(&s_count, cnt);
+        if (P.prof && warp == 4 && lane == 0) { P.prof[blockIdx.x * 8 + 2] = t_ew; P.prof[blockIdx.x * 8 + 3] = t_ld; }
     }
     asm volatile("tcgen05.fence::before_thread_sync;");
     __syncthreads();
@@ -235,7 +301,7 @@ static uint8_t e4m3_encode_floor(float x) {
     return best;
 }
 
-template <int KS>
+template <int KS, int NB, bool H = false>
 static void run(int nt, int tiles_per_cta, bool verify, int wmode = 0) {
     const int L = 8 * KS;
     const int n_cta = 148;
@@ -283,21 +349,29 @@ static void run(int nt, int tiles_per_cta, bool verify, int wmode = 0) {
     CK(cudaMemcpy(d_nmask, nmask.data(), nmask.size() * 4, cudaMemcpyHostToDevice));
     CK(cudaMemcpy(d_bt, bt.data(), bt.size(), cudaMemcpyHostToDevice));
     CK(cudaMemset(d_dump, 0, dump_elems * 4));
-    Params P{d_codes, d_nmask, d_bt, tiles_per_cta, nt, d_count, verify ? d_dump : nullptr, 1};
+    long long *d_prof; CK(cudaMalloc(&d_prof, n_cta * 8 * 8)); CK(cudaMemset(d_prof, 0, n_cta * 8 * 8));
+    long long *d_stamp; CK(cudaMalloc(&d_stamp, 64 * 8)); CK(cudaMemset(d_stamp, 0, 64 * 8));
+    Params P{d_codes, d_nmask, d_bt, tiles_per_cta, nt, d_count, verify ? d_dump : nullptr, 1, d_stamp, d_prof};
     const size_t smem = ((kSlots * kSlotBytes + 1023) & ~1023) + (size_t) nt * KS * 8192 + 1024;
-    CK(cudaFuncSetAttribute(tc_kernel<KS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem));
+    CK(cudaFuncSetAttribute(tc_kernel<KS, NB, H>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem));
     cudaEvent_t e0, e1; CK(cudaEventCreate(&e0)); CK(cudaEventCreate(&e1));
     for (int mode = 1; mode >= 0; mode--) {
         P.epilogue = mode;
-        tc_kernel<KS><<<n_cta, kThreads, smem>>>(P);   // warm-up
+        tc_kernel<KS, NB, H><<<n_cta, kThreads, smem>>>(P);   // warm-up
         CK(cudaDeviceSynchronize());
         CK(cudaEventRecord(e0));
-        tc_kernel<KS><<<n_cta, kThreads, smem>>>(P);
+        tc_kernel<KS, NB, H><<<n_cta, kThreads, smem>>>(P);
         CK(cudaEventRecord(e1));
         CK(cudaDeviceSynchronize());
         float ms = 0; CK(cudaEventElapsedTime(&ms, e0, e1));
         const double units = (double) n_cta * tiles_per_cta * 4 * nt;
         const double macs = units * 128.0 * 256.0 * 32.0 * KS;
+        { long long hp[8]; CK(cudaMemcpy(hp, d_prof, sizeof(hp), cudaMemcpyDeviceToHost));
+          printf("   per unit (cta0, clk): mma_wait_tmem_empty %.0f  mma_wait_stream %.0f  epi_wait_full %.0f  epi_ld %.0f  total %.0f\n",
+                 hp[0] / (units / n_cta), hp[1] / (units / n_cta), hp[2] / (units / n_cta), hp[3] / (units / n_cta), hp[5] / (units / n_cta)); }
+        if (mode == 1 && !verify) { long long st[64]; CK(cudaMemcpy(st, d_stamp, sizeof(st), cudaMemcpyDeviceToHost));
+          printf("   unit: mma_issued  epi_wait_start  epi_woke  ld_done (clk, relative to unit 64's issue)\n");
+          for (int i = 0; i < 8; i++) printf("   %2d: %6lld %6lld %6lld %6lld\n", i, st[i*4]-st[0], st[i*4+1]-st[0], st[i*4+2]-st[0], st[i*4+3]-st[0]); }
         printf("KS=%d (L=%d) nt=%d tiles/cta=%d epilogue=%d: %.3f ms, %.1f TMAC/s (%.2f PFLOP/s), %.1f ns/unit/SM, "
                "%.2f G window*motif-strand/s\n", KS, L, nt, tiles_per_cta, mode, ms, macs / ms / 1e9, 2 * macs / ms / 1e12,
                ms * 1e6 / (units / n_cta), units * 128 * 256 / ms / 1e6);
@@ -305,7 +379,7 @@ static void run(int nt, int tiles_per_cta, bool verify, int wmode = 0) {
     if (verify) {
         std::vector<unsigned long long> cnt(n_cta);
         P.epilogue = 1;
-        tc_kernel<KS><<<n_cta, kThreads, smem>>>(P);
+        tc_kernel<KS, NB, H><<<n_cta, kThreads, smem>>>(P);
         CK(cudaDeviceSynchronize());
         CK(cudaMemcpy(cnt.data(), d_count, n_cta * 8, cudaMemcpyDeviceToHost));
         std::vector<float> dump(dump_elems);
@@ -322,24 +396,27 @@ static void run(int nt, int tiles_per_cta, bool verify, int wmode = 0) {
             return acc;
         };
         double max_pos = 0, max_neg = 0, max_mag = 0; long long inexact = 0;
+        float max_herr = 0;
         long long bad = 0;
         for (int s = 0; s < 4; s++) for (int t = 0; t < nt; t++) for (int r = 0; r < 128; r++) for (int n = 0; n < kN; n++) {
             const float want = score(4 * r + s, t, n), got = dump[(((size_t) (s * nt + t) * 128) + r) * 256 + n];
             if (wmode == 1) {
                 const double wd = score_d(4 * r + s, t, n);
-                const double err = (double) got - wd;
+                double err = (double) got - wd;
+                if (H) { int ex; frexp(fabs(wd) > 6e-5 ? fabs(wd) : 6e-5, &ex); err /= ldexp(1.0, ex - 11); }   // in fp16 ulps of the exact sum
                 if (err > max_pos) max_pos = err;
                 if (err < max_neg) max_neg = err;
                 if (fabs(wd) > max_mag) max_mag = fabs(wd);
                 if ((double) (float) wd != (double) got) inexact++;
                 continue;
             }
+            if (H) { if (fabsf(want - got) > max_herr) max_herr = fabsf(want - got); continue; }
             if (want != got) { if (bad < 5) printf("  MISMATCH s=%d t=%d r=%d n=%d want %g got %g\n", s, t, r, n, want, got); bad++; }
         }
-        printf("  dump check: %lld mismatches of %zu\n", bad, dump_elems);
+        printf("  dump check: %lld mismatches of %zu (f16 accumulators: max abs err %g)\n", bad, dump_elems, max_herr);
         if (wmode == 1) { printf("  adversarial: err range [%g, %g], max |sum| %g, results != RN(exact): %lld\n", max_neg, max_pos, max_mag, inexact); }
         long long cbad = 0;
-        for (int cta = 0; cta < (wmode ? 0 : 4); cta++) {
+        for (int cta = 0; cta < ((wmode || H) ? 0 : 4); cta++) {
             unsigned long long want = 0;
             const long long start = (long long) cta * tiles_per_cta * kTileBases;
             for (long long p = start; p < start + (long long) tiles_per_cta * kTileBases; p++)
@@ -355,10 +432,9 @@ static void run(int nt, int tiles_per_cta, bool verify, int wmode = 0) {
 }
 
 int main(int argc, char **argv) {
-    run<1>(1, 8, true);
-    run<4>(3, 8, true);
-    run<1>(1, 8, true, 1);
-    run<2>(2, 8, true, 1);
-    run<4>(3, 8, true, 1);
+    run<1, 256, true>(3, 8, true, 1);
+    run<2, 256, true>(3, 8, true, 1);
+    run<3, 256, true>(3, 8, true, 1);
+    run<4, 256, true>(3, 8, true, 1);
     return 0;
 }

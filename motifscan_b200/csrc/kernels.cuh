@@ -42,7 +42,7 @@ __global__ void __launch_bounds__(256)
 encode_pack_kernel(const uint8_t *__restrict__ ascii, const int64_t *__restrict__ seq_off,
                    const int64_t *__restrict__ poff, const int32_t *__restrict__ len,
                    int64_t n_seqs, int64_t n_blocks, uint32_t *__restrict__ codes,
-                   uint32_t *__restrict__ nmask) {
+                   uint32_t *__restrict__ nmask, int32_t *__restrict__ blk_seq) {
     int64_t b = (int64_t) blockIdx.x * blockDim.x + threadIdx.x;
     if (b >= n_blocks) return;
     int64_t p = b * kPadBases;
@@ -68,6 +68,7 @@ encode_pack_kernel(const uint8_t *__restrict__ ascii, const int64_t *__restrict_
     codes[2 * b] = lo;
     codes[2 * b + 1] = hi;
     nmask[b] = mask;
+    blk_seq[b] = (int32_t) s;
 }
 
 // Parity accessor: packed -> int8 codes laid out like the ASCII input.
@@ -280,16 +281,30 @@ __device__ __forceinline__ void test_and_emit(const ExactParams &E, uint32_t m, 
     }
 }
 
+// `col_info` == nullptr: keys carry (sorted motif index, position, strand) and were validated by
+// the table prefilter.  Otherwise they are the tensor-core prefilter's raw keys (tile * 256 +
+// column, position): decode the column and drop windows that run past their sequence.
 __global__ void __launch_bounds__(256)
 exact_candidates_kernel(ExactParams E, const uint64_t *__restrict__ cand, int64_t n_cand,
-                        const int32_t *__restrict__ order) {
+                        const int32_t *__restrict__ order, const uint32_t *__restrict__ col_info) {
     int64_t i = (int64_t) blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n_cand) return;
     const uint64_t k = cand[i];
-    const uint32_t m = (uint32_t) __ldg(order + key_motif(k));
     const int64_t p = key_pos(k);
-    const int rev = (int) key_rev(k);
+    uint32_t sorted = key_motif(k);
+    int rev = (int) key_rev(k);
+    if (col_info) {
+        const uint32_t info = __ldg(col_info + sorted);
+        if (info == 0xffffffffu) return;   // padding column of a tile
+        sorted = info >> 1;
+        rev = (int) (info & 1u);
+    }
+    const uint32_t m = (uint32_t) __ldg(order + sorted);
     const int L = __ldg(E.mot.len + m);
+    if (col_info) {
+        const int64_t s = __ldg(E.seq.blk_seq + (p >> 5));
+        if (p - __ldg(E.seq.poff + s) + L > (int64_t) __ldg(E.seq.len + s)) return;   // cscore.c:340
+    }
     const double *pw = E.mot.pwm + 4 * (int64_t) __ldg(E.mot.col_off + m);
     test_and_emit(E, m, p, rev, exact_raw(E.seq, pw, L, p, rev));
 }

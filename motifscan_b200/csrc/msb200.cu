@@ -17,6 +17,7 @@
 #include <numeric>
 
 #include "kernels.cuh"
+#include "prefilter_tc.cuh"
 
 namespace msb {
 
@@ -96,6 +97,18 @@ struct TableSet {
     DevBuf d_tab, d_order, d_slow;
 };
 
+// Tensor-core prefilter tables (prefilter_tc.cuh).
+struct TcTableSet {
+    bool valid = false;
+    uint64_t cutoff_version = 0;
+    std::vector<int32_t> order;       // sorted index -> motif id (fast motifs only, by K steps)
+    std::vector<int32_t> slow;
+    std::vector<TcBatch> batches;
+    int32_t lmax_fast = 0;
+    int any_zero_hit = 0;
+    DevBuf d_btab, d_col_info, d_len, d_order, d_slow;
+};
+
 struct msb_motifs {
     msb_ctx *ctx = nullptr;
     int32_t n = 0;
@@ -107,6 +120,7 @@ struct msb_motifs {
     int32_t lmax = 0;
     DevBuf d_pwm, d_col_off, d_len, d_cutoff, d_max_raw;
     TableSet tables[4];
+    TcTableSet tc_tables[4];
     MotifView view() const {
         MotifView v;
         v.pwm = d_pwm.as<double>();
@@ -124,13 +138,14 @@ struct msb_seqs {
     int64_t n = 0, total_bp = 0, total_packed = 0;
     int32_t min_len = 0;
     std::vector<int64_t> seq_off, poff;
-    DevBuf d_codes, d_nmask, d_poff, d_len, d_seq_off;
+    DevBuf d_codes, d_nmask, d_poff, d_len, d_seq_off, d_blk_seq;
     SeqView view() const {
         SeqView v;
         v.codes = d_codes.as<uint32_t>();
         v.nmask = d_nmask.as<uint32_t>();
         v.poff = d_poff.as<int64_t>();
         v.len = d_len.as<int32_t>();
+        v.blk_seq = d_blk_seq.as<int32_t>();
         v.n_seqs = n;
         v.total_packed = total_packed;
         return v;
@@ -248,6 +263,7 @@ int msb_ctx_create(int device, void *stream, msb_ctx **out) {
     }
     cudaFuncSetAttribute(prefilter_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) ctx->smem_optin);
     cudaFuncSetAttribute(prefilter_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) ctx->smem_optin);
+    cudaFuncSetAttribute(prefilter_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kTcSmemBytes);
     *out = ctx;
     return MSB_OK;
 }
@@ -388,6 +404,9 @@ int msb_motifs_destroy(msb_motifs *M) {
     cudaStreamSynchronize(M->ctx->stream);
     for (DevBuf *b : {&M->d_pwm, &M->d_col_off, &M->d_len, &M->d_cutoff, &M->d_max_raw}) b->release();
     for (auto &t : M->tables) { t.d_tab.release(); t.d_order.release(); t.d_slow.release(); }
+    for (auto &t : M->tc_tables) {
+        t.d_btab.release(); t.d_col_info.release(); t.d_len.release(); t.d_order.release(); t.d_slow.release();
+    }
     delete M;
     return MSB_OK;
 }
@@ -437,6 +456,7 @@ int msb_seqs_from_ascii(msb_ctx *ctx, int64_t n_seqs, const char *bytes, const i
     // starting at the word of a thread's first window.
     if ((rc = S->d_codes.ensure((size_t) (2 * n_blocks + 8) * 4)) != MSB_OK ||
         (rc = S->d_nmask.ensure((size_t) (n_blocks + 4) * 4)) != MSB_OK ||
+        (rc = S->d_blk_seq.ensure((size_t) std::max<int64_t>(n_blocks, 1) * 4)) != MSB_OK ||
         (rc = S->d_poff.ensure((size_t) (n_seqs + 1) * 8)) != MSB_OK ||
         (rc = S->d_len.ensure((size_t) std::max<int64_t>(n_seqs, 1) * 4)) != MSB_OK ||
         (rc = S->d_seq_off.ensure((size_t) (n_seqs + 1) * 8)) != MSB_OK ||
@@ -459,7 +479,7 @@ int msb_seqs_from_ascii(msb_ctx *ctx, int64_t n_seqs, const char *bytes, const i
         const int64_t grid = (n_blocks + 255) / 256;
         encode_pack_kernel<<<(unsigned) grid, 256, 0, st>>>(
             ctx->ascii.as<uint8_t>(), S->d_seq_off.as<int64_t>(), S->d_poff.as<int64_t>(), S->d_len.as<int32_t>(),
-            n_seqs, n_blocks, S->d_codes.as<uint32_t>(), S->d_nmask.as<uint32_t>());
+            n_seqs, n_blocks, S->d_codes.as<uint32_t>(), S->d_nmask.as<uint32_t>(), S->d_blk_seq.as<int32_t>());
         step(cudaGetLastError());
     }
     step(cudaEventRecord(ctx->ev[2], st));
@@ -501,7 +521,7 @@ int msb_seqs_destroy(msb_seqs *S) {
     if (!S) return MSB_OK;
     cudaSetDevice(S->ctx->device);
     cudaStreamSynchronize(S->ctx->stream);
-    for (DevBuf *b : {&S->d_codes, &S->d_nmask, &S->d_poff, &S->d_len, &S->d_seq_off}) b->release();
+    for (DevBuf *b : {&S->d_codes, &S->d_nmask, &S->d_poff, &S->d_len, &S->d_seq_off, &S->d_blk_seq}) b->release();
     delete S;
     return MSB_OK;
 }
@@ -673,6 +693,169 @@ static int ensure_tables(msb_ctx *ctx, msb_motifs *M, int strand, TableSet **out
     return MSB_OK;
 }
 
+// ------------------------------------------------------------------------------------------------
+// Tensor-core prefilter tables (prefilter_tc.cuh).
+//
+// For one strand of motif m let V[b][c] be its PWM (forward: M[b][c], cscore.c:348; reverse:
+// M[3-b][L-1-c], cscore.c:351), colmax_c = max_b V[b][c] and d[b][c] = colmax_c - V[b][c] >= 0 the
+// "deficit" of base b at column c, so that  raw = sum_c colmax_c - sum_c d[b_c][c].  With the
+// conservative raw threshold T of build_motif_table, a window the reference can accept has
+//     sum_c d[b_c][c]  <=  D = sum_c colmax_c - T (+ slack for the rounding of these host sums).
+// The stored e4m3 entries are  e[b][c] = RU( beta - s * d[b][c] )  (rounded towards +inf, floored
+// at -448), with beta an e4m3 value, C = L * beta and s = (C - C/64) / D.  Then for every window
+// with sum d <= D:   sum_c e >= C - s * sum d >= C/64 > 5,  more than the tensor core's f16
+// accumulation can lose (prefilter_tc.cuh), so the accumulator's sign bit is clear: the candidates
+// are a superset of the reference's hits.
+// ------------------------------------------------------------------------------------------------
+static float e4m3_value(int v) {
+    const int e = (v >> 3) & 15, m = v & 7;
+    const float mag = e == 0 ? std::ldexp((float) m / 8.f, -6) : std::ldexp(1.f + (float) m / 8.f, e - 7);
+    return (v & 0x80) ? -mag : mag;
+}
+// smallest e4m3 value >= x, saturating at +-448; never the byte 0x80 (-0)
+static uint8_t e4m3_round_up(double x) {
+    if (!(x > -448.0)) return 0xFE;  // -448 (also NaN -> most negative: cannot create candidates)
+    if (x > 448.0) return 0x7E;
+    if (x <= 0) {
+        // largest magnitude <= |x| among the negatives, i.e. round towards zero
+        int best = 0x00;
+        for (int v = 0; v < 0x7F; v++)
+            if ((double) e4m3_value(v) <= -x) best = v; else break;
+        return best == 0 ? 0x00 : (uint8_t) (0x80 | best);
+    }
+    for (int v = 0; v < 0x7F; v++)
+        if ((double) e4m3_value(v) >= x) return (uint8_t) v;
+    return 0x7E;
+}
+
+static inline size_t tc_byte(int ks_idx, int col, int k_in_step) {
+    return (size_t) ks_idx * kTcUnitBytes + (size_t) (k_in_step >> 4) * 4096 + (size_t) col * 16 + (size_t) (k_in_step & 15);
+}
+
+static void tc_fill_never(uint8_t *tile, int col) {
+    for (int b = 0; b < 4; b++) tile[tc_byte(0, col, b)] = 0xFE;  // any ACGT base at offset 0: -448
+}
+
+static void tc_fill_column(const msb_motifs *M, int32_t m, int rev, uint8_t *tile, int col) {
+    const int L = M->lens[m];
+    const double *mat = M->mats.data() + M->mat_off[m];
+    auto V = [&](int b, int c) { return rev ? mat[(size_t) (3 - b) * L + (L - 1 - c)] : mat[(size_t) b * L + c]; };
+    const double max_raw = M->max_raw[m];
+    const double cutoff = M->cutoffs[m];
+    if (!(max_raw > 0) || std::isnan(cutoff) || (std::isinf(cutoff) && cutoff > 0)) { tc_fill_never(tile, col); return; }
+    double cms = 0, abs_sum = 0;
+    double colmax[kMaxFastLen];
+    for (int c = 0; c < L; c++) {
+        double mx = -INFINITY, a = 0;
+        for (int b = 0; b < 4; b++) { mx = std::max(mx, V(b, c)); a = std::max(a, std::fabs(V(b, c))); }
+        colmax[c] = mx;
+        cms += mx;
+        abs_sum += a;
+    }
+    double D;
+    if (std::isinf(cutoff)) {
+        D = INFINITY;  // -inf: every window with a finite score is a site
+    } else {
+        const double T = max_raw * (cutoff - 1e-10) - 1e-12 * (max_raw * (std::fabs(cutoff) + 1.0) + abs_sum);
+        D = cms - T;
+        D += 1e-12 * (std::fabs(cms) + std::fabs(T) + abs_sum);
+        if (D < 0) { tc_fill_never(tile, col); return; }  // even the best window is below the cutoff
+    }
+    // beta: an e4m3 value near 384 / L (exactly representable, so the all-best window sums to C)
+    const double beta = (double) e4m3_value(e4m3_round_up(384.0 / L));
+    const double C = beta * L;
+    double s = std::isinf(D) ? 0.0 : (C - C / 64.0) / std::max(D, 1e-300);
+    if (!(s < 1e30)) s = 1e30;
+    for (int c = 0; c < L; c++)
+        for (int b = 0; b < 4; b++) {
+            const double d = colmax[c] - V(b, c);
+            const double x = d > 0 ? beta - s * d : beta;
+            const int k = 4 * c + b;
+            tile[tc_byte(k >> 5, col, k & 31)] = e4m3_round_up(x);
+        }
+}
+
+static int ensure_tc_tables(msb_ctx *ctx, msb_motifs *M, int strand, TcTableSet **out) {
+    TcTableSet &T = M->tc_tables[strand];
+    if (T.valid && T.cutoff_version == M->cutoff_version) { *out = &T; return MSB_OK; }
+    T.valid = false;
+    T.order.clear();
+    T.slow.clear();
+    T.batches.clear();
+    T.lmax_fast = 0;
+    T.any_zero_hit = 0;
+    std::vector<int32_t> fast;
+    for (int32_t m = 0; m < M->n; m++) {
+        if (motif_is_fast(M, m)) fast.push_back(m);
+        else if (M->lens[m] >= 1) T.slow.push_back(m);
+    }
+    auto ksteps = [&](int32_t m) { return (M->lens[m] + 7) / 8; };
+    std::stable_sort(fast.begin(), fast.end(), [&](int32_t a, int32_t b) { return M->lens[a] < M->lens[b]; });
+    T.order = fast;
+    const int cols_per_motif = strand == 3 ? 2 : 1;
+    const int motifs_per_tile = kTcCols / cols_per_motif;
+    const size_t n_tiles = (fast.size() + motifs_per_tile - 1) / motifs_per_tile;
+    std::vector<uint32_t> col_info(std::max<size_t>(n_tiles, 1) * kTcCols, 0xffffffffu);
+    std::vector<int32_t> tc_len(std::max<size_t>(fast.size(), 1), 0);
+    std::vector<uint8_t> btab;
+    const uint32_t max_units = kTcMaxUnits;
+    TcBatch cur;
+    std::memset(&cur, 0, sizeof(cur));
+    uint32_t cur_units = 0;
+    for (size_t t = 0; t < n_tiles; t++) {
+        const size_t k0 = t * motifs_per_tile, k1 = std::min(fast.size(), k0 + motifs_per_tile);
+        int ks = 1;
+        for (size_t k = k0; k < k1; k++) ks = std::max(ks, ksteps(fast[k]));
+        if (cur.n_tiles == kTcMaxTiles || cur_units + ks > max_units) {
+            T.batches.push_back(cur);
+            std::memset(&cur, 0, sizeof(cur));
+            cur_units = 0;
+        }
+        if (cur.n_tiles == 0) { cur.b_off = (uint32_t) btab.size(); cur.first_tile = (uint32_t) t; }
+        cur.ks[cur.n_tiles] = (uint8_t) ks;
+        cur.unit_off[cur.n_tiles] = (uint8_t) cur_units;
+        cur.n_tiles++;
+        cur_units += ks;
+        cur.b_bytes = cur_units * kTcUnitBytes;
+        const size_t base = btab.size();
+        btab.resize(base + (size_t) ks * kTcUnitBytes, 0);
+        uint8_t *tile = btab.data() + base;
+        for (int col = 0; col < kTcCols; col++) {
+            const size_t k = k0 + (size_t) (col / cols_per_motif);
+            if (k >= k1) { tc_fill_never(tile, col); continue; }
+            const int32_t m = fast[k];
+            const int rev = strand == 3 ? (col & 1) : (strand == 2 ? 1 : 0);
+            tc_fill_column(M, m, rev, tile, col);
+            col_info[t * kTcCols + col] = ((uint32_t) k << 1) | (uint32_t) rev;
+        }
+        for (size_t k = k0; k < k1; k++) {
+            const int32_t m = fast[k];
+            tc_len[k] = M->lens[m];
+            T.lmax_fast = std::max(T.lmax_fast, M->lens[m]);
+            const double z = 0.0 / M->max_raw[m];
+            if (z - M->cutoffs[m] >= -1e-10) T.any_zero_hit = 1;
+        }
+    }
+    if (cur.n_tiles) T.batches.push_back(cur);
+    if (btab.empty()) btab.resize(16, 0);
+    MSB_TRY(T.d_btab.ensure(btab.size()));
+    MSB_TRY(T.d_col_info.ensure(col_info.size() * 4));
+    MSB_TRY(T.d_len.ensure(tc_len.size() * 4));
+    MSB_TRY(T.d_order.ensure(std::max<size_t>(fast.size() * 4, 16)));
+    MSB_TRY(T.d_slow.ensure(std::max<size_t>(T.slow.size() * 4, 16)));
+    cudaStream_t st = ctx->stream;
+    MSB_CUDA(cudaMemcpyAsync(T.d_btab.p, btab.data(), btab.size(), cudaMemcpyHostToDevice, st));
+    MSB_CUDA(cudaMemcpyAsync(T.d_col_info.p, col_info.data(), col_info.size() * 4, cudaMemcpyHostToDevice, st));
+    MSB_CUDA(cudaMemcpyAsync(T.d_len.p, tc_len.data(), tc_len.size() * 4, cudaMemcpyHostToDevice, st));
+    if (!fast.empty()) MSB_CUDA(cudaMemcpyAsync(T.d_order.p, fast.data(), fast.size() * 4, cudaMemcpyHostToDevice, st));
+    if (!T.slow.empty()) MSB_CUDA(cudaMemcpyAsync(T.d_slow.p, T.slow.data(), T.slow.size() * 4, cudaMemcpyHostToDevice, st));
+    MSB_CUDA(cudaStreamSynchronize(st));
+    T.cutoff_version = M->cutoff_version;
+    T.valid = true;
+    *out = &T;
+    return MSB_OK;
+}
+
 static int read_counters(msb_ctx *ctx) {
     MSB_CUDA(cudaMemcpyAsync(ctx->h_counters, ctx->counters.p, 4 * sizeof(unsigned long long),
                              cudaMemcpyDeviceToHost, ctx->stream));
@@ -704,15 +887,25 @@ static int launch_positions(msb_ctx *ctx, const ExactParams &E, const int64_t *p
     return MSB_OK;
 }
 
-static int g_prefilter_w = 4;  // windows per thread (4 or 8); overridable for experiments
+static int g_prefilter_w = 4;   // windows per thread of the table prefilter (4 or 8)
+static int g_prefilter_tc = 1;  // 1: tensor-core prefilter (prefilter_tc.cuh), 0: shared-memory table prefilter
 
 static int scan_device(msb_ctx *ctx, msb_motifs *M, const msb_seqs *S, int strand, int flags) {
     if (!ctx || !M || !S) { set_error("msb_scan: null argument"); return MSB_EINVAL; }
     if (strand < 1 || strand > 3) { set_error("msb_scan: strand must be 1, 2 or 3"); return MSB_EINVAL; }
     if (M->ctx != ctx || S->ctx != ctx) { set_error("msb_scan: motifs/seqs belong to another context"); return MSB_EINVAL; }
     MSB_CUDA(cudaSetDevice(ctx->device));
+    const bool use_tc = g_prefilter_tc != 0;
     TableSet *T = nullptr;
-    MSB_TRY(ensure_tables(ctx, M, strand, &T));
+    TcTableSet *TT = nullptr;
+    if (use_tc) MSB_TRY(ensure_tc_tables(ctx, M, strand, &TT));
+    else MSB_TRY(ensure_tables(ctx, M, strand, &T));
+    const int32_t n_fast = (int32_t) (use_tc ? TT->order.size() : T->order.size());
+    const int32_t n_slow = (int32_t) (use_tc ? TT->slow.size() : T->slow.size());
+    const int32_t *d_order = use_tc ? TT->d_order.as<int32_t>() : T->d_order.as<int32_t>();
+    const int32_t *d_slow = use_tc ? TT->d_slow.as<int32_t>() : T->d_slow.as<int32_t>();
+    const int32_t lmax_fast = use_tc ? TT->lmax_fast : T->lmax_fast;
+    const int any_zero_hit = use_tc ? TT->any_zero_hit : T->any_zero_hit;
     cudaStream_t st = ctx->stream;
     std::fill(ctx->c, ctx->c + MSB_C_COUNT, 0);
     ctx->last_sites = 0;
@@ -727,7 +920,7 @@ static int scan_device(msb_ctx *ctx, msb_motifs *M, const msb_seqs *S, int stran
     const MotifView mv = M->view();
 
     // ---- stage 1: prefilter ------------------------------------------------------------------
-    const double cells = (double) S->total_packed * (double) std::max<size_t>(T->order.size(), 1);
+    const double cells = (double) S->total_packed * (double) std::max<int32_t>(n_fast, 1);
     int64_t cand_cap = (int64_t) std::min<double>(std::max<double>(cells / 512.0, 1 << 20), (double) (1ll << 30));
     int64_t dirty_cap = std::max<int64_t>(1 << 16, S->total_packed / 64);
     if (ctx->cand.cap / 8 > (size_t) cand_cap) cand_cap = (int64_t) (ctx->cand.cap / 8);
@@ -738,6 +931,29 @@ static int scan_device(msb_ctx *ctx, msb_motifs *M, const msb_seqs *S, int stran
         MSB_TRY(ctx->cand.ensure((size_t) cand_cap * 8));
         MSB_TRY(ctx->dirty.ensure((size_t) dirty_cap * 8));
         MSB_CUDA(cudaMemsetAsync(ctx->counters.p, 0, 4 * sizeof(unsigned long long), st));
+        if (use_tc) {
+            TcParams P;
+            P.seq = sv;
+            P.btab = TT->d_btab.as<uint8_t>();
+            P.lmax_all = std::max(lmax_fast, 1);
+            P.any_zero_hit = any_zero_hit;
+            P.cand = ctx->cand.as<uint64_t>();
+            P.cand_cap = cand_cap;
+            P.dirty = ctx->dirty.as<int64_t>();
+            P.dirty_cap = dirty_cap;
+            P.counters = ctx->counters.as<unsigned long long>();
+            const int64_t n_ptiles = (S->total_packed + kTcTileBases - 1) / kTcTileBases;
+            const unsigned grid = (unsigned) std::min<int64_t>(ctx->sm_count, n_ptiles);
+            const size_t smem = kTcSmemBytes;  // > half an SM's shared memory: one CTA per SM, which owns the TMEM
+            for (size_t b = 0; b < TT->batches.size(); b++) {
+                P.batch = TT->batches[b];
+                P.emit_dirty = (b == 0);
+                prefilter_tc_kernel<<<grid, kTcThreads, smem, st>>>(P);
+                MSB_CUDA(cudaGetLastError());
+                ctx->c[MSB_C_LAUNCHES]++;
+                ctx->c[MSB_C_PREFILTER_LAUNCHES]++;
+            }
+        } else {
         PrefilterParams P;
         P.seq = sv;
         P.tab = T->d_tab.as<uint32_t>();
@@ -762,6 +978,7 @@ static int scan_device(msb_ctx *ctx, msb_motifs *M, const msb_seqs *S, int stran
             ctx->c[MSB_C_LAUNCHES]++;
             ctx->c[MSB_C_PREFILTER_LAUNCHES]++;
         }
+        }
         MSB_CUDA(cudaEventRecord(ctx->ev[1], st));
         MSB_TRY(read_counters(ctx));
         n_cand = (int64_t) ctx->h_counters[0];
@@ -777,7 +994,6 @@ static int scan_device(msb_ctx *ctx, msb_motifs *M, const msb_seqs *S, int stran
     ctx->c[MSB_C_DIRTY] = n_dirty;
 
     // ---- stage 2: exact fp64 re-score ----------------------------------------------------------
-    const int32_t n_fast = (int32_t) T->order.size(), n_slow = (int32_t) T->slow.size();
     int64_t hit_cap = std::max<int64_t>(n_cand + 1024, 1 << 16);
     if (n_dirty) hit_cap += std::min<int64_t>(n_dirty * 2 * std::max(n_fast, 1), 1 << 24);
     if (n_slow) hit_cap += 1 << 20;
@@ -797,14 +1013,14 @@ static int scan_device(msb_ctx *ctx, msb_motifs *M, const msb_seqs *S, int stran
         E.counters = ctx->counters.as<unsigned long long>();
         if (n_cand) {
             exact_candidates_kernel<<<(unsigned) ((n_cand + 255) / 256), 256, 0, st>>>(
-                E, ctx->cand.as<uint64_t>(), n_cand, T->d_order.as<int32_t>());
+                E, ctx->cand.as<uint64_t>(), n_cand, d_order, use_tc ? TT->d_col_info.as<uint32_t>() : nullptr);
             MSB_CUDA(cudaGetLastError());
             ctx->c[MSB_C_LAUNCHES]++;
         }
         if (n_dirty && n_fast)
-            MSB_TRY(launch_positions(ctx, E, ctx->dirty.as<int64_t>(), n_dirty, T->d_order.as<int32_t>(), n_fast));
+            MSB_TRY(launch_positions(ctx, E, ctx->dirty.as<int64_t>(), n_dirty, d_order, n_fast));
         if (n_slow)
-            MSB_TRY(launch_positions(ctx, E, nullptr, S->total_packed, T->d_slow.as<int32_t>(), n_slow));
+            MSB_TRY(launch_positions(ctx, E, nullptr, S->total_packed, d_slow, n_slow));
         MSB_CUDA(cudaEventRecord(ctx->ev[2], st));
         MSB_TRY(read_counters(ctx));
         n_hits = (int64_t) ctx->h_counters[2];
@@ -898,6 +1114,7 @@ extern "C" {
 
 int msb_set_option(const char *name, int value) {
     if (name && !std::strcmp(name, "prefilter_w") && (value == 4 || value == 8)) { g_prefilter_w = value; return MSB_OK; }
+    if (name && !std::strcmp(name, "prefilter_tc") && (value == 0 || value == 1)) { g_prefilter_tc = value; return MSB_OK; }
     set_error("msb_set_option: unknown option or value");
     return MSB_EINVAL;
 }

@@ -172,9 +172,9 @@ def test_zero_score_windows_hit_when_cutoff_allows(eng):
 
 
 def test_many_motifs_multiple_batches(eng):
-    """More motifs than fit one shared-memory batch (tables > 227 KB)."""
+    """More motifs than fit one shared-memory batch (> 24 tensor-core tile steps / > 227 KB of tables)."""
     rng = np.random.default_rng(11)
-    pwms = synth_pwms(rng, 900, lmin=6, lmax=30)
+    pwms = synth_pwms(rng, 2100, lmin=6, lmax=30)
     seqs = synth_seqs(rng, 24, 400, 600)
     cutoffs = cutoffs_for(pwms, seqs, 1e-3)
     ctx = eng.default_context(0)
@@ -254,12 +254,42 @@ def test_prefilter_w8_same_sites(eng):
     sset = eng.SequenceSet(ctx, seqs)
     expect = oracle.scan_arrays(pwms, cutoffs, seqs, 3, n_threads=8)
     try:
+        _lib.check(_lib.load().msb_set_option(b"prefilter_tc", 0))
         _lib.check(_lib.load().msb_set_option(b"prefilter_w", 8))
         res = eng.scan(ctx, motifs, sset, 3)
         assert_scan_equal(res, expect)
         res.close()
     finally:
         _lib.check(_lib.load().msb_set_option(b"prefilter_w", 4))
+        _lib.check(_lib.load().msb_set_option(b"prefilter_tc", 1))
+    sset.close(), motifs.close()
+
+
+@pytest.mark.parametrize("strand", [1, 2, 3])
+def test_table_and_tensor_prefilters_same_sites(eng, strand):
+    """The shared-memory table prefilter and the tensor-core prefilter (the default) are both
+    conservative: after the exact stage they give the oracle's sites, and the tensor-core one does
+    not flood the exact stage with candidates."""
+    from motifscan_b200 import _lib
+    rng = np.random.default_rng(150 + strand)
+    pwms = synth_pwms(rng, 300)
+    seqs = synth_seqs(rng, 150, 700, 1300, p_n=0.002, n_blocks=True)
+    cutoffs = cutoffs_for(pwms, seqs, 5e-4)
+    ctx = eng.default_context(0)
+    motifs = eng.MotifSet(ctx, pwms, cutoffs)
+    sset = eng.SequenceSet(ctx, seqs)
+    expect = oracle.scan_arrays(pwms, cutoffs, seqs, strand, n_threads=8)
+    cand = {}
+    try:
+        for tc in (0, 1):
+            _lib.check(_lib.load().msb_set_option(b"prefilter_tc", tc))
+            res = eng.scan(ctx, motifs, sset, strand)
+            assert_scan_equal(res, expect)
+            cand[tc] = ctx.counters()["candidates"]
+            res.close()
+    finally:
+        _lib.check(_lib.load().msb_set_option(b"prefilter_tc", 1))
+    assert cand[1] <= 3 * cand[0] + 1000, cand
     sset.close(), motifs.close()
 
 
