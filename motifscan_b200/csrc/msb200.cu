@@ -10,6 +10,8 @@
 
 #include <algorithm>
 #include <cmath>
+#include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <limits>
 #include <mutex>
@@ -263,7 +265,8 @@ int msb_ctx_create(int device, void *stream, msb_ctx **out) {
     }
     cudaFuncSetAttribute(prefilter_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) ctx->smem_optin);
     cudaFuncSetAttribute(prefilter_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) ctx->smem_optin);
-    cudaFuncSetAttribute(prefilter_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kTcSmemBytes);
+    cudaFuncSetAttribute(prefilter_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kTcSmemBytes);
+    cudaFuncSetAttribute(prefilter_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kTcSmemBytes);
     *out = ctx;
     return MSB_OK;
 }
@@ -888,6 +891,7 @@ static int launch_positions(msb_ctx *ctx, const ExactParams &E, const int64_t *p
 }
 
 static int g_prefilter_w = 4;   // windows per thread of the table prefilter (4 or 8)
+static int g_tc_prof = std::getenv("MSB_TC_PROF") ? 1 : 0;   // 1: print per-role cycle counters of the tensor-core prefilter to stderr
 static int g_prefilter_tc = 1;  // 1: tensor-core prefilter (prefilter_tc.cuh), 0: shared-memory table prefilter
 
 static int scan_device(msb_ctx *ctx, msb_motifs *M, const msb_seqs *S, int strand, int flags) {
@@ -942,16 +946,43 @@ static int scan_device(msb_ctx *ctx, msb_motifs *M, const msb_seqs *S, int stran
             P.dirty = ctx->dirty.as<int64_t>();
             P.dirty_cap = dirty_cap;
             P.counters = ctx->counters.as<unsigned long long>();
+            P.prof = nullptr;
+            DevBuf prof;
+            if (g_tc_prof) {
+                MSB_TRY(prof.ensure((size_t) (ctx->sm_count + 16) * 16 * 8));
+                MSB_CUDA(cudaMemsetAsync(prof.p, 0, (size_t) (ctx->sm_count + 16) * 16 * 8, st));
+                P.prof = prof.as<long long>();
+            }
             const int64_t n_ptiles = (S->total_packed + kTcTileBases - 1) / kTcTileBases;
             const unsigned grid = (unsigned) std::min<int64_t>(ctx->sm_count, n_ptiles);
             const size_t smem = kTcSmemBytes;  // > half an SM's shared memory: one CTA per SM, which owns the TMEM
             for (size_t b = 0; b < TT->batches.size(); b++) {
                 P.batch = TT->batches[b];
                 P.emit_dirty = (b == 0);
-                prefilter_tc_kernel<<<grid, kTcThreads, smem, st>>>(P);
+                if (g_tc_prof) prefilter_tc_kernel<true><<<grid, kTcThreads, smem, st>>>(P);
+                else prefilter_tc_kernel<false><<<grid, kTcThreads, smem, st>>>(P);
                 MSB_CUDA(cudaGetLastError());
                 ctx->c[MSB_C_LAUNCHES]++;
                 ctx->c[MSB_C_PREFILTER_LAUNCHES]++;
+            }
+            if (g_tc_prof) {
+                std::vector<long long> h((size_t) (ctx->sm_count + 16) * 16);
+                MSB_CUDA(cudaMemcpyAsync(h.data(), prof.p, h.size() * 8, cudaMemcpyDeviceToHost, st));
+                MSB_CUDA(cudaStreamSynchronize(st));
+                const long long *o = h.data();   // CTA 0 of the last batch
+                const double un = (double) std::max<long long>(o[4], 1);
+                fprintf(stderr, "[tc_prof] cta0: %lld units, %.0f clk/unit | issuer: wait stream %.0f, wait tmem_empty %.0f, issue %.0f | "
+                        "epilogue warp 4: wait stream %.0f, wait tmem_full %.0f, ld %.0f, process %.0f (clk/unit); "
+                        "units with a candidate %.3f, process there %.0f clk, elsewhere %.0f clk\n",
+                        o[4], o[0] / un, o[1] / un, o[2] / un, o[3] / un, o[11] / un, o[8] / un, o[9] / un, o[10] / un,
+                        o[14] / un, (double) o[13] / std::max<long long>(o[14], 1),
+                        (double) (o[10] - o[13]) / std::max<long long>(o[12] - o[14], 1));
+                const long long *tl = h.data() + (size_t) grid * 16;
+                for (int i = 0; i < 12; i++)
+                    fprintf(stderr, "[tc_prof] unit %d: issuer woke %6lld issued %6lld | warp %lld wait_start %6lld woke %6lld ld_done %6lld proc_done %6lld\n",
+                            2000 + i, tl[i * 8 + 0] - tl[0], tl[i * 8 + 1] - tl[0], tl[i * 8 + 6], tl[i * 8 + 2] - tl[0], tl[i * 8 + 3] - tl[0],
+                            tl[i * 8 + 4] - tl[0], tl[i * 8 + 5] - tl[0]);
+                prof.release();
             }
         } else {
         PrefilterParams P;
@@ -1115,6 +1146,7 @@ extern "C" {
 int msb_set_option(const char *name, int value) {
     if (name && !std::strcmp(name, "prefilter_w") && (value == 4 || value == 8)) { g_prefilter_w = value; return MSB_OK; }
     if (name && !std::strcmp(name, "prefilter_tc") && (value == 0 || value == 1)) { g_prefilter_tc = value; return MSB_OK; }
+    if (name && !std::strcmp(name, "tc_prof") && (value == 0 || value == 1)) { g_tc_prof = value; return MSB_OK; }
     set_error("msb_set_option: unknown option or value");
     return MSB_EINVAL;
 }
