@@ -281,6 +281,34 @@ __device__ __forceinline__ void test_and_emit(const ExactParams &E, uint32_t m, 
     }
 }
 
+// The bases of window [p, p + 32) as registers: 2-bit codes in a 64-bit word, N flags in 32 bits.
+struct Window32 {
+    uint64_t codes;
+    uint32_t nmask;
+};
+__device__ __forceinline__ Window32 load_window32(const SeqView &S, int64_t p) {
+    // the packed buffers carry >= 4 words of zero padding behind the last sequence (msb_seqs_from_ascii)
+    const uint32_t *cp = S.codes + (p >> 4);
+    const uint32_t sh = (uint32_t) (p & 15) * 2;
+    const uint32_t c0 = __ldg(cp), c1 = __ldg(cp + 1), c2 = __ldg(cp + 2);
+    Window32 w;
+    w.codes = ((uint64_t) __funnelshift_r(c1, c2, sh) << 32) | __funnelshift_r(c0, c1, sh);
+    const uint32_t *mp = S.nmask + (p >> 5);
+    w.nmask = __funnelshift_r(__ldg(mp), __ldg(mp + 1), (uint32_t) (p & 31));
+    return w;
+}
+// exact_raw over a register window (L <= 32): same additions in the same order.
+__device__ __forceinline__ double exact_raw_w(const Window32 &w, const double *__restrict__ pw, int L, int rev) {
+    double acc = 0.0;
+    for (int c = 0; c < L; c++) {
+        if ((w.nmask >> c) & 1u) continue;
+        const int row = (int) ((w.codes >> (2 * c)) & 3u);
+        const double v = rev ? __ldg(pw + 4 * (L - 1 - c) + (3 - row)) : __ldg(pw + 4 * c + row);
+        acc = __dadd_rn(acc, v);
+    }
+    return acc;
+}
+
 // `col_info` == nullptr: keys carry (sorted motif index, position, strand) and were validated by
 // the table prefilter.  Otherwise they are the tensor-core prefilter's raw keys (tile * 256 +
 // column, position): decode the column and drop windows that run past their sequence.
@@ -306,7 +334,7 @@ exact_candidates_kernel(ExactParams E, const uint64_t *__restrict__ cand, int64_
         if (p - __ldg(E.seq.poff + s) + L > (int64_t) __ldg(E.seq.len + s)) return;   // cscore.c:340
     }
     const double *pw = E.mot.pwm + 4 * (int64_t) __ldg(E.mot.col_off + m);
-    test_and_emit(E, m, p, rev, exact_raw(E.seq, pw, L, p, rev));
+    test_and_emit(E, m, p, rev, exact_raw_w(load_window32(E.seq, p), pw, L, rev));   // prefilter motifs have L <= 32
 }
 
 // One thread per (listed position, motif); consecutive threads take consecutive motifs of the
@@ -328,6 +356,29 @@ exact_positions_kernel(ExactParams E, const int64_t *__restrict__ pos, int64_t n
     const double *pw = E.mot.pwm + 4 * (int64_t) __ldg(E.mot.col_off + m);
     if (E.strand & 1) test_and_emit(E, m, p, 0, exact_raw(E.seq, pw, L, p, 0));
     if (E.strand & 2) test_and_emit(E, m, p, 1, exact_raw(E.seq, pw, L, p, 1));
+}
+
+// Dirty windows (they touch a non-ACGT base) x the table-path motifs: one warp per listed
+// position, the window's bases loaded once, lanes stride over the motifs.
+__global__ void __launch_bounds__(256)
+exact_dirty_kernel(ExactParams E, const int64_t *__restrict__ pos, int64_t n_pos,
+                   const int32_t *__restrict__ motif_ids, int32_t n_ids) {
+    const int64_t d = ((int64_t) blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    if (d >= n_pos) return;
+    const int lane = threadIdx.x & 31;
+    const int64_t p = __ldg(pos + d);
+    const int64_t s = __ldg(E.seq.blk_seq + (p >> 5));
+    const int64_t left = (int64_t) __ldg(E.seq.len + s) - (p - __ldg(E.seq.poff + s));
+    if (left <= 0) return;
+    const Window32 w = load_window32(E.seq, p);
+    for (int32_t k = lane; k < n_ids; k += 32) {
+        const uint32_t m = (uint32_t) __ldg(motif_ids + k);
+        const int L = __ldg(E.mot.len + m);
+        if (L > left) continue;   // cscore.c:337,340
+        const double *pw = E.mot.pwm + 4 * (int64_t) __ldg(E.mot.col_off + m);
+        if (E.strand & 1) test_and_emit(E, m, p, 0, exact_raw_w(w, pw, L, 0));
+        if (E.strand & 2) test_and_emit(E, m, p, 1, exact_raw_w(w, pw, L, 1));
+    }
 }
 
 __global__ void __launch_bounds__(256)

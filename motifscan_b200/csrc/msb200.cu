@@ -1048,8 +1048,12 @@ static int scan_device(msb_ctx *ctx, msb_motifs *M, const msb_seqs *S, int stran
             MSB_CUDA(cudaGetLastError());
             ctx->c[MSB_C_LAUNCHES]++;
         }
-        if (n_dirty && n_fast)
-            MSB_TRY(launch_positions(ctx, E, ctx->dirty.as<int64_t>(), n_dirty, d_order, n_fast));
+        if (n_dirty && n_fast) {
+            const int64_t threads = n_dirty * 32;
+            exact_dirty_kernel<<<(unsigned) ((threads + 255) / 256), 256, 0, st>>>(E, ctx->dirty.as<int64_t>(), n_dirty, d_order, n_fast);
+            MSB_CUDA(cudaGetLastError());
+            ctx->c[MSB_C_LAUNCHES]++;
+        }
         if (n_slow)
             MSB_TRY(launch_positions(ctx, E, nullptr, S->total_packed, d_slow, n_slow));
         MSB_CUDA(cudaEventRecord(ctx->ev[2], st));
