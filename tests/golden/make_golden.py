@@ -334,6 +334,85 @@ def gen_build_case(ref):
                 cutoffs=final)
 
 
+def gen_host_cases():
+    """stats.motif_enrichment, the region-file parsers, the control-region generator and the result
+    writers of the reference, run on small inputs (inputs and outputs both stored)."""
+    import random
+    import tempfile
+    from collections import namedtuple
+    from motifscan.io import write_enrich_table, write_sites_bed, write_sites_table
+    from motifscan.region import GenomicRegion, load_motifscan_regions
+    from motifscan.region.utils import generate_control_regions
+    from motifscan.scanner import MotifSite
+    from motifscan.stats import motif_enrichment
+
+    rng = np.random.default_rng(77)
+    Pwm = namedtuple("Pwm", ["matrix_id", "name", "length"])
+    pwms = [Pwm(f"MA{k:04d}.1", f"TF{k}" if k % 3 else f"TF{k}::X-{k}", int(rng.integers(6, 20))) for k in range(9)]
+
+    def random_sites(n_regions, density):
+        out = []
+        for _ in pwms:
+            per = []
+            for r in range(n_regions):
+                n = int(rng.poisson(density))
+                cell = [MotifSite(int(rng.integers(0, 5000)), float(rng.uniform(0.7, 1.0)), "+-"[int(rng.integers(2))])
+                        for _ in range(n)]
+                per.append(sorted(cell, key=lambda s: s.start))
+            out.append(per)
+        return out
+
+    cases = {}
+    # --- enrichment -----------------------------------------------------------------------------
+    enrich = []
+    for n_in, n_ctl, d_in, d_ctl in [(40, 60, 0.5, 0.3), (25, 25, 0.05, 0.6), (30, 10, 1.5, 0.0), (8, 200, 0.2, 0.2)]:
+        sites, ctl = random_sites(n_in, d_in), random_sites(n_ctl, d_ctl)
+        res = motif_enrichment(pwms, sites, ctl)
+        enrich.append(dict(
+            n_input_total=n_in, n_control_total=n_ctl,
+            hits_input=[[int(len(c) > 0) for c in per] for per in sites],
+            hits_control=[[int(len(c) > 0) for c in per] for per in ctl],
+            results=[dict(name=r.name, n_input=int(r.n_input), n_control=int(r.n_control),
+                          fold_change=hexf(r.fold_change), p_enriched=hexf(r.p_enriched),
+                          p_depleted=hexf(r.p_depleted), p_corrected=hexf(r.p_corrected)) for r in res]))
+    cases["enrichment"] = dict(pwms=[list(p) for p in pwms], cases=enrich)
+    # --- region parsers -------------------------------------------------------------------------
+    region_dir = os.path.join(REFERENCE, "tests", "data", "regions")
+    files = {"bed": "test_regions.bed", "bed3-summit": "test_regions_summit.bed", "macs": "test_regions_macs.xls",
+             "macs2": "test_regions_macs2.xls", "narrowpeak": "test_regions.narrowPeak",
+             "broadpeak": "test_regions.broadPeak", "manorm": "test_regions_manorm.xls"}
+    parsed = {}
+    for fmt, fname in files.items():
+        path = os.path.join(region_dir, fname)
+        regions = load_motifscan_regions(path, fmt)
+        parsed[fmt] = dict(text=open(path).read(),
+                           regions=[[r.chrom, r.start, r.end, r.summit, r.score] for r in regions])
+    cases["regions"] = parsed
+    # --- control regions ------------------------------------------------------------------------
+    base = [GenomicRegion("chr1", 100, 350), GenomicRegion("chr2", 5, 1005), GenomicRegion("chrX", 40, 41)]
+    sizes = {"chr1": 5000, "chr2": 1200, "chrX": 300}
+    ctl = generate_control_regions(3, base, sizes, genes=None, random_seed=11)
+    cases["control_regions"] = dict(regions=[[r.chrom, r.start, r.end] for r in base], chrom_size=sizes, n_random=3,
+                                    seed=11, out=[[r.chrom, r.start, r.end] for r in ctl])
+    # --- writers --------------------------------------------------------------------------------
+    regions = [GenomicRegion("chr1", 10, 510), GenomicRegion("chr1", 700, 1300), GenomicRegion("chr7", 0, 90),
+               GenomicRegion("chrX", 5, 45)]
+    sites, ctl_sites = random_sites(len(regions), 0.8), random_sites(6, 0.4)
+    with tempfile.TemporaryDirectory() as tmp:
+        write_sites_table(tmp, pwms, regions, sites)
+        write_sites_bed(tmp, pwms, regions, sites)
+        write_enrich_table(tmp, motif_enrichment(pwms, sites, ctl_sites))
+        files_out = {}
+        for root, _, names in os.walk(tmp):
+            for n in names:
+                full = os.path.join(root, n)
+                files_out[os.path.relpath(full, tmp)] = open(full).read()
+    dump = lambda nested: [[[[s.start, hexf(s.score), s.strand] for s in cell] for cell in per] for per in nested]
+    cases["writers"] = dict(regions=[[r.chrom, r.start, r.end] for r in regions], sites=dump(sites),
+                            control_sites=dump(ctl_sites), files=files_out)
+    return cases
+
+
 def main():
     ref = import_reference()
     out = {
@@ -344,6 +423,7 @@ def main():
         "matrix_cases.json": gen_matrix_cases(),
         "sampler_cases.json": gen_sampler_cases(),
         "build_case.json": gen_build_case(ref),
+        "host_cases.json": gen_host_cases(),
     }
     for name, obj in out.items():
         path = os.path.join(HERE, name)
