@@ -87,6 +87,12 @@ int msb_motifs_destroy(msb_motifs *motifs);
 int msb_seqs_from_ascii(msb_ctx *ctx, int64_t n_seqs, const char *seq_bytes,
                         const int64_t *seq_off, msb_seqs **out);
 int msb_seqs_count(const msb_seqs *seqs, int64_t *n_seqs, int64_t *total_bp);
+/* Genome-wide scans cut a chromosome into chunks that overlap by (longest motif - 1) bases, so a
+ * window belongs to the chunk that holds its START (the reference scans a chromosome as one
+ * string, cscore.c:336-340).  limit[i] = number of leading positions of sequence i at which a
+ * window may start; sites starting at or behind it are not reported.  NULL restores the default
+ * (the whole sequence). */
+int msb_seqs_set_start_limit(msb_seqs *seqs, const int32_t *limit);
 /* Parity accessor: decode the packed device representation back to the reference's int8 codes
  * (0..3, -1) for all sequences, concatenated like the input. */
 int msb_seqs_codes(msb_ctx *ctx, const msb_seqs *seqs, int8_t *codes);
@@ -108,6 +114,9 @@ int msb_scan_ex(msb_ctx *ctx, const msb_motifs *motifs, const msb_seqs *seqs, in
 /* Device-only variant for measurement: same kernels, results left on the device, no D2H. */
 int msb_scan_device(msb_ctx *ctx, const msb_motifs *motifs, const msb_seqs *seqs, int strand,
                     int flags, int64_t *n_sites);
+/* Per-motif site counts of the last msb_scan_device on this context (n_motifs entries): the only
+ * thing a counts-only genome-wide scan copies back. */
+int msb_scan_device_counts(msb_ctx *ctx, int64_t *counts, int32_t n_motifs);
 int msb_result_total(const msb_result *res, int64_t *n_sites);
 int msb_result_counts(const msb_result *res, int64_t *counts /* n_motifs */);
 /* Borrowed pointers into the result (valid until msb_result_destroy): n_sites entries each. */

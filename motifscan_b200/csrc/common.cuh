@@ -63,6 +63,7 @@ struct SeqView {
     const int64_t *poff;     // [n_seqs + 1] packed start of every sequence (multiple of 32)
     const int32_t *len;      // [n_seqs] true length in bases
     const int32_t *blk_seq;  // [total_packed / 32] sequence that owns each 32-base block
+    const int32_t *limit;    // [n_seqs] windows may start at positions < limit (<= len); nullptr = len
     int64_t n_seqs;
     int64_t total_packed;    // poff[n_seqs]
 };

@@ -329,9 +329,11 @@ exact_candidates_kernel(ExactParams E, const uint64_t *__restrict__ cand, int64_
     }
     const uint32_t m = (uint32_t) __ldg(order + sorted);
     const int L = __ldg(E.mot.len + m);
-    if (col_info) {
+    if (col_info || E.seq.limit) {
         const int64_t s = __ldg(E.seq.blk_seq + (p >> 5));
-        if (p - __ldg(E.seq.poff + s) + L > (int64_t) __ldg(E.seq.len + s)) return;   // cscore.c:340
+        const int64_t j = p - __ldg(E.seq.poff + s);
+        if (j + L > (int64_t) __ldg(E.seq.len + s)) return;   // cscore.c:340
+        if (E.seq.limit && j >= (int64_t) __ldg(E.seq.limit + s)) return;   // the next chunk owns this start
     }
     const double *pw = E.mot.pwm + 4 * (int64_t) __ldg(E.mot.col_off + m);
     test_and_emit(E, m, p, rev, exact_raw_w(load_window32(E.seq, p), pw, L, rev));   // prefilter motifs have L <= 32
@@ -353,6 +355,7 @@ exact_positions_kernel(ExactParams E, const int64_t *__restrict__ pos, int64_t n
     const int L = __ldg(E.mot.len + m);
     const int64_t slen = __ldg(E.seq.len + s);
     if (j >= slen || j + L > slen) return;   // cscore.c:337,340
+    if (E.seq.limit && j >= (int64_t) __ldg(E.seq.limit + s)) return;
     const double *pw = E.mot.pwm + 4 * (int64_t) __ldg(E.mot.col_off + m);
     if (E.strand & 1) test_and_emit(E, m, p, 0, exact_raw(E.seq, pw, L, p, 0));
     if (E.strand & 2) test_and_emit(E, m, p, 1, exact_raw(E.seq, pw, L, p, 1));
@@ -370,6 +373,7 @@ exact_dirty_kernel(ExactParams E, const int64_t *__restrict__ pos, int64_t n_pos
     const int64_t s = __ldg(E.seq.blk_seq + (p >> 5));
     const int64_t left = (int64_t) __ldg(E.seq.len + s) - (p - __ldg(E.seq.poff + s));
     if (left <= 0) return;
+    if (E.seq.limit && p - __ldg(E.seq.poff + s) >= (int64_t) __ldg(E.seq.limit + s)) return;
     const Window32 w = load_window32(E.seq, p);
     for (int32_t k = lane; k < n_ids; k += 32) {
         const uint32_t m = (uint32_t) __ldg(motif_ids + k);

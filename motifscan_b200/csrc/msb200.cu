@@ -140,7 +140,8 @@ struct msb_seqs {
     int64_t n = 0, total_bp = 0, total_packed = 0;
     int32_t min_len = 0;
     std::vector<int64_t> seq_off, poff;
-    DevBuf d_codes, d_nmask, d_poff, d_len, d_seq_off, d_blk_seq;
+    DevBuf d_codes, d_nmask, d_poff, d_len, d_seq_off, d_blk_seq, d_limit;
+    bool has_limit = false;
     SeqView view() const {
         SeqView v;
         v.codes = d_codes.as<uint32_t>();
@@ -148,6 +149,7 @@ struct msb_seqs {
         v.poff = d_poff.as<int64_t>();
         v.len = d_len.as<int32_t>();
         v.blk_seq = d_blk_seq.as<int32_t>();
+        v.limit = has_limit ? d_limit.as<int32_t>() : nullptr;
         v.n_seqs = n;
         v.total_packed = total_packed;
         return v;
@@ -497,6 +499,19 @@ int msb_seqs_from_ascii(msb_ctx *ctx, int64_t n_seqs, const char *bytes, const i
     return MSB_OK;
 }
 
+int msb_seqs_set_start_limit(msb_seqs *S, const int32_t *limit) {
+    if (!S) { set_error("null seqs"); return MSB_EINVAL; }
+    if (!limit || S->n == 0) { S->has_limit = false; return MSB_OK; }
+    for (int64_t i = 0; i < S->n; i++)
+        if (limit[i] < 0) { set_error("msb_seqs_set_start_limit: negative limit"); return MSB_EINVAL; }
+    MSB_CUDA(cudaSetDevice(S->ctx->device));
+    MSB_TRY(S->d_limit.ensure((size_t) S->n * 4));
+    MSB_CUDA(cudaMemcpyAsync(S->d_limit.p, limit, (size_t) S->n * 4, cudaMemcpyHostToDevice, S->ctx->stream));
+    MSB_CUDA(cudaStreamSynchronize(S->ctx->stream));
+    S->has_limit = true;
+    return MSB_OK;
+}
+
 int msb_seqs_count(const msb_seqs *S, int64_t *n_seqs, int64_t *total_bp) {
     if (!S) { set_error("null seqs"); return MSB_EINVAL; }
     if (n_seqs) *n_seqs = S->n;
@@ -524,7 +539,7 @@ int msb_seqs_destroy(msb_seqs *S) {
     if (!S) return MSB_OK;
     cudaSetDevice(S->ctx->device);
     cudaStreamSynchronize(S->ctx->stream);
-    for (DevBuf *b : {&S->d_codes, &S->d_nmask, &S->d_poff, &S->d_len, &S->d_seq_off, &S->d_blk_seq}) b->release();
+    for (DevBuf *b : {&S->d_codes, &S->d_nmask, &S->d_poff, &S->d_len, &S->d_seq_off, &S->d_blk_seq, &S->d_limit}) b->release();
     delete S;
     return MSB_OK;
 }
@@ -1158,6 +1173,19 @@ int msb_set_option(const char *name, int value) {
 int msb_scan_device(msb_ctx *ctx, const msb_motifs *M, const msb_seqs *S, int strand, int flags, int64_t *n_sites) {
     MSB_TRY(scan_device(ctx, const_cast<msb_motifs *>(M), S, strand, flags));
     if (n_sites) *n_sites = ctx->last_sites;
+    return MSB_OK;
+}
+
+int msb_scan_device_counts(msb_ctx *ctx, int64_t *counts, int32_t n_motifs) {
+    if (!ctx || (!counts && n_motifs)) { set_error("msb_scan_device_counts: null"); return MSB_EINVAL; }
+    if (n_motifs != ctx->last_n_motifs) { set_error("msb_scan_device_counts: no scan with that many motifs"); return MSB_EINVAL; }
+    if (n_motifs == 0) return MSB_OK;
+    MSB_CUDA(cudaSetDevice(ctx->device));
+    std::vector<int64_t> offsets((size_t) n_motifs + 1, 0);
+    if (ctx->last_sites)
+        MSB_CUDA(cudaMemcpyAsync(offsets.data(), ctx->out_counts.p, offsets.size() * 8, cudaMemcpyDeviceToHost, ctx->stream));
+    MSB_CUDA(cudaStreamSynchronize(ctx->stream));
+    for (int32_t m = 0; m < n_motifs; m++) counts[m] = offsets[m + 1] - offsets[m];
     return MSB_OK;
 }
 

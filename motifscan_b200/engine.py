@@ -44,6 +44,12 @@ class Context:
         check(self._lib.msb_ctx_timings(self._h, ptr(a, ctypes.c_double), len(a)))
         return dict(zip(_lib.T_NAMES, a.tolist()))
 
+    def site_counts(self, n_motifs):
+        """Per-motif site counts of the last `scan_device` on this context."""
+        out = np.zeros(max(n_motifs, 1), dtype=np.int64)
+        check(self._lib.msb_scan_device_counts(self._h, ptr(out, ctypes.c_int64), int(n_motifs)))
+        return out[:n_motifs]
+
     def counters(self):
         a = np.zeros(len(_lib.C_NAMES), dtype=np.int64)
         check(self._lib.msb_ctx_counters(self._h, ptr(a, ctypes.c_int64), len(a)))
@@ -117,6 +123,17 @@ class SequenceSet:
         data = blob.ctypes.data if blob.size else None
         check(self._lib.msb_seqs_from_ascii(ctx._h, self.n, ctypes.c_void_p(data), ptr(seq_off, ctypes.c_int64),
                                             ctypes.byref(self._h)))
+
+    def set_start_limit(self, limit):
+        """Windows may only start at the first limit[i] positions of sequence i (chunked genome
+        scans: starts inside the overlap belong to the next chunk).  None restores the default."""
+        if limit is None:
+            check(self._lib.msb_seqs_set_start_limit(self._h, None))
+            return
+        limit = np.ascontiguousarray(np.asarray(limit, dtype=np.int32))
+        if limit.shape != (self.n,):
+            raise ValueError("one start limit per sequence is required")
+        check(self._lib.msb_seqs_set_start_limit(self._h, ptr(limit, ctypes.c_int32)))
 
     def codes(self):
         """Parity accessor: the reference's int8 codes (cscore.c:81-114) decoded from the device."""
