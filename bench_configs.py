@@ -1,0 +1,248 @@
+#!/usr/bin/env python3
+"""Measurements of the BASELINE.json configurations that `bench.py` does not time
+(bench.py = configs[1], the one the headline metric is quoted on):
+
+    python bench_configs.py build      configs[2]: motif --build, 750 motifs x 1e6 background samples
+    python bench_configs.py genome     configs[3]: genome-wide scan, one GPU's share (1/8 of 3.1 Gbp)
+    python bench_configs.py enrich     configs[4]: 200k target + 200k control 1 kb regions, 1900 motifs
+
+Each prints one JSON line: device-resident and end-to-end time, throughput, and a parity check of a
+bounded sample against the reference's CPU implementation (oracle/_ref when it compiled, else the
+oracle port).  Synthetic inputs (motifscan_b200/synth.py), nothing is read from /root/reference.
+"""
+import argparse
+import json
+import os
+import sys
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+
+def cpu_ext():
+    import oracle
+    ref = oracle.load_reference_cscore()
+    return ("reference", ref) if ref is not None else ("port", oracle)
+
+
+def device_ms(ctx, *names):
+    t = ctx.timings()
+    return {k: t[k] for k in names}
+
+
+def strs(blob, off, idx):
+    raw = blob.tobytes()
+    return [raw[off[i]:off[i + 1]].decode() for i in idx]
+
+
+def bench_build(args):
+    """cli/motif.py:119-153 at --n-random 1e6: score every sample at offset 0 on both strands, keep the
+    order statistics for p = 1e-2 .. 1e-6."""
+    from motifscan_b200 import engine, synth
+    from motifscan_b200.motif import cutoff_ranks
+    ctx = engine.default_context(0)
+    _, pwms, _ = synth.motif_set(args.motifs, seed=2020)
+    lmax = max(p.shape[1] for p in pwms)
+    motifs = engine.MotifSet(ctx, pwms)
+    blob, off = synth.background_samples(args.n_random, lmax, seed=1)
+    ranks = cutoff_ranks(args.n_random)
+    keys = list(ranks)
+    times = []
+    for _ in range(args.steps + 1):
+        t0 = time.perf_counter()
+        sset = engine.SequenceSet(ctx, blob=blob, seq_off=off)
+        sel = engine.score_select(ctx, motifs, sset, 3, [ranks[k] for k in keys])
+        times.append(time.perf_counter() - t0)
+        dev = device_ms(ctx, "score", "select")
+        sset.close()
+    e2e = min(times[1:])
+    # parity on a bounded sample: the same pipeline on the first n samples vs the CPU reference
+    kind, ext = cpu_ext()
+    n = args.cpu_samples
+    sub_ranks = cutoff_ranks(n)
+    sset = engine.SequenceSet(ctx, blob=blob[:off[n]], seq_off=off[:n + 1])
+    got = engine.score_select(ctx, motifs, sset, 3, list(sub_ranks.values()))
+    sset.close()
+    t0 = time.perf_counter()
+    scores = ext.c_score([p.tolist() for p in pwms], strs(blob, off, range(n)), 3, os.cpu_count() or 1)
+    want = np.array([[sorted(row, reverse=True)[r] for r in sub_ranks.values()] for row in scores])
+    cpu_s = time.perf_counter() - t0
+    same = bool(np.array_equal(got.view(np.uint64), want.view(np.uint64)))
+    units = args.motifs * args.n_random
+    return {"config": f"configs[2]: motif --build cutoffs, {args.motifs} motifs x {args.n_random} samples x {lmax} bp, "
+                      f"p=1e-2..1e-{len(keys) + 1}",
+            "metric": "motif*samples scored and ranked per second", "e2e_s": e2e,
+            "value": units / e2e, "device_ms": dev,
+            "cutoffs_p1e-4_head": np.around(sel[:3, keys.index("1e-4")], 8).tolist(),
+            "cpu_baseline": {"kind": kind, "cores": os.cpu_count(), "sample": f"{n} samples (c_score + sort)",
+                             "value": args.motifs * n / cpu_s, "seconds": cpu_s},
+            "parity": {"order_statistics_bit_identical_on_sample": same}}
+
+
+def bench_genome(args):
+    """One GPU's share of the hg19-shaped genome (3.1 Gbp / 8): chunked counts-only scan."""
+    from motifscan_b200 import engine, synth
+    from motifscan_b200.genome_scan import scan_genome
+    ctx = engine.default_context(0)
+    _, pwms, _ = synth.motif_set(args.motifs, seed=2020)
+    motifs = engine.MotifSet(ctx, pwms)
+    lmax = max(p.shape[1] for p in pwms)
+    bblob, boff = synth.background_samples(100000, lmax, seed=1)
+    bg = engine.SequenceSet(ctx, blob=bblob, seq_off=boff)
+    cutoffs = np.around(engine.score_select(ctx, motifs, bg, 3, [int(100000 * 1e-4) - 1])[:, 0], 8)
+    bg.close(), motifs.close()
+    n = args.genome_bp
+    t0 = time.perf_counter()
+    seq = synth.genome_chunk(n, seed=19, n_block=(n // 3, int(n * 0.07)))   # ~7 % N like the assembly gaps
+    seq[:10000] = ord("N")
+    gen_s = time.perf_counter() - t0
+
+    class OneChrom:
+        chroms = ["chrS"]
+        chrom_sizes = {"chrS": n}
+
+        @staticmethod
+        def fetch_bytes(chrom, a, b):
+            return seq[a:b].tobytes()
+
+    # 51 of the 750 synthetic motifs get a NEGATIVE p=1e-4 cutoff on an iid background (long, very
+    # specific columns: even the best of 1e5 random windows scores below 0).  By the reference's rule
+    # (N adds 0, cscore.c:346) every all-N window then scores 0 >= cutoff and is a site: 27 M gap
+    # positions x 51 motifs x 2 strands.  Motif sets built on real genomes have positive cutoffs, so
+    # the headline run floors the cutoffs at 1e-6; the as-built run is reported beside it.
+    def timed(cut):
+        runs = []
+        for _ in range(args.steps + 1):
+            t0 = time.perf_counter()
+            out = scan_genome(OneChrom, pwms, cutoffs=cut, chunk_bp=args.chunk_bp, batch_bp=args.batch_bp,
+                              ctx=ctx, collect_sites=False)
+            runs.append(time.perf_counter() - t0)
+        return min(runs[1:]), out
+    as_built_s, as_built = timed(cutoffs)
+    n_nonpos = int((cutoffs <= 1e-10).sum())
+    cutoffs = np.maximum(cutoffs, 1e-6)
+    e2e, sites = timed(cutoffs)
+    # parity: a 2 Mbp window with sites, vs the CPU reference
+    kind, ext = cpu_ext()
+    a = n // 3 - 1000000
+    piece = seq[a:a + args.cpu_bp]
+
+    class Piece:
+        chroms = ["chrS"]
+        chrom_sizes = {"chrS": len(piece)}
+
+        @staticmethod
+        def fetch_bytes(chrom, x, y):
+            return piece[x:y].tobytes()
+
+    got = scan_genome(Piece, pwms, cutoffs=cutoffs, chunk_bp=1 << 18, batch_bp=1 << 20, ctx=ctx)
+    t0 = time.perf_counter()
+    ref = ext.c_scan_motif([p.tolist() for p in pwms], cutoffs.tolist(), [piece.tobytes().decode()], 3, os.cpu_count() or 1)
+    cpu_s = time.perf_counter() - t0
+    ok = all(len(r) == c for r, c in zip(ref, got.counts))
+    flat = [s for r in ref for s in r]
+    ok = ok and np.array_equal(got.start, np.array([s[1] for s in flat], dtype=np.int64)) and \
+        np.array_equal(got.score.view(np.uint64), np.array([s[2] for s in flat]).view(np.uint64)) and \
+        np.array_equal(got.strand, np.array([s[3] for s in flat], dtype=np.int8))
+    return {"config": f"configs[3]: genome-wide scan, one GPU's share: {n} bp (7 % N, soft-masked) x {args.motifs} motifs, "
+                      f"both strands, p=1e-4, chunks of {args.chunk_bp} bp in batches of {args.batch_bp} bp, counts only",
+            "metric": "motif*bp/s (host ASCII in, per-motif counts out)", "e2e_s": e2e, "value": args.motifs * n / e2e,
+            "sites": int(sites.counts.sum()), "host_generation_s": gen_s,
+            "cutoffs": f"p=1e-4 from 1e5 background samples, floored at 1e-6 ({n_nonpos} motifs had a cutoff <= 0)",
+            "as_built_cutoffs": {"e2e_s": as_built_s, "value": args.motifs * n / as_built_s,
+                                 "sites": int(as_built.counts.sum()),
+                                 "note": "all-N windows are sites for the motifs with a non-positive cutoff"},
+            "cpu_baseline": {"kind": kind, "cores": os.cpu_count(), "sample": f"{len(piece)} bp x all motifs",
+                             "value": args.motifs * len(piece) / cpu_s, "seconds": cpu_s},
+            "parity": {"sites_compared": len(flat), "identical": bool(ok)}}
+
+
+def bench_enrich(args):
+    """Scan target and control regions, count regions with a site per motif, Fisher tests."""
+    from motifscan_b200 import engine, synth
+    from motifscan_b200.scanner import MotifSites
+    from motifscan_b200.stats import enrichment_from_counts
+    ctx = engine.default_context(0)
+    _, pwms, ids = synth.motif_set(args.motifs, seed=2020)
+    motifs = engine.MotifSet(ctx, pwms)
+    lmax = max(p.shape[1] for p in pwms)
+    bblob, boff = synth.background_samples(100000, lmax, seed=1)
+    bg = engine.SequenceSet(ctx, blob=bblob, seq_off=boff)
+    cutoffs = np.around(engine.score_select(ctx, motifs, bg, 3, [int(100000 * 1e-4) - 1])[:, 0], 8)
+    bg.close()
+    motifs.set_cutoffs(cutoffs)
+    sets = [synth.peak_set(args.regions, 1000, seed=200), synth.peak_set(args.regions, 1000, seed=201)]
+    lengths = [p.shape[1] for p in pwms]
+
+    def scan_hits(blob, off):
+        """Regions with >= 1 site per motif; the regions go through in blocks that bound the site buffers."""
+        hits = np.zeros(args.motifs, dtype=np.int64)
+        n_sites = 0
+        step = args.region_block
+        for a in range(0, args.regions, step):
+            b = min(args.regions, a + step)
+            sset = engine.SequenceSet(ctx, blob=blob[off[a]:off[b]], seq_off=off[a:b + 1] - off[a])
+            res = engine.scan(ctx, motifs, sset, 3, remove_dup=True)
+            view = MotifSites(res, args.motifs, [0] * (b - a), lengths)
+            hits += view.regions_with_sites()
+            n_sites += res.n_sites
+            res.close(), sset.close()
+        return hits, n_sites
+
+    runs = []
+    for _ in range(args.steps + 1):
+        t0 = time.perf_counter()
+        (h_in, s_in), (h_ctl, s_ctl) = scan_hits(*sets[0]), scan_hits(*sets[1])
+        t_scan = time.perf_counter() - t0
+        results = enrichment_from_counts(ids, h_in, args.regions, h_ctl, args.regions)
+        runs.append((time.perf_counter() - t0, t_scan))
+    e2e, t_scan = min(runs[1:])
+    # parity of the counts on a bounded sample of regions vs the CPU reference (dedup never empties a cell)
+    kind, ext = cpu_ext()
+    n = args.cpu_regions
+    blob, off = sets[0]
+    t0 = time.perf_counter()
+    ref = ext.c_scan_motif([p.tolist() for p in pwms], cutoffs.tolist(), strs(blob, off, range(n)), 3, os.cpu_count() or 1)
+    cpu_s = time.perf_counter() - t0
+    want = np.array([len({s[0] for s in r}) for r in ref], dtype=np.int64)
+    sset = engine.SequenceSet(ctx, blob=blob[:off[n]], seq_off=off[:n + 1])
+    res = engine.scan(ctx, motifs, sset, 3, remove_dup=True)
+    got = MotifSites(res, args.motifs, [0] * n, lengths).regions_with_sites()
+    res.close(), sset.close()
+    units = args.motifs * 2 * args.regions * 1000
+    return {"config": f"configs[4]: {args.regions} target + {args.regions} control 1 kb regions x {args.motifs} motifs, "
+                      "scan (dedup on device) + regions-with-site counts + Fisher exact tests",
+            "metric": "motif*bp/s (host ASCII in, enrichment table out)", "e2e_s": e2e, "scan_s": t_scan,
+            "value": units / e2e, "sites": int(s_in + s_ctl),
+            "top_result": list(min(results, key=lambda r: r.p_enriched))[:5],
+            "cpu_baseline": {"kind": kind, "cores": os.cpu_count(), "sample": f"{n} regions x all motifs (scan only)",
+                             "value": args.motifs * n * 1000 / cpu_s, "seconds": cpu_s},
+            "parity": {"regions_with_site_counts_identical_on_sample": bool(np.array_equal(got, want))}}
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("which", choices=["build", "genome", "enrich"])
+    ap.add_argument("--steps", type=int, default=2)
+    ap.add_argument("--motifs", type=int, default=None)
+    ap.add_argument("--n-random", dest="n_random", type=int, default=1000000)
+    ap.add_argument("--cpu-samples", dest="cpu_samples", type=int, default=100000)
+    ap.add_argument("--genome-bp", dest="genome_bp", type=int, default=388000000)
+    ap.add_argument("--chunk-bp", dest="chunk_bp", type=int, default=1 << 23)
+    ap.add_argument("--batch-bp", dest="batch_bp", type=int, default=1 << 27)
+    ap.add_argument("--cpu-bp", dest="cpu_bp", type=int, default=2000000)
+    ap.add_argument("--regions", type=int, default=200000)
+    ap.add_argument("--region-block", dest="region_block", type=int, default=50000)
+    ap.add_argument("--cpu-regions", dest="cpu_regions", type=int, default=4000)
+    args = ap.parse_args()
+    if args.motifs is None:
+        args.motifs = 1900 if args.which == "enrich" else 750
+    out = {"build": bench_build, "genome": bench_genome, "enrich": bench_enrich}[args.which](args)
+    print(json.dumps(out))
+
+
+if __name__ == "__main__":
+    main()
