@@ -81,6 +81,8 @@ struct msb_ctx {
     unsigned long long *h_counters = nullptr;  // pinned, 4 entries
     std::vector<PinnedBlock> pinned_free;
     std::mutex pinned_mu;
+    std::vector<DevBuf> dev_free;     // device buffers of destroyed sequence sets, reused by the next one
+    std::mutex dev_mu;
     // results of the last msb_scan_device, still on the device
     int64_t last_sites = 0;
     int32_t last_n_motifs = 0;
@@ -197,6 +199,37 @@ static void pinned_put(msb_ctx *ctx, PinnedBlock b) {
     else cudaFreeHost(b.p);
 }
 
+// Device buffers of sequence sets come from / go back to a small per-context pool: a scan service
+// creates and destroys one msb_seqs per request, and cudaMalloc / cudaFree would otherwise
+// synchronise the device twice per request.
+static int dev_take(msb_ctx *ctx, DevBuf &b, size_t bytes) {
+    {
+        std::lock_guard<std::mutex> g(ctx->dev_mu);
+        int best = -1;
+        for (size_t i = 0; i < ctx->dev_free.size(); i++)
+            if (ctx->dev_free[i].cap >= bytes && ctx->dev_free[i].cap <= 2 * bytes + (1 << 20) &&
+                (best < 0 || ctx->dev_free[i].cap < ctx->dev_free[best].cap))
+                best = (int) i;
+        if (best >= 0) {
+            b = ctx->dev_free[best];
+            ctx->dev_free.erase(ctx->dev_free.begin() + best);
+            return MSB_OK;
+        }
+    }
+    return b.ensure(bytes);
+}
+static void dev_give(msb_ctx *ctx, DevBuf &b) {
+    if (!b.p) return;
+    std::lock_guard<std::mutex> g(ctx->dev_mu);
+    if (ctx->dev_free.size() < 24) {
+        ctx->dev_free.push_back(b);
+        b.p = nullptr;
+        b.cap = 0;
+    } else {
+        b.release();
+    }
+}
+
 static inline float ev_ms(cudaEvent_t a, cudaEvent_t b) {
     float ms = 0;
     cudaEventElapsedTime(&ms, a, b);
@@ -284,6 +317,7 @@ int msb_ctx_destroy(msb_ctx *ctx) {
                       &ctx->out2_seq, &ctx->out2_start, &ctx->out2_strand})
         b->release();
     for (auto &b : ctx->pinned_free) cudaFreeHost(b.p);
+    for (auto &b : ctx->dev_free) b.release();
     if (ctx->h_counters) cudaFreeHost(ctx->h_counters);
     for (auto &evt : ctx->ev) if (evt) cudaEventDestroy(evt);
     if (ctx->own_stream) cudaStreamDestroy(ctx->stream);
@@ -459,12 +493,12 @@ int msb_seqs_from_ascii(msb_ctx *ctx, int64_t n_seqs, const char *bytes, const i
     const int64_t n_blocks = at / kPadBases;
     // +8 / +4 words of zero padding: the prefilter reads up to 3 code words / 2 mask words
     // starting at the word of a thread's first window.
-    if ((rc = S->d_codes.ensure((size_t) (2 * n_blocks + 8) * 4)) != MSB_OK ||
-        (rc = S->d_nmask.ensure((size_t) (n_blocks + 4) * 4)) != MSB_OK ||
-        (rc = S->d_blk_seq.ensure((size_t) std::max<int64_t>(n_blocks, 1) * 4)) != MSB_OK ||
-        (rc = S->d_poff.ensure((size_t) (n_seqs + 1) * 8)) != MSB_OK ||
-        (rc = S->d_len.ensure((size_t) std::max<int64_t>(n_seqs, 1) * 4)) != MSB_OK ||
-        (rc = S->d_seq_off.ensure((size_t) (n_seqs + 1) * 8)) != MSB_OK ||
+    if ((rc = dev_take(ctx, S->d_codes, (size_t) (2 * n_blocks + 8) * 4)) != MSB_OK ||
+        (rc = dev_take(ctx, S->d_nmask, (size_t) (n_blocks + 4) * 4)) != MSB_OK ||
+        (rc = dev_take(ctx, S->d_blk_seq, (size_t) std::max<int64_t>(n_blocks, 1) * 4)) != MSB_OK ||
+        (rc = dev_take(ctx, S->d_poff, (size_t) (n_seqs + 1) * 8)) != MSB_OK ||
+        (rc = dev_take(ctx, S->d_len, (size_t) std::max<int64_t>(n_seqs, 1) * 4)) != MSB_OK ||
+        (rc = dev_take(ctx, S->d_seq_off, (size_t) (n_seqs + 1) * 8)) != MSB_OK ||
         (rc = ctx->ascii.ensure((size_t) std::max<int64_t>(S->total_bp, 16))) != MSB_OK) {
         msb_seqs_destroy(S);
         return rc;
@@ -539,7 +573,7 @@ int msb_seqs_destroy(msb_seqs *S) {
     if (!S) return MSB_OK;
     cudaSetDevice(S->ctx->device);
     cudaStreamSynchronize(S->ctx->stream);
-    for (DevBuf *b : {&S->d_codes, &S->d_nmask, &S->d_poff, &S->d_len, &S->d_seq_off, &S->d_blk_seq, &S->d_limit}) b->release();
+    for (DevBuf *b : {&S->d_codes, &S->d_nmask, &S->d_poff, &S->d_len, &S->d_seq_off, &S->d_blk_seq, &S->d_limit}) dev_give(S->ctx, *b);
     delete S;
     return MSB_OK;
 }

@@ -451,7 +451,7 @@ prefilter_tc_kernel(const __grid_constant__ TcParams P) {
         Stage stg;
         stg.slots = smem_u32(smem + kTcStageOff) + ((warp - 4) * kTcStageCap + lane * kTcLaneSlots) * 8;
         stg.n = 0;
-        const uint32_t taddr0 = tmem + h * kTcWarpCols + ((uint32_t) (q * 32) << 16);
+        const uint32_t taddr0 = tmem + set * kTcCols + h * kTcWarpCols + ((uint32_t) (q * 32) << 16);
         const uint32_t colid0 = P.batch.first_tile * kTcCols + h * kTcWarpCols;
         uint32_t u = 0, it = 0;
         long long t_wf = 0, t_ld = 0, t_pr = 0, t_wsf = 0, t_slow = 0, n_slow = 0;
@@ -466,43 +466,47 @@ prefilter_tc_kernel(const __grid_constant__ TcParams P) {
             if (lane == 0) mbar_arrive_a(B.stream_empty + 8 * slot);
             if (skip) continue;
             const int64_t tile_start = t * kTcTileBases;
+            // units of this tile: v = 0 .. 4 NT - 1 (shift s = v / NT, tile nt = v % NT); 4 NT is even, so
+            // the TMEM buffer of unit u + v is v & 1 and this warp set reads v = set, set + 2, ...
+            uint32_t sh = 0, nt = (uint32_t) set;
+            while (nt >= NT) { nt -= NT; sh++; }
 #pragma unroll 1
-            for (uint32_t s = 0; s < 4; s++) {
-                const bool live = !((ign4 >> s) & 1u);
-                const int64_t p = tile_start + 4 * row + s;
-                uint32_t colid = colid0;
-#pragma unroll 1
-                for (uint32_t nt = 0; nt < NT; nt++, u++, colid += kTcCols) {
-                    const uint32_t buf = u & 1;
-                    if (buf != (uint32_t) set) continue;   // the other warp set reads this buffer
-                    const long long c0 = now();
-                    mbar_wait_a(B.tmem_full + 8 * buf, (u >> 1) & 1);
-                    const long long c1 = now();
-                    t_wf += c1 - c0;
-                    fence_after();
-                    const uint32_t taddr = taddr0 + buf * kTcCols;
-                    uint32_t r0[32], r1[32];
-                    MSB_TC_LD32P(r0, taddr);        // columns [0, 64) of this warp's share, two per register
-                    if (kTcWarpCols == 128) MSB_TC_LD32P(r1, taddr + 64);
-                    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-                    fence_before();
-                    __syncwarp();
-                    if (lane == 0) mbar_arrive_a(B.tmem_empty + 8 * buf);   // accumulators are in registers
-                    const long long c2 = now() + ((r0[0] ^ r0[31]) == 0x12345679u);   // depends on the loaded data
-                    t_ld += c2 - c1;
-                    const uint32_t n_before = stg.n;
-                    scan_chunk(P, stg, r0, live, colid, p);
-                    if (kTcWarpCols == 128) scan_chunk(P, stg, r1, live, colid + 64, p);
-                    if (__any_sync(0xffffffffu, stg.n >= kTcLaneSlots - 1)) { stage_flush(P, stg, lane); stg.n = 0; }
+            for (uint32_t v = (uint32_t) set; v < 4 * NT; v += 2) {
+                const uint32_t uu = u + v;
+                const bool live = !((ign4 >> sh) & 1u);
+                const int64_t p = tile_start + 4 * row + sh;
+                const uint32_t colid = colid0 + nt * kTcCols;
+                const long long c0 = now();
+                mbar_wait_a(B.tmem_full + 8 * set, (uu >> 1) & 1);
+                const long long c1 = now();
+                t_wf += c1 - c0;
+                fence_after();
+                uint32_t r0[32], r1[32];
+                MSB_TC_LD32P(r0, taddr0);        // columns [0, 64) of this warp's share, two per register
+                MSB_TC_LD32P(r1, taddr0 + 64);
+                asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+                fence_before();
+                __syncwarp();
+                if (lane == 0) mbar_arrive_a(B.tmem_empty + 8 * set);   // accumulators are in registers
+                const long long c2 = now() + ((r0[0] ^ r0[31]) == 0x12345679u);   // depends on the loaded data
+                t_ld += c2 - c1;
+                const uint32_t n_before = stg.n;
+                scan_chunk(P, stg, r0, live, colid, p);
+                scan_chunk(P, stg, r1, live, colid + 64, p);
+                if (__any_sync(0xffffffffu, stg.n >= kTcLaneSlots - 1)) { stage_flush(P, stg, lane); stg.n = 0; }
+                if (kProf) {
                     const long long c3 = now();
                     t_pr += c3 - c2;
                     if (__any_sync(0xffffffffu, stg.n != n_before)) { t_slow += c3 - c2; n_slow++; }
-                    if (kProf && P.prof && blockIdx.x == 0 && lane == 0 && (warp == 4 || warp == 12) && u >= 2000 && u < 2012) {
-                        long long *o = P.prof + gridDim.x * 16 + (u - 2000) * 8;
+                    if (P.prof && blockIdx.x == 0 && lane == 0 && (warp == 4 || warp == 12) && uu >= 2000 && uu < 2012) {
+                        long long *o = P.prof + gridDim.x * 16 + (uu - 2000) * 8;
                         o[2] = c0; o[3] = c1; o[4] = c2; o[5] = c3; o[6] = warp;
                     }
                 }
+                nt += 2;
+                while (nt >= NT) { nt -= NT; sh++; }
             }
+            u += 4 * NT;
         }
         stage_flush(P, stg, lane);
         if (kProf && P.prof && warp == 4 && lane == 0) {
