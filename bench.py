@@ -376,9 +376,11 @@ def run_ours(args, rank, local_rank, world):
         n_pre = max(counters["prefilter_launches"], 1)
         sm_count = torch.cuda.get_device_properties(local_rank).multi_processor_count
         # Dominant kernel: prefilter_tc_kernel (tcgen05.mma kind::f8f6f4).  Algorithmic work per
-        # window and motif = the one-hot x PWM contraction: 4 L_m MACs per strand = 2 x the
-        # reference's adds (OPS = 2 sum L_m adds per window), 2 flops per MAC.
-        alg_flops = 4.0 * adds
+        # window and motif = the unpadded one-hot x PWM contraction: 4 L_m MACs per strand and window
+        # = 4 x the reference's adds (OPS = 2 L_m adds per window, both strands), and
+        # 2 flops per MAC as in every tensor-core peak figure: 8 x OPS.  (Until r1_c this line used
+        # 4 x OPS, i.e. counted MACs against a flop/s peak, and under-reported `frac` twofold.)
+        alg_flops = 8.0 * adds
         issued_flops = tc_issued_flops(pwm_lens, float(seq_off[-1]), n_regions=N_REGIONS)
         bf16_peak = peaks.get("bf16_tflops", 1590.0)
         tensor_peak = 2.0 * bf16_peak          # e4m3 runs at twice the bf16 rate; only bf16 is measured

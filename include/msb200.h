@@ -86,7 +86,17 @@ int msb_motifs_destroy(msb_motifs *motifs);
 /* Copies the bytes to the device and encodes + packs them there. */
 int msb_seqs_from_ascii(msb_ctx *ctx, int64_t n_seqs, const char *seq_bytes,
                         const int64_t *seq_off, msb_seqs **out);
+/* Resident genome: instead of one host fetch per region (Scanner._extract_seq,
+ * scanner.py:71-87 -> Genome.fetch_sequence -> pysam FastaFile.fetch, genome/__init__.py:135) the
+ * chromosomes are encoded once into a resident msb_seqs and every later sequence set is cut out of
+ * it on the device: sequence i of the result = bases [start[i], end[i]) of sequence src_idx[i] of
+ * `src`, `end` clipped at the source length as fetch does (start < 0 or a bad index: MSB_EINVAL).
+ * Only the 20 n bytes of the interval table cross PCIe. */
+int msb_seqs_extract(msb_ctx *ctx, const msb_seqs *src, int64_t n, const int32_t *src_idx,
+                     const int64_t *start, const int64_t *end, msb_seqs **out);
 int msb_seqs_count(const msb_seqs *seqs, int64_t *n_seqs, int64_t *total_bp);
+/* True length in bases of every sequence (n_seqs entries). */
+int msb_seqs_lengths(const msb_seqs *seqs, int64_t *lens);
 /* Genome-wide scans cut a chromosome into chunks that overlap by (longest motif - 1) bases, so a
  * window belongs to the chunk that holds its START (the reference scans a chromosome as one
  * string, cscore.c:336-340).  limit[i] = number of leading positions of sequence i at which a
@@ -111,6 +121,18 @@ int msb_scan(msb_ctx *ctx, const msb_motifs *motifs, const msb_seqs *seqs, int s
 #define MSB_SCAN_DEDUP 1
 int msb_scan_ex(msb_ctx *ctx, const msb_motifs *motifs, const msb_seqs *seqs, int strand,
                 int flags, msb_result **out);
+/* Range scan over a resident sequence set (genome-wide scans, configs[3]): only windows that START
+ * in [start[k], end[k]) of sequence seq_idx[k] are scored; a window may run past `end` into the rest
+ * of its sequence, exactly as if the whole sequence had been scanned (cscore.c:336-340), so the
+ * union over a partition of a chromosome into ranges equals the unchunked scan and no overlap has
+ * to be shipped.  `end` is clipped at the sequence length; ranges must not overlap (MSB_EINVAL).
+ * seq_idx / start of the sites refer to `seqs`. */
+int msb_scan_ranges(msb_ctx *ctx, const msb_motifs *motifs, const msb_seqs *seqs, int strand,
+                    int flags, int64_t n_ranges, const int64_t *seq_idx, const int64_t *start,
+                    const int64_t *end, msb_result **out);
+int msb_scan_ranges_device(msb_ctx *ctx, const msb_motifs *motifs, const msb_seqs *seqs, int strand,
+                           int flags, int64_t n_ranges, const int64_t *seq_idx, const int64_t *start,
+                           const int64_t *end, int64_t *n_sites);
 /* Device-only variant for measurement: same kernels, results left on the device, no D2H. */
 int msb_scan_device(msb_ctx *ctx, const msb_motifs *motifs, const msb_seqs *seqs, int strand,
                     int flags, int64_t *n_sites);

@@ -42,12 +42,18 @@ SIGNATURES = {
     "msb_motifs_max_raw": (ctypes.c_int, [c_vp, c_f64p]),
     "msb_motifs_destroy": (ctypes.c_int, [c_vp]),
     "msb_seqs_from_ascii": (ctypes.c_int, [c_vp, ctypes.c_int64, c_vp, c_i64p, ctypes.POINTER(c_vp)]),
+    "msb_seqs_extract": (ctypes.c_int, [c_vp, c_vp, ctypes.c_int64, c_i32p, c_i64p, c_i64p, ctypes.POINTER(c_vp)]),
+    "msb_seqs_lengths": (ctypes.c_int, [c_vp, c_i64p]),
     "msb_seqs_set_start_limit": (ctypes.c_int, [c_vp, c_i32p]),
     "msb_seqs_count": (ctypes.c_int, [c_vp, c_i64p, c_i64p]),
     "msb_seqs_codes": (ctypes.c_int, [c_vp, c_vp, c_i8p]),
     "msb_seqs_destroy": (ctypes.c_int, [c_vp]),
     "msb_scan": (ctypes.c_int, [c_vp, c_vp, c_vp, ctypes.c_int, ctypes.POINTER(c_vp)]),
     "msb_scan_ex": (ctypes.c_int, [c_vp, c_vp, c_vp, ctypes.c_int, ctypes.c_int, ctypes.POINTER(c_vp)]),
+    "msb_scan_ranges": (ctypes.c_int, [c_vp, c_vp, c_vp, ctypes.c_int, ctypes.c_int, ctypes.c_int64, c_i64p, c_i64p,
+                                       c_i64p, ctypes.POINTER(c_vp)]),
+    "msb_scan_ranges_device": (ctypes.c_int, [c_vp, c_vp, c_vp, ctypes.c_int, ctypes.c_int, ctypes.c_int64, c_i64p,
+                                              c_i64p, c_i64p, c_i64p]),
     "msb_scan_device": (ctypes.c_int, [c_vp, c_vp, c_vp, ctypes.c_int, ctypes.c_int, c_i64p]),
     "msb_scan_device_counts": (ctypes.c_int, [c_vp, c_i64p, ctypes.c_int32]),
     "msb_result_total": (ctypes.c_int, [c_vp, c_i64p]),

@@ -12,7 +12,7 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 ROOT = os.path.dirname(HERE)
 SRC = [os.path.join(HERE, "csrc", "msb200.cu")]
-DEPS = SRC + [os.path.join(HERE, "csrc", f) for f in ("kernels.cuh", "common.cuh")] + \
+DEPS = SRC + [os.path.join(HERE, "csrc", f) for f in ("kernels.cuh", "common.cuh", "prefilter_tc.cuh")] + \
     [os.path.join(ROOT, "include", "msb200.h")]
 OUT = os.path.join(HERE, "libmsb200.so")
 

@@ -71,6 +71,45 @@ encode_pack_kernel(const uint8_t *__restrict__ ascii, const int64_t *__restrict_
     blk_seq[b] = (int32_t) s;
 }
 
+// ---------------------------------------------------------------------------------------------
+// extract: build a packed sequence set from intervals of a resident one (the device-side
+// counterpart of Scanner._extract_seq's per-region fetch, scanner.py:71-87).  One thread per
+// 32-base block of the destination: 64 code bits + 32 mask bits funnel-shifted out of the source.
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+extract_pack_kernel(SeqView src, const int32_t *__restrict__ src_idx, const int64_t *__restrict__ src_start,
+                    const int64_t *__restrict__ poff, const int32_t *__restrict__ len, int64_t n_seqs,
+                    int64_t n_blocks, uint32_t *__restrict__ codes, uint32_t *__restrict__ nmask,
+                    int32_t *__restrict__ blk_seq) {
+    const int64_t b = (int64_t) blockIdx.x * blockDim.x + threadIdx.x;
+    if (b >= n_blocks) return;
+    const int64_t p = b * kPadBases;
+    const int64_t s = find_seq(poff, n_seqs, p);
+    const int64_t j = p - __ldg(poff + s);
+    const int n = (int) min((int64_t) kPadBases, (int64_t) __ldg(len + s) - j);
+    uint32_t lo = 0, hi = 0, mask = 0;
+    if (n > 0) {
+        const int64_t q = __ldg(src.poff + __ldg(src_idx + s)) + __ldg(src_start + s) + j;
+        // the source buffers carry zero padding behind their last block (msb_seqs_from_ascii)
+        const uint32_t *cp = src.codes + (q >> 4);
+        const uint32_t sh = (uint32_t) (q & 15) * 2;
+        const uint32_t c0 = __ldg(cp), c1 = __ldg(cp + 1), c2 = __ldg(cp + 2);
+        lo = __funnelshift_r(c0, c1, sh);
+        hi = __funnelshift_r(c1, c2, sh);
+        const uint32_t *mp = src.nmask + (q >> 5);
+        mask = __funnelshift_r(__ldg(mp), __ldg(mp + 1), (uint32_t) (q & 31));
+        if (n < 32) {
+            mask &= (1u << n) - 1u;
+            if (n <= 16) { hi = 0; lo &= n == 16 ? 0xffffffffu : ((1u << (2 * n)) - 1u); }
+            else hi &= (1u << (2 * (n - 16))) - 1u;
+        }
+    }
+    codes[2 * b] = lo;
+    codes[2 * b + 1] = hi;
+    nmask[b] = mask;
+    blk_seq[b] = (int32_t) s;
+}
+
 // Parity accessor: packed -> int8 codes laid out like the ASCII input.
 __global__ void __launch_bounds__(256)
 unpack_codes_kernel(SeqView S, const int64_t *__restrict__ seq_off, int8_t *__restrict__ out) {
@@ -342,13 +381,13 @@ exact_candidates_kernel(ExactParams E, const uint64_t *__restrict__ cand, int64_
 // One thread per (listed position, motif); consecutive threads take consecutive motifs of the
 // same position.  `motif_ids` == nullptr means all motifs.
 __global__ void __launch_bounds__(256)
-exact_positions_kernel(ExactParams E, const int64_t *__restrict__ pos, int64_t n_pos,
+exact_positions_kernel(ExactParams E, const int64_t *__restrict__ pos, int64_t n_pos, int64_t pos_base,
                        const int32_t *__restrict__ motif_ids, int32_t n_ids) {
     const int64_t t = (int64_t) blockIdx.x * blockDim.x + threadIdx.x;
     const int64_t d = t / n_ids;
     if (d >= n_pos) return;
     const uint32_t m = motif_ids ? (uint32_t) __ldg(motif_ids + (t - d * n_ids)) : (uint32_t) (t - d * n_ids);
-    const int64_t p = pos ? __ldg(pos + d) : d;
+    const int64_t p = pos ? __ldg(pos + d) : pos_base + d;
     if (p >= E.seq.total_packed) return;
     const int64_t s = find_seq(E.seq.poff, E.seq.n_seqs, p);
     const int64_t j = p - __ldg(E.seq.poff + s);

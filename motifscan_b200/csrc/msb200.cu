@@ -451,22 +451,12 @@ int msb_motifs_destroy(msb_motifs *M) {
 }
 
 // ---- sequences ---------------------------------------------------------------------------------
-int msb_seqs_from_ascii(msb_ctx *ctx, int64_t n_seqs, const char *bytes, const int64_t *seq_off,
-                        msb_seqs **out) {
-    if (!ctx || !out || n_seqs < 0 || !seq_off || (seq_off[n_seqs] > 0 && !bytes)) {
-        set_error("msb_seqs_from_ascii: bad argument");
-        return MSB_EINVAL;
-    }
-    *out = nullptr;
-    if (seq_off[0] != 0) { set_error("seq_off[0] must be 0"); return MSB_EINVAL; }
-    for (int64_t i = 0; i < n_seqs; i++) {
-        const int64_t len = seq_off[i + 1] - seq_off[i];
-        if (len < 0 || len > (int64_t) 0x7fffffff - 64) {
-            set_error("msb_seqs_from_ascii: sequence offsets not ascending or sequence >= 2^31 bases");
-            return MSB_EINVAL;
-        }
-    }
-    MSB_CUDA(cudaSetDevice(ctx->device));
+// Shared by msb_seqs_from_ascii and msb_seqs_extract: lay the sequences out in the packed space
+// (every sequence starts at a multiple of 32 bases), take the device buffers from the pool, upload
+// the per-sequence tables and clear the code / mask planes (the kernels that read windows rely on
+// zero padding behind the last block).  `seq_off` holds the n_seqs + 1 cumulative lengths.
+static int seqs_prepare(msb_ctx *ctx, int64_t n_seqs, const int64_t *seq_off, msb_seqs **out,
+                        std::vector<int32_t> &lens) {
     msb_seqs *S = new (std::nothrow) msb_seqs();
     if (!S) { set_error("out of host memory"); return MSB_ENOMEM; }
     S->ctx = ctx;
@@ -474,7 +464,7 @@ int msb_seqs_from_ascii(msb_ctx *ctx, int64_t n_seqs, const char *bytes, const i
     S->total_bp = seq_off[n_seqs];
     S->seq_off.assign(seq_off, seq_off + n_seqs + 1);
     S->poff.resize(n_seqs + 1);
-    std::vector<int32_t> lens((size_t) std::max<int64_t>(n_seqs, 1));
+    lens.assign((size_t) std::max<int64_t>(n_seqs, 1), 0);
     int64_t at = 0;
     int32_t min_len = n_seqs ? std::numeric_limits<int32_t>::max() : 0;
     for (int64_t i = 0; i < n_seqs; i++) {
@@ -498,20 +488,52 @@ int msb_seqs_from_ascii(msb_ctx *ctx, int64_t n_seqs, const char *bytes, const i
         (rc = dev_take(ctx, S->d_blk_seq, (size_t) std::max<int64_t>(n_blocks, 1) * 4)) != MSB_OK ||
         (rc = dev_take(ctx, S->d_poff, (size_t) (n_seqs + 1) * 8)) != MSB_OK ||
         (rc = dev_take(ctx, S->d_len, (size_t) std::max<int64_t>(n_seqs, 1) * 4)) != MSB_OK ||
-        (rc = dev_take(ctx, S->d_seq_off, (size_t) (n_seqs + 1) * 8)) != MSB_OK ||
-        (rc = ctx->ascii.ensure((size_t) std::max<int64_t>(S->total_bp, 16))) != MSB_OK) {
+        (rc = dev_take(ctx, S->d_seq_off, (size_t) (n_seqs + 1) * 8)) != MSB_OK) {
         msb_seqs_destroy(S);
         return rc;
     }
     cudaStream_t st = ctx->stream;
     cudaError_t e = cudaSuccess;
     auto step = [&](cudaError_t x) { if (e == cudaSuccess) e = x; };
-    step(cudaEventRecord(ctx->ev[0], st));
     step(cudaMemsetAsync(S->d_codes.p, 0, (size_t) (2 * n_blocks + 8) * 4, st));
     step(cudaMemsetAsync(S->d_nmask.p, 0, (size_t) (n_blocks + 4) * 4, st));
     step(cudaMemcpyAsync(S->d_poff.p, S->poff.data(), (size_t) (n_seqs + 1) * 8, cudaMemcpyHostToDevice, st));
     step(cudaMemcpyAsync(S->d_seq_off.p, S->seq_off.data(), (size_t) (n_seqs + 1) * 8, cudaMemcpyHostToDevice, st));
     if (n_seqs) step(cudaMemcpyAsync(S->d_len.p, lens.data(), (size_t) n_seqs * 4, cudaMemcpyHostToDevice, st));
+    if (e != cudaSuccess) {
+        msb_seqs_destroy(S);
+        return cuda_fail(e, "seqs_prepare", __FILE__, __LINE__);
+    }
+    *out = S;
+    return MSB_OK;
+}
+
+int msb_seqs_from_ascii(msb_ctx *ctx, int64_t n_seqs, const char *bytes, const int64_t *seq_off,
+                        msb_seqs **out) {
+    if (!ctx || !out || n_seqs < 0 || !seq_off || (seq_off[n_seqs] > 0 && !bytes)) {
+        set_error("msb_seqs_from_ascii: bad argument");
+        return MSB_EINVAL;
+    }
+    *out = nullptr;
+    if (seq_off[0] != 0) { set_error("seq_off[0] must be 0"); return MSB_EINVAL; }
+    for (int64_t i = 0; i < n_seqs; i++) {
+        const int64_t len = seq_off[i + 1] - seq_off[i];
+        if (len < 0 || len > (int64_t) 0x7fffffff - 64) {
+            set_error("msb_seqs_from_ascii: sequence offsets not ascending or sequence >= 2^31 bases");
+            return MSB_EINVAL;
+        }
+    }
+    MSB_CUDA(cudaSetDevice(ctx->device));
+    cudaStream_t st = ctx->stream;
+    MSB_CUDA(cudaEventRecord(ctx->ev[0], st));
+    msb_seqs *S = nullptr;
+    std::vector<int32_t> lens;
+    MSB_TRY(seqs_prepare(ctx, n_seqs, seq_off, &S, lens));
+    int rc = ctx->ascii.ensure((size_t) std::max<int64_t>(S->total_bp, 16));
+    if (rc != MSB_OK) { msb_seqs_destroy(S); return rc; }
+    const int64_t n_blocks = S->total_packed / kPadBases;
+    cudaError_t e = cudaSuccess;
+    auto step = [&](cudaError_t x) { if (e == cudaSuccess) e = x; };
     if (S->total_bp) step(cudaMemcpyAsync(ctx->ascii.p, bytes, (size_t) S->total_bp, cudaMemcpyHostToDevice, st));
     step(cudaEventRecord(ctx->ev[1], st));
     if (e == cudaSuccess && n_blocks > 0) {
@@ -530,6 +552,69 @@ int msb_seqs_from_ascii(msb_ctx *ctx, int64_t n_seqs, const char *bytes, const i
     ctx->t[MSB_T_H2D] = ev_ms(ctx->ev[0], ctx->ev[1]);
     ctx->t[MSB_T_ENCODE] = ev_ms(ctx->ev[1], ctx->ev[2]);
     *out = S;
+    return MSB_OK;
+}
+
+int msb_seqs_extract(msb_ctx *ctx, const msb_seqs *src, int64_t n, const int32_t *src_idx,
+                     const int64_t *start, const int64_t *end, msb_seqs **out) {
+    if (!ctx || !src || !out || n < 0 || (n > 0 && (!src_idx || !start || !end))) {
+        set_error("msb_seqs_extract: bad argument");
+        return MSB_EINVAL;
+    }
+    *out = nullptr;
+    if (src->ctx != ctx) { set_error("msb_seqs_extract: source belongs to another context"); return MSB_EINVAL; }
+    // pysam's fetch (genome/__init__.py:135) clips `end` at the sequence length; an interval that
+    // starts behind it, or is reversed, is empty.
+    std::vector<int64_t> seq_off((size_t) n + 1, 0), clipped_start((size_t) std::max<int64_t>(n, 1), 0);
+    for (int64_t i = 0; i < n; i++) {
+        if (src_idx[i] < 0 || src_idx[i] >= src->n) { set_error("msb_seqs_extract: source index out of range"); return MSB_EINVAL; }
+        if (start[i] < 0) { set_error("msb_seqs_extract: negative start"); return MSB_EINVAL; }
+        const int64_t slen = src->seq_off[src_idx[i] + 1] - src->seq_off[src_idx[i]];
+        const int64_t a = std::min(start[i], slen), b = std::min(end[i], slen);
+        clipped_start[i] = a;
+        seq_off[i + 1] = seq_off[i] + std::max<int64_t>(b - a, 0);
+    }
+    MSB_CUDA(cudaSetDevice(ctx->device));
+    cudaStream_t st = ctx->stream;
+    MSB_CUDA(cudaEventRecord(ctx->ev[0], st));
+    msb_seqs *S = nullptr;
+    std::vector<int32_t> lens;
+    MSB_TRY(seqs_prepare(ctx, n, seq_off.data(), &S, lens));
+    // the interval table rides in the (otherwise unused here) ASCII scratch: src_idx (4n) | start (8n)
+    const size_t idx_bytes = ((size_t) n * 4 + 15) & ~(size_t) 15;
+    int rc = ctx->ascii.ensure(std::max<size_t>(idx_bytes + (size_t) n * 8, 16));
+    if (rc != MSB_OK) { msb_seqs_destroy(S); return rc; }
+    const int64_t n_blocks = S->total_packed / kPadBases;
+    cudaError_t e = cudaSuccess;
+    auto step = [&](cudaError_t x) { if (e == cudaSuccess) e = x; };
+    if (n) {
+        step(cudaMemcpyAsync(ctx->ascii.p, src_idx, (size_t) n * 4, cudaMemcpyHostToDevice, st));
+        step(cudaMemcpyAsync((char *) ctx->ascii.p + idx_bytes, clipped_start.data(), (size_t) n * 8, cudaMemcpyHostToDevice, st));
+    }
+    step(cudaEventRecord(ctx->ev[1], st));
+    if (e == cudaSuccess && n_blocks > 0) {
+        const int64_t grid = (n_blocks + 255) / 256;
+        extract_pack_kernel<<<(unsigned) grid, 256, 0, st>>>(
+            src->view(), ctx->ascii.as<int32_t>(), (const int64_t *) ((char *) ctx->ascii.p + idx_bytes),
+            S->d_poff.as<int64_t>(), S->d_len.as<int32_t>(), n, n_blocks, S->d_codes.as<uint32_t>(),
+            S->d_nmask.as<uint32_t>(), S->d_blk_seq.as<int32_t>());
+        step(cudaGetLastError());
+    }
+    step(cudaEventRecord(ctx->ev[2], st));
+    step(cudaStreamSynchronize(st));  // host tables go out of scope
+    if (e != cudaSuccess) {
+        msb_seqs_destroy(S);
+        return cuda_fail(e, "msb_seqs_extract", __FILE__, __LINE__);
+    }
+    ctx->t[MSB_T_H2D] = ev_ms(ctx->ev[0], ctx->ev[1]);
+    ctx->t[MSB_T_ENCODE] = ev_ms(ctx->ev[1], ctx->ev[2]);
+    *out = S;
+    return MSB_OK;
+}
+
+int msb_seqs_lengths(const msb_seqs *S, int64_t *lens) {
+    if (!S || (!lens && S->n)) { set_error("msb_seqs_lengths: null"); return MSB_EINVAL; }
+    for (int64_t i = 0; i < S->n; i++) lens[i] = S->seq_off[i + 1] - S->seq_off[i];
     return MSB_OK;
 }
 
@@ -766,18 +851,20 @@ static float e4m3_value(int v) {
 }
 // smallest e4m3 value >= x, saturating at +-448; never the byte 0x80 (-0)
 static uint8_t e4m3_round_up(double x) {
+    static const std::vector<double> mag = [] {     // the 127 non-negative magnitudes, ascending
+        std::vector<double> v(0x7F);
+        for (int i = 0; i < 0x7F; i++) v[i] = (double) e4m3_value(i);
+        return v;
+    }();
     if (!(x > -448.0)) return 0xFE;  // -448 (also NaN -> most negative: cannot create candidates)
     if (x > 448.0) return 0x7E;
     if (x <= 0) {
         // largest magnitude <= |x| among the negatives, i.e. round towards zero
-        int best = 0x00;
-        for (int v = 0; v < 0x7F; v++)
-            if ((double) e4m3_value(v) <= -x) best = v; else break;
-        return best == 0 ? 0x00 : (uint8_t) (0x80 | best);
+        const int best = (int) (std::upper_bound(mag.begin(), mag.end(), -x) - mag.begin()) - 1;
+        return best <= 0 ? 0x00 : (uint8_t) (0x80 | best);
     }
-    for (int v = 0; v < 0x7F; v++)
-        if ((double) e4m3_value(v) >= x) return (uint8_t) v;
-    return 0x7E;
+    const int v = (int) (std::lower_bound(mag.begin(), mag.end(), x) - mag.begin());
+    return v >= 0x7F ? 0x7E : (uint8_t) v;
 }
 
 static inline size_t tc_byte(int ks_idx, int col, int k_in_step) {
@@ -915,7 +1002,7 @@ static int read_counters(msb_ctx *ctx) {
     return MSB_OK;
 }
 
-static int launch_positions(msb_ctx *ctx, const ExactParams &E, const int64_t *pos, int64_t n_pos,
+static int launch_positions(msb_ctx *ctx, const ExactParams &E, const int64_t *pos, int64_t n_pos, int64_t pos_base,
                             const int32_t *ids, int32_t n_ids) {
     // one thread per (position, motif); split so that a launch stays below 2^31 blocks
     if (n_pos <= 0 || n_ids <= 0) return MSB_OK;
@@ -926,12 +1013,10 @@ static int launch_positions(msb_ctx *ctx, const ExactParams &E, const int64_t *p
         const int64_t threads = cnt * n_ids;
         ExactParams e2 = E;
         if (pos) {
-            exact_positions_kernel<<<(unsigned) ((threads + 255) / 256), 256, 0, ctx->stream>>>(e2, pos + at, cnt, ids, n_ids);
+            exact_positions_kernel<<<(unsigned) ((threads + 255) / 256), 256, 0, ctx->stream>>>(e2, pos + at, cnt, 0, ids, n_ids);
         } else {
-            // pos == nullptr: the kernel takes the thread's position index as the packed position.
-            // Only one slice is supported (needs total_packed * n_ids <= 2^38 threads).
-            if (at != 0) { set_error("sequence set too large for the slow-motif path"); return MSB_EINVAL; }
-            exact_positions_kernel<<<(unsigned) ((threads + 255) / 256), 256, 0, ctx->stream>>>(e2, nullptr, cnt, ids, n_ids);
+            // pos == nullptr: the packed position is pos_base + the thread's position index
+            exact_positions_kernel<<<(unsigned) ((threads + 255) / 256), 256, 0, ctx->stream>>>(e2, nullptr, cnt, pos_base + at, ids, n_ids);
         }
         MSB_CUDA(cudaGetLastError());
         ctx->c[MSB_C_LAUNCHES]++;
@@ -943,12 +1028,41 @@ static int g_prefilter_w = 4;   // windows per thread of the table prefilter (4 
 static int g_tc_prof = std::getenv("MSB_TC_PROF") ? 1 : 0;   // 1: print per-role cycle counters of the tensor-core prefilter to stderr
 static int g_prefilter_tc = 1;  // 1: tensor-core prefilter (prefilter_tc.cuh), 0: shared-memory table prefilter
 
-static int scan_device(msb_ctx *ctx, msb_motifs *M, const msb_seqs *S, int strand, int flags) {
+// Packed-position ranges [lo, hi) of a range scan; nullptr = the whole sequence set.
+typedef std::vector<std::pair<int64_t, int64_t>> RangeList;
+
+static int make_ranges(const msb_seqs *S, int64_t n_ranges, const int64_t *r_seq, const int64_t *r_start,
+                       const int64_t *r_end, RangeList *out) {
+    if (n_ranges < 0 || (n_ranges > 0 && (!r_seq || !r_start || !r_end))) { set_error("msb_scan_ranges: bad ranges"); return MSB_EINVAL; }
+    out->clear();
+    for (int64_t i = 0; i < n_ranges; i++) {
+        if (r_seq[i] < 0 || r_seq[i] >= S->n) { set_error("msb_scan_ranges: sequence index out of range"); return MSB_EINVAL; }
+        if (r_start[i] < 0) { set_error("msb_scan_ranges: negative start"); return MSB_EINVAL; }
+        const int64_t slen = S->seq_off[r_seq[i] + 1] - S->seq_off[r_seq[i]];
+        const int64_t a = std::min(r_start[i], slen), b = std::min(r_end[i], slen);
+        if (b > a) out->push_back({S->poff[r_seq[i]] + a, S->poff[r_seq[i]] + b});
+    }
+    std::sort(out->begin(), out->end());
+    for (size_t i = 1; i < out->size(); i++)
+        if ((*out)[i].first < (*out)[i - 1].second) { set_error("msb_scan_ranges: ranges overlap"); return MSB_EINVAL; }
+    return MSB_OK;
+}
+
+static int scan_device(msb_ctx *ctx, msb_motifs *M, const msb_seqs *S, int strand, int flags,
+                       const RangeList *ranges = nullptr) {
     if (!ctx || !M || !S) { set_error("msb_scan: null argument"); return MSB_EINVAL; }
     if (strand < 1 || strand > 3) { set_error("msb_scan: strand must be 1, 2 or 3"); return MSB_EINVAL; }
     if (M->ctx != ctx || S->ctx != ctx) { set_error("msb_scan: motifs/seqs belong to another context"); return MSB_EINVAL; }
     MSB_CUDA(cudaSetDevice(ctx->device));
     const bool use_tc = g_prefilter_tc != 0;
+    if (ranges && !use_tc) { set_error("msb_scan_ranges needs the tensor-core prefilter (prefilter_tc = 1)"); return MSB_EINVAL; }
+    RangeList whole;
+    if (!ranges) {
+        if (S->total_packed) whole.push_back({0, S->total_packed});
+        ranges = &whole;
+    }
+    int64_t span = 0;
+    for (auto &r : *ranges) span += r.second - r.first;
     TableSet *T = nullptr;
     TcTableSet *TT = nullptr;
     if (use_tc) MSB_TRY(ensure_tc_tables(ctx, M, strand, &TT));
@@ -965,7 +1079,7 @@ static int scan_device(msb_ctx *ctx, msb_motifs *M, const msb_seqs *S, int stran
     ctx->last_n_motifs = M->n;
     MSB_TRY(ctx->out_counts.ensure((size_t) (M->n + 1) * 8));  // CSR offsets over motifs
     MSB_CUDA(cudaMemsetAsync(ctx->out_counts.p, 0, (size_t) (M->n + 1) * 8, st));
-    if (M->n == 0 || S->total_packed == 0) {
+    if (M->n == 0 || span == 0) {
         MSB_CUDA(cudaStreamSynchronize(st));
         return MSB_OK;
     }
@@ -973,9 +1087,9 @@ static int scan_device(msb_ctx *ctx, msb_motifs *M, const msb_seqs *S, int stran
     const MotifView mv = M->view();
 
     // ---- stage 1: prefilter ------------------------------------------------------------------
-    const double cells = (double) S->total_packed * (double) std::max<int32_t>(n_fast, 1);
+    const double cells = (double) span * (double) std::max<int32_t>(n_fast, 1);
     int64_t cand_cap = (int64_t) std::min<double>(std::max<double>(cells / 512.0, 1 << 20), (double) (1ll << 30));
-    int64_t dirty_cap = std::max<int64_t>(1 << 16, S->total_packed / 64);
+    int64_t dirty_cap = std::max<int64_t>(1 << 16, span / 64);
     if (ctx->cand.cap / 8 > (size_t) cand_cap) cand_cap = (int64_t) (ctx->cand.cap / 8);
     if (ctx->dirty.cap / 8 > (size_t) dirty_cap) dirty_cap = (int64_t) (ctx->dirty.cap / 8);
     int64_t n_cand = 0, n_dirty = 0;
@@ -1002,17 +1116,22 @@ static int scan_device(msb_ctx *ctx, msb_motifs *M, const msb_seqs *S, int stran
                 MSB_CUDA(cudaMemsetAsync(prof.p, 0, (size_t) (ctx->sm_count + 16) * 16 * 8, st));
                 P.prof = prof.as<long long>();
             }
-            const int64_t n_ptiles = (S->total_packed + kTcTileBases - 1) / kTcTileBases;
-            const unsigned grid = (unsigned) std::min<int64_t>(ctx->sm_count, n_ptiles);
             const size_t smem = kTcSmemBytes;  // > half an SM's shared memory: one CTA per SM, which owns the TMEM
-            for (size_t b = 0; b < TT->batches.size(); b++) {
-                P.batch = TT->batches[b];
-                P.emit_dirty = (b == 0);
-                if (g_tc_prof) prefilter_tc_kernel<true><<<grid, kTcThreads, smem, st>>>(P);
-                else prefilter_tc_kernel<false><<<grid, kTcThreads, smem, st>>>(P);
-                MSB_CUDA(cudaGetLastError());
-                ctx->c[MSB_C_LAUNCHES]++;
-                ctx->c[MSB_C_PREFILTER_LAUNCHES]++;
+            unsigned grid = 1;
+            for (auto &r : *ranges) {
+                P.pos_lo = r.first;
+                P.pos_hi = r.second;
+                const int64_t n_ptiles = (r.second + kTcTileBases - 1) / kTcTileBases - r.first / kTcTileBases;
+                grid = (unsigned) std::min<int64_t>(ctx->sm_count, n_ptiles);
+                for (size_t b = 0; b < TT->batches.size(); b++) {
+                    P.batch = TT->batches[b];
+                    P.emit_dirty = (b == 0);
+                    if (g_tc_prof) prefilter_tc_kernel<true><<<grid, kTcThreads, smem, st>>>(P);
+                    else prefilter_tc_kernel<false><<<grid, kTcThreads, smem, st>>>(P);
+                    MSB_CUDA(cudaGetLastError());
+                    ctx->c[MSB_C_LAUNCHES]++;
+                    ctx->c[MSB_C_PREFILTER_LAUNCHES]++;
+                }
             }
             if (g_tc_prof) {
                 std::vector<long long> h((size_t) (ctx->sm_count + 16) * 16);
@@ -1104,7 +1223,8 @@ static int scan_device(msb_ctx *ctx, msb_motifs *M, const msb_seqs *S, int stran
             ctx->c[MSB_C_LAUNCHES]++;
         }
         if (n_slow)
-            MSB_TRY(launch_positions(ctx, E, nullptr, S->total_packed, d_slow, n_slow));
+            for (auto &r : *ranges)
+                MSB_TRY(launch_positions(ctx, E, nullptr, r.second - r.first, r.first, d_slow, n_slow));
         MSB_CUDA(cudaEventRecord(ctx->ev[2], st));
         MSB_TRY(read_counters(ctx));
         n_hits = (int64_t) ctx->h_counters[2];
@@ -1223,10 +1343,37 @@ int msb_scan_device_counts(msb_ctx *ctx, int64_t *counts, int32_t n_motifs) {
     return MSB_OK;
 }
 
+int msb_scan_ranges_device(msb_ctx *ctx, const msb_motifs *M, const msb_seqs *S, int strand, int flags,
+                           int64_t n_ranges, const int64_t *seq_idx, const int64_t *start, const int64_t *end,
+                           int64_t *n_sites) {
+    if (!S) { set_error("msb_scan_ranges: null seqs"); return MSB_EINVAL; }
+    RangeList ranges;
+    MSB_TRY(make_ranges(S, n_ranges, seq_idx, start, end, &ranges));
+    MSB_TRY(scan_device(ctx, const_cast<msb_motifs *>(M), S, strand, flags, &ranges));
+    if (n_sites) *n_sites = ctx->last_sites;
+    return MSB_OK;
+}
+
+static int collect_result(msb_ctx *ctx, const msb_motifs *M, msb_result **out);
+
+int msb_scan_ranges(msb_ctx *ctx, const msb_motifs *M, const msb_seqs *S, int strand, int flags,
+                    int64_t n_ranges, const int64_t *seq_idx, const int64_t *start, const int64_t *end,
+                    msb_result **out) {
+    if (!out) { set_error("msb_scan_ranges: null out"); return MSB_EINVAL; }
+    *out = nullptr;
+    MSB_TRY(msb_scan_ranges_device(ctx, M, S, strand, flags, n_ranges, seq_idx, start, end, nullptr));
+    return collect_result(ctx, M, out);
+}
+
 int msb_scan_ex(msb_ctx *ctx, const msb_motifs *M, const msb_seqs *S, int strand, int flags, msb_result **out) {
     if (!out) { set_error("msb_scan: null out"); return MSB_EINVAL; }
     *out = nullptr;
     MSB_TRY(scan_device(ctx, const_cast<msb_motifs *>(M), S, strand, flags));
+    return collect_result(ctx, M, out);
+}
+
+// Sites of the last scan_device on this context -> pinned host memory.
+static int collect_result(msb_ctx *ctx, const msb_motifs *M, msb_result **out) {
     msb_result *R = new (std::nothrow) msb_result();
     if (!R) { set_error("out of host memory"); return MSB_ENOMEM; }
     R->ctx = ctx;

@@ -64,6 +64,7 @@ struct TcParams {
     int32_t lmax_all;
     int32_t emit_dirty;
     int32_t any_zero_hit;
+    int64_t pos_lo, pos_hi;    // only windows starting at packed positions [pos_lo, pos_hi) are scored (range scans)
     uint64_t *cand;            // raw candidates: key(tile * 256 + column, packed position, 0)
     int64_t cand_cap;
     int64_t *dirty;
@@ -292,7 +293,9 @@ prefilter_tc_kernel(const __grid_constant__ TcParams P) {
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const SeqView &S = P.seq;
-    const int64_t n_ptiles = (S.total_packed + kTcTileBases - 1) / kTcTileBases;
+    // position tiles [pt_first + blockIdx.x, pt_end) in steps of gridDim.x
+    const int64_t pt_first = P.pos_lo / kTcTileBases + blockIdx.x;
+    const int64_t n_ptiles = (P.pos_hi + kTcTileBases - 1) / kTcTileBases;
 
     if (threadIdx.x == 0) {
         for (int i = 0; i < kTcSlots; i++) { mbar_init(&bar_stream_full[i], 3); mbar_init(&bar_stream_empty[i], 1 + kTcEpiWarps); }
@@ -334,7 +337,7 @@ prefilter_tc_kernel(const __grid_constant__ TcParams P) {
         uint32_t u = 0, it = 0;
         long long t_ws = 0, t_we = 0, t_is = 0;
         const long long t_begin = now();
-        for (int64_t t = blockIdx.x; t < n_ptiles; t += gridDim.x, it++) {
+        for (int64_t t = pt_first; t < n_ptiles; t += gridDim.x, it++) {
             const uint32_t slot = it % kTcSlots;
             long long c0 = now();
             mbar_wait_a(B.stream_full + 8 * slot, (it / kTcSlots) & 1);
@@ -385,7 +388,7 @@ prefilter_tc_kernel(const __grid_constant__ TcParams P) {
         const int tid_p = (warp - 1) * 32 + lane;
         const uint32_t horizon = P.lmax_all >= 32 ? 0xffffffffu : ((1u << P.lmax_all) - 1u);
         uint32_t it = 0;
-        for (int64_t t = blockIdx.x; t < n_ptiles; t += gridDim.x, it++) {
+        for (int64_t t = pt_first; t < n_ptiles; t += gridDim.x, it++) {
             const uint32_t slot = it % kTcSlots;
             mbar_wait_a(B.stream_empty + 8 * slot, ((it / kTcSlots) & 1) ^ 1);
             const int64_t tile_start = t * kTcTileBases;
@@ -414,7 +417,10 @@ prefilter_tc_kernel(const __grid_constant__ TcParams P) {
                         const int64_t j0 = q0 - __ldg(S.poff + s);
                         const int64_t left = (int64_t) __ldg(S.len + s) - j0;
                         const int nvalid = left <= 0 ? 0 : (left >= 32 ? 32 : (int) left);
-                        const uint32_t valid = nvalid >= 32 ? 0xffffffffu : ((1u << nvalid) - 1u);
+                        uint32_t valid = nvalid >= 32 ? 0xffffffffu : ((1u << nvalid) - 1u);
+                        // range scans: starts outside [pos_lo, pos_hi) belong to another call
+                        if (q0 < P.pos_lo) valid &= P.pos_lo - q0 >= 32 ? 0u : ~((1u << (int) (P.pos_lo - q0)) - 1u);
+                        if (q0 + 32 > P.pos_hi) valid &= P.pos_hi <= q0 ? 0u : ((1u << (int) (P.pos_hi - q0)) - 1u);
                         const uint64_t m64 = ((uint64_t) __ldg(S.nmask + blk + 1) << 32) | __ldg(S.nmask + blk);
                         uint32_t dirtym = 0, emitm = 0;
 #pragma unroll 1
@@ -455,7 +461,7 @@ prefilter_tc_kernel(const __grid_constant__ TcParams P) {
         const uint32_t colid0 = P.batch.first_tile * kTcCols + h * kTcWarpCols;
         uint32_t u = 0, it = 0;
         long long t_wf = 0, t_ld = 0, t_pr = 0, t_wsf = 0, t_slow = 0, n_slow = 0;
-        for (int64_t t = blockIdx.x; t < n_ptiles; t += gridDim.x, it++) {
+        for (int64_t t = pt_first; t < n_ptiles; t += gridDim.x, it++) {
             const uint32_t slot = it % kTcSlots;
             const long long cs = now();
             mbar_wait_a(B.stream_full + 8 * slot, (it / kTcSlots) & 1);

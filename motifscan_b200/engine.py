@@ -109,9 +109,19 @@ class MotifSet:
 class SequenceSet:
     """Device-resident packed sequences (msb_seqs): 2-bit codes + N mask."""
 
-    def __init__(self, ctx, seqs=None, blob=None, seq_off=None):
+    def __init__(self, ctx, seqs=None, blob=None, seq_off=None, _handle=None):
         self.ctx = ctx
         self._lib = ctx._lib
+        if _handle is not None:
+            self._h = _handle
+            n, bp = ctypes.c_int64(0), ctypes.c_int64(0)
+            check(self._lib.msb_seqs_count(self._h, ctypes.byref(n), ctypes.byref(bp)))
+            self.n, self.total_bp = n.value, bp.value
+            lens = np.zeros(max(self.n, 1), dtype=np.int64)
+            check(self._lib.msb_seqs_lengths(self._h, ptr(lens, ctypes.c_int64)))
+            self.seq_off = np.zeros(self.n + 1, dtype=np.int64)
+            np.cumsum(lens[:self.n], out=self.seq_off[1:])
+            return
         if seqs is not None:
             blob, seq_off = _lib.flatten_seqs(seqs)
         blob = np.ascontiguousarray(blob, dtype=np.uint8) if not isinstance(blob, np.ndarray) else blob
@@ -123,6 +133,20 @@ class SequenceSet:
         data = blob.ctypes.data if blob.size else None
         check(self._lib.msb_seqs_from_ascii(ctx._h, self.n, ctypes.c_void_p(data), ptr(seq_off, ctypes.c_int64),
                                             ctypes.byref(self._h)))
+
+    def extract(self, src_idx, start, end):
+        """A new sequence set cut out of this (resident) one on the device: sequence i = bases
+        [start[i], end[i]) of sequence src_idx[i], `end` clipped at the source length like
+        pysam's fetch (genome/__init__.py:135).  No sequence bytes cross PCIe."""
+        src_idx = np.ascontiguousarray(np.asarray(src_idx, dtype=np.int32))
+        start = np.ascontiguousarray(np.asarray(start, dtype=np.int64))
+        end = np.ascontiguousarray(np.asarray(end, dtype=np.int64))
+        if not (src_idx.shape == start.shape == end.shape and src_idx.ndim == 1):
+            raise ValueError("src_idx, start and end must be 1-d arrays of one length")
+        h = ctypes.c_void_p()
+        check(self._lib.msb_seqs_extract(self.ctx._h, self._h, len(src_idx), ptr(src_idx, ctypes.c_int32),
+                                         ptr(start, ctypes.c_int64), ptr(end, ctypes.c_int64), ctypes.byref(h)))
+        return SequenceSet(self.ctx, _handle=h)
 
     def set_start_limit(self, limit):
         """Windows may only start at the first limit[i] positions of sequence i (chunked genome
@@ -221,6 +245,32 @@ def scan_device(ctx, motifs, seqs, strand, remove_dup=False):
     flags = _lib.MSB_SCAN_DEDUP if remove_dup else 0
     check(ctx._lib.msb_scan_device(ctx._h, motifs._h, seqs._h, int(strand), flags, ctypes.byref(n)))
     return n.value
+
+
+def _ranges(ranges):
+    r = np.ascontiguousarray(np.asarray(ranges, dtype=np.int64).reshape(-1, 3))
+    return (len(r), np.ascontiguousarray(r[:, 0]), np.ascontiguousarray(r[:, 1]), np.ascontiguousarray(r[:, 2]))
+
+
+def scan_ranges(ctx, motifs, seqs, strand, ranges, remove_dup=False):
+    """Scan only the windows that start in the given (sequence index, start, end) ranges of a
+    resident sequence set; sites refer to the sequences of `seqs` (msb_scan_ranges)."""
+    n, a, b, c = _ranges(ranges)
+    h = ctypes.c_void_p()
+    flags = _lib.MSB_SCAN_DEDUP if remove_dup else 0
+    check(ctx._lib.msb_scan_ranges(ctx._h, motifs._h, seqs._h, int(strand), flags, n, ptr(a, ctypes.c_int64),
+                                   ptr(b, ctypes.c_int64), ptr(c, ctypes.c_int64), ctypes.byref(h)))
+    return ScanResult(ctx, h, motifs.n)
+
+
+def scan_ranges_device(ctx, motifs, seqs, strand, ranges, remove_dup=False):
+    """The same, results left on the device (`ctx.site_counts`); returns the number of sites."""
+    n, a, b, c = _ranges(ranges)
+    total = ctypes.c_int64(0)
+    flags = _lib.MSB_SCAN_DEDUP if remove_dup else 0
+    check(ctx._lib.msb_scan_ranges_device(ctx._h, motifs._h, seqs._h, int(strand), flags, n, ptr(a, ctypes.c_int64),
+                                          ptr(b, ctypes.c_int64), ptr(c, ctypes.c_int64), ctypes.byref(total)))
+    return total.value
 
 
 def score(ctx, motifs, seqs, strand):

@@ -132,6 +132,50 @@ class Genome:
             attempt += 1
 
 
+class DeviceGenome:
+    """The chromosomes of a genome encoded once (2-bit codes + N mask, 0.375 B/bp) and kept resident
+    in one GPU's HBM.
+
+    The reference fetches every region's sequence from the FASTA through pysam
+    (scanner.py:76-87 -> genome/__init__.py:135) and hands strings to the extension; here a
+    `Scanner` built on a DeviceGenome ships (chromosome, start, end) descriptors and the device
+    cuts the packed windows out of the resident copy (`msb_seqs_extract`), and a genome-wide scan
+    walks position ranges of the resident chromosomes (`msb_scan_ranges`).  Everything else
+    (`chroms`, `chrom_sizes`, `fetch_sequence`, `random_sequences`, `bg_freq`, ...) is the
+    wrapped host genome's."""
+
+    def __init__(self, genome, ctx=None, device=0):
+        from . import engine
+        self.genome = genome
+        self.ctx = ctx or engine.default_context(device)
+        self.chroms = list(genome.chroms)
+        self.chrom_sizes = {c: int(genome.chrom_sizes[c]) for c in self.chroms}
+        self.chrom_index = {c: i for i, c in enumerate(self.chroms)}
+        off = np.zeros(len(self.chroms) + 1, dtype=np.int64)
+        np.cumsum([self.chrom_sizes[c] for c in self.chroms], out=off[1:])
+        blob = np.empty(int(off[-1]), dtype=np.uint8)
+        fetch = getattr(genome, "fetch_bytes", None)
+        for i, c in enumerate(self.chroms):
+            raw = fetch(c, 0, self.chrom_sizes[c]) if fetch else genome.fetch_sequence(c, 0, self.chrom_sizes[c]).encode()
+            if len(raw) != off[i + 1] - off[i]:
+                raise ValueError(f"chromosome {c}: fetched {len(raw)} bases, index says {off[i + 1] - off[i]}")
+            blob[off[i]:off[i + 1]] = np.frombuffer(raw, dtype=np.uint8)
+        self.seqs = engine.SequenceSet(self.ctx, blob=blob, seq_off=off)
+
+    def __getattr__(self, name):
+        # only reached for attributes this class does not define: delegate to the host genome
+        return getattr(self.__dict__["genome"], name)
+
+    def extract(self, chroms, starts, ends):
+        """Device sequence set of the intervals [start, end) (end clipped at the chromosome size);
+        an unknown chromosome raises KeyError like `Genome.fetch_sequence`."""
+        idx = np.fromiter((self.chrom_index[c] for c in chroms), dtype=np.int32, count=len(chroms))
+        return self.seqs.extract(idx, starts, ends)
+
+    def close(self):
+        self.seqs.close()
+
+
 def read_bg_freq(path):
     """`Base<TAB>Frequency` table for A, C, G, T (reference genome/__init__.py:223-260)."""
     freq = {}

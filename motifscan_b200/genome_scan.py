@@ -2,12 +2,18 @@
 every chromosome, chunked and sharded over the GPUs of a box.
 
 The reference would scan a chromosome as one string (`c_scan_motif` over a list with one sequence
-per chromosome, cscore.c:336-389).  Here a chromosome is cut into chunks of `chunk_bp` window
-starts, each fetched with a right overlap of (longest motif - 1) bases; the device drops sites
-whose start lies in the overlap (`msb_seqs_set_start_limit`), so every window is reported exactly
-once, by the chunk that holds its start, and the union equals the unchunked scan bit for bit.
-Chunks are dealt to ranks longest-first (`shard.assign_lpt`); ranks never exchange data -- the only
-cross-rank step is the caller's gather of the per-motif counts / site arrays.
+per chromosome, cscore.c:336-389).  Two paths produce the same sites bit for bit:
+
+* resident (default): the genome is encoded once into HBM (`genome.DeviceGenome`, 0.375 B/bp) and
+  each chunk is a position RANGE of a resident chromosome (`msb_scan_ranges`): only windows that
+  start inside the range are scored, and they read on into the rest of the chromosome, so no
+  overlap is shipped and nothing is scored twice.  Chunks are dealt round-robin to the ranks.
+* streamed (`resident=False`): a chunk is fetched from the host genome with a right overlap of
+  (longest motif - 1) bases; the device drops sites whose start lies in the overlap
+  (`msb_seqs_set_start_limit`).  Chunks are dealt to ranks longest-first (`shard.assign_lpt`).
+
+Ranks never exchange data -- the only cross-rank step is the caller's gather of the per-motif
+counts / site arrays.
 """
 import ctypes
 
@@ -32,6 +38,105 @@ class GenomeSites:
         return int(self.counts.sum())
 
 
+def _merge_parts(parts, n_motifs):
+    """Per-batch motif-major results -> one motif-major list.  Batches are scanned in ascending
+    (chromosome, start) order and never overlap, so motif m's sites are the concatenation of its
+    slice of every batch: no sort."""
+    if not parts:
+        return (np.zeros(0, np.int32), np.zeros(0, np.int32), np.zeros(0, np.int32), np.zeros(0, np.float64),
+                np.zeros(0, np.int8))
+    if len(parts) == 1:
+        c, cidx, start, score, strand = parts[0]
+        return np.repeat(np.arange(n_motifs, dtype=np.int32), c), cidx, start, score, strand
+    counts = np.stack([p[0] for p in parts])                  # [batch][motif]
+    offs = np.zeros((len(parts), n_motifs + 1), dtype=np.int64)
+    np.cumsum(counts, axis=1, out=offs[:, 1:])
+    total = int(counts.sum())
+    out_off = np.zeros(n_motifs + 1, dtype=np.int64)
+    np.cumsum(counts.sum(axis=0), out=out_off[1:])
+    cidx, start = np.empty(total, np.int32), np.empty(total, np.int32)
+    score, strand = np.empty(total, np.float64), np.empty(total, np.int8)
+    at = out_off[:-1].copy()
+    for b, (_, c, s, sc, st) in enumerate(parts):
+        for m in np.nonzero(counts[b])[0]:
+            a, e = offs[b, m], offs[b, m + 1]
+            d = at[m]
+            cidx[d:d + e - a], start[d:d + e - a] = c[a:e], s[a:e]
+            score[d:d + e - a], strand[d:d + e - a] = sc[a:e], st[a:e]
+            at[m] += e - a
+    motif = np.repeat(np.arange(n_motifs, dtype=np.int32), np.diff(out_off))
+    return motif, cidx, start, score, strand
+
+
+def plan_ranges(chrom_sizes, chunk_bp, world=1, rank=0):
+    """This rank's (chrom, start, end) ranges for the resident path: chromosomes in the given
+    order cut every `chunk_bp` window starts, dealt round-robin (chunk k -> rank k % world).
+    Ascending (chromosome, start) order within a rank."""
+    out = []
+    k = 0
+    for chrom, size in chrom_sizes.items():
+        for start in range(0, size, chunk_bp):
+            if k % world == rank:
+                out.append((chrom, start, min(start + chunk_bp, size)))
+            k += 1
+    return out
+
+
+def scan_genome_resident(dgenome, pwms, p_value="1e-4", strand="both", chunk_bp=1 << 22, batch_bp=1 << 29,
+                         world=1, rank=0, collect_sites=True, cutoffs=None, motifs=None, stats=None):
+    """Range scan of a `genome.DeviceGenome`.  `motifs`: an engine.MotifSet to reuse (cutoffs set);
+    `stats`: a dict that receives the summed device milliseconds per phase and the batch count."""
+    ctx = dgenome.ctx
+    matrices = [getattr(pwm, "matrix", pwm) for pwm in pwms]
+    own_motifs = motifs is None
+    if own_motifs:
+        if cutoffs is None:
+            cutoffs = [pwm.cutoffs[p_value] for pwm in pwms]
+        motifs = engine.MotifSet(ctx, matrices, cutoffs)
+    chroms = list(dgenome.chroms)
+    sizes = {c: dgenome.chrom_sizes[c] for c in chroms}
+    ranges = plan_ranges(sizes, chunk_bp, world, rank)
+    counts = np.zeros(len(matrices), dtype=np.int64)
+    parts, held = [], []
+    try:
+        i = 0
+        while i < len(ranges):
+            batch, total = [], 0
+            while i < len(ranges) and (not batch or total + ranges[i][2] - ranges[i][1] <= batch_bp):
+                c, a, e = ranges[i]
+                if batch and batch[-1][0] == dgenome.chrom_index[c] and batch[-1][2] == a:
+                    batch[-1][2] = e                      # adjacent chunks of one chromosome: one range
+                else:
+                    batch.append([dgenome.chrom_index[c], a, e])
+                total += e - a
+                i += 1
+            if collect_sites:
+                res = engine.scan_ranges(ctx, motifs, dgenome.seqs, _STRAND_ARG[strand], batch)
+                counts += res.counts
+                # the arrays stay views into the result's pinned block (kept alive by `held`): no host copy
+                parts.append((res.counts.copy(), res.seq_idx, res.start, res.score, res.strand))
+                held.append(res)
+            else:
+                engine.scan_ranges_device(ctx, motifs, dgenome.seqs, _STRAND_ARG[strand], batch)
+                counts += ctx.site_counts(len(matrices))
+            if stats is not None:
+                t = ctx.timings()
+                for k in ("prefilter", "exact", "order", "d2h"):
+                    stats[k] = stats.get(k, 0.0) + t[k]
+                stats["batches"] = stats.get("batches", 0) + 1
+    finally:
+        if own_motifs:
+            motifs.close()
+    motif, cidx, start, score, strnd = _merge_parts(parts, len(matrices))
+    out = GenomeSites(chroms, len(matrices), counts, motif, cidx, start, score, strnd)
+    if len(held) == 1:
+        out._result = held[0]        # single batch: the site arrays ARE the pinned result block
+    else:
+        for res in held:
+            res.close()
+    return out
+
+
 def plan_chunks(chrom_sizes, chunk_bp, halo, world=1, rank=0):
     """This rank's chunks as (chrom, start, end, fetch_end), in (chromosome, start) order."""
     chunks = shard.genome_chunks(chrom_sizes, chunk_bp, halo)
@@ -42,11 +147,24 @@ def plan_chunks(chrom_sizes, chunk_bp, halo, world=1, rank=0):
 
 
 def scan_genome(genome, pwms, p_value="1e-4", strand="both", chunk_bp=1 << 22, batch_bp=1 << 28,
-                ctx=None, world=1, rank=0, collect_sites=True, cutoffs=None):
+                ctx=None, world=1, rank=0, collect_sites=True, cutoffs=None, resident=True):
     """Scan all chromosomes of `genome` (anything with `.chroms`, `.chrom_sizes`, `.fetch_bytes`).
 
     Returns a GenomeSites for this rank's chunks (`collect_sites=False`: counts only, the site
-    arrays stay empty and nothing but the counts leaves the device)."""
+    arrays stay empty and nothing but the counts leaves the device).  A `genome.DeviceGenome` is
+    scanned in place; a host genome is first made resident (`resident=True`, the default) or
+    streamed chunk by chunk with overlaps (`resident=False`)."""
+    if hasattr(genome, "chrom_index") and hasattr(genome, "seqs"):
+        return scan_genome_resident(genome, pwms, p_value, strand, chunk_bp, batch_bp, world, rank,
+                                    collect_sites, cutoffs)
+    if resident:
+        from .genome import DeviceGenome
+        dg = DeviceGenome(genome, ctx or engine.default_context(0))
+        try:
+            return scan_genome_resident(dg, pwms, p_value, strand, chunk_bp, batch_bp, world, rank,
+                                        collect_sites, cutoffs)
+        finally:
+            dg.close()
     if cutoffs is None:
         cutoffs = [pwm.cutoffs[p_value] for pwm in pwms]
     matrices = [getattr(pwm, "matrix", pwm) for pwm in pwms]

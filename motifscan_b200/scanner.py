@@ -37,7 +37,11 @@ class Scanner:
         self.seq_starts = []
         self.seq_ends = []
         self._chunks = []
+        self._chroms = []
         self._sequences = None
+        # a genome.DeviceGenome keeps the packed chromosomes in HBM: windows are cut out on the device
+        self._resident = genome if hasattr(genome, "extract") and hasattr(genome, "chrom_index") else None
+        self._genome = genome
         self._extract_seq(genome, regions)
 
     def _extract_seq(self, genome, regions):
@@ -53,7 +57,10 @@ class Scanner:
                 end = min(region.summit + self.extend, sizes[region.chrom])
             self.seq_starts.append(start)
             self.seq_ends.append(end)
-            if fetch is not None:
+            if self._resident is not None:
+                self._resident.chrom_index[region.chrom]   # KeyError for unknown chromosomes, as fetch raises
+                self._chroms.append(region.chrom)
+            elif fetch is not None:
                 self._chunks.append(fetch(region.chrom, start, end))
             else:
                 self._chunks.append(genome.fetch_sequence(region.chrom, start, end).encode("utf-8"))
@@ -61,7 +68,11 @@ class Scanner:
     @property
     def sequences(self):
         if self._sequences is None:
-            self._sequences = [c.decode("utf-8") for c in self._chunks]
+            if self._resident is not None:   # only materialised when somebody asks for the strings
+                self._sequences = [self._genome.fetch_sequence(c, a, b)
+                                   for c, a, b in zip(self._chroms, self.seq_starts, self.seq_ends)]
+            else:
+                self._sequences = [c.decode("utf-8") for c in self._chunks]
         return self._sequences
 
     def _flat(self):
@@ -79,6 +90,8 @@ class Scanner:
                 cutoffs.append(pwm.cutoffs[self.p_value])
             except (TypeError, KeyError):
                 raise ValueError(f"PWM has no motif score cutoff set for P-value {self.p_value!r}")
+        if self._resident is not None:
+            ctx = self._resident.ctx       # the windows live where the genome lives
         if ctx is None:
             dev = self.device
             if dev is None:
@@ -90,8 +103,11 @@ class Scanner:
             return MotifSites(None, 0, self.seq_starts, lengths)
         motifs = engine.MotifSet(ctx, matrices, cutoffs)
         try:
-            blob, off = self._flat()
-            sset = engine.SequenceSet(ctx, blob=blob, seq_off=off)
+            if self._resident is not None:
+                sset = self._resident.extract(self._chroms, self.seq_starts, self.seq_ends)
+            else:
+                blob, off = self._flat()
+                sset = engine.SequenceSet(ctx, blob=blob, seq_off=off)
             try:
                 res = engine.scan(ctx, motifs, sset, _STRAND_ARG[self.strand], remove_dup=self.remove_dup)
             finally:

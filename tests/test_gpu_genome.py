@@ -1,12 +1,15 @@
 """Genome-wide chunked scan (configs[3]) == the reference's scan of whole chromosomes, bit for bit:
-chunking with overlap + device-side start limits must neither lose nor duplicate a window, for any
-chunk size and any rank count."""
+neither the resident path (position ranges of chromosomes kept in HBM) nor the streamed path
+(chunks with overlap + device-side start limits) may lose or duplicate a window, for any chunk
+size and any rank count.  Also: windows cut out of the resident genome on the device
+(msb_seqs_extract) == the same windows sent as ASCII."""
 import numpy as np
 import pytest
 
 import oracle
 from motifscan_b200 import engine
-from motifscan_b200.genome_scan import plan_chunks, scan_genome
+from motifscan_b200.genome import DeviceGenome
+from motifscan_b200.genome_scan import plan_chunks, plan_ranges, scan_genome
 from test_gpu_parity import cutoffs_for, synth_pwms
 
 pytestmark = pytest.mark.gpu
@@ -29,6 +32,9 @@ class ToyGenome:
     def fetch_bytes(self, chrom, start, end):
         return self.seqs[chrom][start:end]
 
+    def fetch_sequence(self, chrom, start, end):
+        return self.seqs[chrom][start:end].decode()
+
 
 @pytest.fixture(scope="module")
 def setup():
@@ -50,11 +56,12 @@ def assert_same(sites, expect):
     assert np.array_equal(sites.score.view(np.uint64), score.view(np.uint64))
 
 
+@pytest.mark.parametrize("resident", [True, False])
 @pytest.mark.parametrize("chunk_bp,batch_bp", [(1 << 22, 1 << 28), (10000, 64000), (4099, 9000), (512, 5000)])
-def test_chunked_scan_equals_whole_chromosome_scan(setup, chunk_bp, batch_bp):
+def test_chunked_scan_equals_whole_chromosome_scan(setup, chunk_bp, batch_bp, resident):
     genome, pwms, cutoffs, expect = setup
     sites = scan_genome(genome, pwms, cutoffs=cutoffs, chunk_bp=chunk_bp, batch_bp=batch_bp,
-                        ctx=engine.default_context(0))
+                        ctx=engine.default_context(0), resident=resident)
     assert_same(sites, expect)
     assert len(sites) > 1000
 
@@ -68,7 +75,7 @@ def test_rank_shards_partition_the_genome(setup):
     all_chunks = sorted(c for p in plans for c in p)
     assert all_chunks == sorted(plan_chunks(genome.chrom_sizes, 7000, 29))
     parts = [scan_genome(genome, pwms, cutoffs=cutoffs, chunk_bp=7000, batch_bp=50000, world=world, rank=r,
-                         ctx=engine.default_context(0)) for r in range(world)]
+                         ctx=engine.default_context(0), resident=False) for r in range(world)]
     assert np.array_equal(sum(p.counts for p in parts), expect[0])
     motif = np.concatenate([p.motif for p in parts])
     cidx = np.concatenate([p.chrom_idx for p in parts])
@@ -82,6 +89,104 @@ def test_rank_shards_partition_the_genome(setup):
     # loads are balanced by the longest-first deal
     loads = [sum(c[2] - c[1] for c in p) for p in plans]
     assert max(loads) - min(loads) <= 7000
+
+
+def merged(parts):
+    motif = np.concatenate([p.motif for p in parts])
+    cidx = np.concatenate([p.chrom_idx for p in parts])
+    start = np.concatenate([p.start for p in parts])
+    score = np.concatenate([p.score for p in parts])
+    strand = np.concatenate([p.strand for p in parts])
+    order = np.lexsort((strand, start, cidx, motif))
+    return motif[order], cidx[order], start[order], score[order], strand[order]
+
+
+def test_resident_rank_shards_partition_the_genome(setup):
+    """Resident path, three ranks sharing ONE device-resident genome: round-robin ranges are a
+    partition, per-rank counts add up, the merged sites are the unsharded list."""
+    genome, pwms, cutoffs, expect = setup
+    world = 3
+    plans = [plan_ranges(genome.chrom_sizes, 6000, world, r) for r in range(world)]
+    assert sorted(c for p in plans for c in p) == sorted(plan_ranges(genome.chrom_sizes, 6000))
+    dg = DeviceGenome(genome, engine.default_context(0))
+    parts = [scan_genome(dg, pwms, cutoffs=cutoffs, chunk_bp=6000, batch_bp=40000, world=world, rank=r)
+             for r in range(world)]
+    dg.close()
+    assert np.array_equal(sum(p.counts for p in parts), expect[0])
+    _, cidx, start, score, strand = merged(parts)
+    assert np.array_equal(cidx, expect[1].astype(np.int32))
+    assert np.array_equal(start, expect[2].astype(np.int64))
+    assert np.array_equal(score.view(np.uint64), expect[3].view(np.uint64))
+    assert np.array_equal(strand, expect[4])
+
+
+def test_scan_ranges_unaligned(setup):
+    """msb_scan_ranges with arbitrary (not tile-aligned) ranges == the whole-chromosome sites whose
+    start falls in a range; overlapping ranges are refused."""
+    genome, pwms, cutoffs, expect = setup
+    counts, seq_idx, start, score, strand = expect
+    ctx = engine.default_context(0)
+    dg = DeviceGenome(genome, ctx)
+    motifs = engine.MotifSet(ctx, pwms, cutoffs)
+    rng = np.random.default_rng(5)
+    i1, i2 = dg.chrom_index["chr1"], dg.chrom_index["chr2"]
+    ranges = [(i1, 0, 1), (i1, 37, 1000), (i1, 1000, 1531), (i1, 50001, 123457 + 50), (i2, 511, 513), (i2, 69990, 70001),
+              (dg.chrom_index["chrM"], 3, 1571), (dg.chrom_index["chr10"], 0, 33), (i2, 600, 600)]
+    res = engine.scan_ranges(ctx, motifs, dg.seqs, 3, ranges)
+    motif_of = np.repeat(np.arange(len(pwms)), counts)
+    keep = np.zeros(len(start), dtype=bool)
+    for c, a, b in ranges:
+        keep |= (seq_idx == c) & (start >= a) & (start < b)
+    assert np.array_equal(res.counts, np.bincount(motif_of[keep], minlength=len(pwms)))
+    assert np.array_equal(res.seq_idx, seq_idx[keep].astype(np.int32))
+    assert np.array_equal(res.start, start[keep].astype(np.int32))
+    assert np.array_equal(res.strand, strand[keep])
+    assert np.array_equal(res.score.view(np.uint64), score[keep].view(np.uint64))
+    assert keep.sum() > 500 and (~keep).sum() > 500
+    res.close()
+    with pytest.raises(ValueError):
+        engine.scan_ranges(ctx, motifs, dg.seqs, 3, [(i1, 0, 100), (i1, 99, 200)])
+    with pytest.raises(ValueError):
+        engine.scan_ranges(ctx, motifs, dg.seqs, 3, [(99, 0, 100)])
+    empty = engine.scan_ranges(ctx, motifs, dg.seqs, 3, [])
+    assert empty.n_sites == 0
+    empty.close(), motifs.close(), dg.close()
+
+
+def test_extract_equals_ascii_windows(setup):
+    """Windows cut out of the resident genome (any alignment, clipped ends, empty intervals) are the
+    same packed sequences -- codes and scan results -- as the same windows sent as ASCII."""
+    genome, pwms, cutoffs, _ = setup
+    ctx = engine.default_context(0)
+    dg = DeviceGenome(genome, ctx)
+    rng = np.random.default_rng(9)
+    chroms, starts, ends = [], [], []
+    for _ in range(300):
+        c = genome.chroms[int(rng.integers(len(genome.chroms)))]
+        n = genome.chrom_sizes[c]
+        a = int(rng.integers(0, n))
+        b = a + int(rng.integers(0, 700))          # may run past the chromosome end: clipped
+        chroms.append(c), starts.append(a), ends.append(b)
+    chroms += ["chr1", "chr1", "chr10", "chr2"]
+    starts += [0, 123457, 0, 70000]
+    ends += [32, 123500, 33, 70001]
+    want_seqs = [genome.fetch_sequence(c, a, b) for c, a, b in zip(chroms, starts, ends)]
+    a_set = engine.SequenceSet(ctx, want_seqs)
+    x_set = dg.extract(chroms, starts, ends)
+    assert x_set.n == a_set.n and x_set.total_bp == a_set.total_bp
+    assert np.array_equal(x_set.seq_off, a_set.seq_off)
+    assert np.array_equal(x_set.codes(), a_set.codes())
+    motifs = engine.MotifSet(ctx, pwms, cutoffs)
+    ra, rx = engine.scan(ctx, motifs, a_set, 3), engine.scan(ctx, motifs, x_set, 3)
+    assert ra.n_sites > 50
+    assert np.array_equal(ra.counts, rx.counts) and np.array_equal(ra.seq_idx, rx.seq_idx)
+    assert np.array_equal(ra.start, rx.start) and np.array_equal(ra.strand, rx.strand)
+    assert np.array_equal(ra.score.view(np.uint64), rx.score.view(np.uint64))
+    with pytest.raises(KeyError):
+        dg.extract(["chr9"], [0], [10])
+    with pytest.raises(ValueError):
+        dg.seqs.extract([0], [-1], [10])
+    ra.close(), rx.close(), motifs.close(), a_set.close(), x_set.close(), dg.close()
 
 
 def test_counts_only_mode(setup):
