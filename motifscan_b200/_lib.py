@@ -9,7 +9,8 @@ import os
 import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libmsb200.so")
+# MSB200_LIB: an experiment build of the same library (motifscan_b200.build(out=..., defines=...))
+LIB_PATH = os.environ.get("MSB200_LIB") or os.path.join(_HERE, "libmsb200.so")
 
 MSB_OK, MSB_EINVAL, MSB_ENOMEM, MSB_ECUDA, MSB_ESHORT = 0, -1, -2, -3, -4
 MSB_SCAN_DEDUP = 1

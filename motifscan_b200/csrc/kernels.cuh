@@ -357,6 +357,7 @@ exact_candidates_kernel(ExactParams E, const uint64_t *__restrict__ cand, int64_
     int64_t i = (int64_t) blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n_cand) return;
     const uint64_t k = cand[i];
+    if (k == ~0ull) return;   // padding of a partly filled candidate block (prefilter_tc.cuh, kTcNoKey)
     const int64_t p = key_pos(k);
     uint32_t sorted = key_motif(k);
     int rev = (int) key_rev(k);

@@ -1189,7 +1189,7 @@ static int scan_device(msb_ctx *ctx, msb_motifs *M, const msb_seqs *S, int stran
         dirty_cap = std::max(dirty_cap, n_dirty + n_dirty / 16 + 1024);
         MSB_CUDA(cudaEventRecord(ctx->ev[0], st));
     }
-    ctx->c[MSB_C_CANDIDATES] = n_cand;
+    ctx->c[MSB_C_CANDIDATES] = n_cand - (int64_t) ctx->h_counters[3];   // slots minus the padding of partly filled blocks
     ctx->c[MSB_C_DIRTY] = n_dirty;
 
     // ---- stage 2: exact fp64 re-score ----------------------------------------------------------

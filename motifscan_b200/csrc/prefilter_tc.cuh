@@ -27,6 +27,14 @@
 #pragma once
 #include "common.cuh"
 
+// Compile-time experiment switch (bench_micro/tc_ablate.sh builds one library per value; results in
+// profiles/): 0 = product, 1 = no candidate emission, 2 = no accumulator scan either, 3 = no TMEM
+// read-back either (tensor pipe alone); 4/5/6 = emission cut after the register dump / after the
+// decode / before the global flush.  Anything but 0 gives wrong results by design.
+#ifndef MSB_TC_EXP
+#define MSB_TC_EXP 0
+#endif
+
 namespace msb {
 
 constexpr int kTcTileBases = 512;                       // window starts per position tile
@@ -40,12 +48,14 @@ constexpr int kTcUnitBytes = 8192;                      // one K=32 step of a 25
 constexpr int kTcMaxUnits = 22;                         // 8 KB K-steps of B per batch (180 KB of shared memory)
 constexpr int kTcMaxTiles = kTcMaxUnits;                // tiles per batch
 constexpr int kTcStageOff = kTcBOff + kTcMaxUnits * kTcUnitBytes;   // candidate staging, per epilogue warp
-constexpr int kTcStageCap = 128;                        // staged candidate keys per warp (8 B each)
+constexpr int kTcStageCap = 128;                        // staged candidate keys per warp (8 B each), a power of two
+constexpr int kTcScratchBytes = 128;                    // per epilogue warp: one chunk's 32 registers
 constexpr int kTcCols = 256;                            // motif-strand columns per tile
 constexpr int kTcEpiWarps = 16;                         // two sets of 8: set g reads the units that land in TMEM buffer g
 constexpr int kTcThreads = (4 + kTcEpiWarps) * 32;
 constexpr int kTcWarpCols = 128;                        // accumulator columns one epilogue warp reads per unit
-constexpr int kTcSmemBytes = kTcStageOff + kTcEpiWarps * kTcStageCap * 8;   // dynamic shared memory of the kernel
+constexpr int kTcScratchOff = kTcStageOff + kTcEpiWarps * kTcStageCap * 8;
+constexpr int kTcSmemBytes = kTcScratchOff + kTcEpiWarps * kTcScratchBytes;   // dynamic shared memory of the kernel
 constexpr int kTcStaticSmemReserve = 1024;             // static __shared__ (barriers) + alignment slack
 
 struct TcBatch {
@@ -132,16 +142,32 @@ __device__ __forceinline__ uint32_t and8(const uint32_t (&r)[32], int g) {
     return (r[8 * g] & r[8 * g + 1] & r[8 * g + 2]) & (r[8 * g + 3] & r[8 * g + 4] & r[8 * g + 5]) & (r[8 * g + 6] & r[8 * g + 7]);
 }
 
-// Candidate staging.  The epilogue must never wait on global memory or on an atomic: a warp that
-// stalls keeps its TMEM buffer from being recycled and all eight warps meet at every unit.  So
-// every lane owns kTcLaneSlots key slots in shared memory and a register counter; a push is one
-// shared store.  When some lane is nearly full the warp flushes all lanes with one global
-// atomic.  Column -> (motif, strand) decoding and the sequence-end check happen in the exact stage.
-constexpr int kTcLaneSlots = kTcStageCap / 32;   // 4
+// Candidate staging.  A unit's accumulators are in registers when its TMEM buffer is released, but
+// the warp cannot start on its next unit before it is done with this one, and a set of eight warps
+// recycles a buffer only when all eight have read it -- with ~0.3 candidates per warp and unit,
+// nearly every unit has SOME warp on the rare path, so the rare path's latency, not its share of
+// the work, sets the pace.  It is therefore warp-uniform and call-free: the lanes vote; for each
+// lane with a clear sign bit in the 64-column chunk (usually one) that lane spills the chunk's 32
+// registers to a 128 B scratch line, every lane picks up one register = two accumulators, the
+// sign tests are two ballots, and the keys go to a per-warp staging queue in shared memory
+// (a ring of kTcStageCap keys, warp-uniform head and count in registers).  Whenever the ring holds
+// kTcFlushKeys keys they go to a block of the candidate buffer that the warp RESERVED EARLIER: the
+// atomic that reserves the next block is issued right after a flush and its result is not touched
+// until the next one, so no epilogue warp ever waits for a global round trip (a ~1000-cycle stall
+// of one warp holds up its TMEM buffer, and with it the tensor pipe).  Blocks are always written in
+// full; the tail of a warp's last block is padded with kTcNoKey, which the exact stage skips.
+// Column -> (motif, strand) decoding and the sequence-end check happen in the exact stage.
+constexpr int kTcFlushKeys = 64;
+constexpr uint64_t kTcNoKey = ~0ull;
 
 struct Stage {
-    uint32_t slots;       // shared-memory address of this lane's kTcLaneSlots keys
-    uint32_t n;           // keys staged by this lane
+    uint32_t keys;        // shared-memory address of this warp's ring of kTcStageCap keys
+    uint32_t scratch;     // shared-memory address of this warp's 32-word scratch line
+    uint32_t addend;      // shared-memory address of this lane's 64-bit word holding kTcFlushKeys (see reserve_block)
+    int leader;           // 0, read from shared memory: the lane that reserves blocks
+    uint32_t head;        // ring index of the oldest staged key (warp-uniform, not wrapped)
+    uint32_t n;           // keys staged (warp-uniform)
+    unsigned long long resv;   // lane 0: first slot of the reserved block of kTcFlushKeys candidate slots
 };
 
 __device__ __forceinline__ unsigned long long atom_add_global(unsigned long long *p, unsigned long long v) {
@@ -153,83 +179,92 @@ __device__ __forceinline__ void st_global(uint64_t *p, uint64_t v) {
     asm volatile("st.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
 }
 
-// lane full within one unit (dense hits): straight to global memory
-__device__ __noinline__ void push_direct(const TcParams &P, uint64_t key) {
-    const unsigned long long at = atom_add_global(P.counters + 0, 1ull);
-    if ((int64_t) at < P.cand_cap) st_global(P.cand + at, key);
+// Lane 0 only.  ptxas rewrites an atomic add of a warp-uniform value into its warp-aggregated form
+// (vote, leader atomic, SHFL of the result), and that SHFL would wait for the round trip on the
+// spot.  So the addend comes from a per-lane word of shared memory (always kTcFlushKeys) and the
+// reserving lane from another (always 0): values the compiler cannot prove uniform keep the plain
+// ATOMG, whose result register is first read at the next flush.
+__device__ __forceinline__ unsigned long long reserve_block(const TcParams &P, const Stage &st) {
+    unsigned long long add;
+    asm volatile("ld.shared.b64 %0, [%1];" : "=l"(add) : "r"(st.addend) : "memory");
+    return atom_add_global(P.counters + 0, add);
 }
 
-__device__ __forceinline__ uint32_t stage_push(const TcParams &P, uint32_t slots, uint32_t n, uint32_t colid, int64_t p) {
-    const uint64_t key = make_key(colid, p, 0);
-    if (n < kTcLaneSlots) {
-        asm volatile("st.shared.b64 [%0], %1;" ::"r"(slots + 8 * n), "l"(key) : "memory");
-        return n + 1;
-    }
-    push_direct(P, key);
-    return n;
-}
-
-// The kernel's instruction footprint matters (the epilogue's per-unit path must stay in the
-// instruction cache while twelve warps run four different roles), so the rare path is one
-// out-of-line function over 8 registers = 16 packed f16 accumulators of columns col0 .. col0+15:
-// push those with a clear sign bit, return the lane's new slot count.
-// prmt.b32 with selector 0xFDB9: bytes 1 and 3 of x, bytes 1 and 3 of y, each replaced by its sign
-// bit replicated over the byte (selector nibble msb = sign mode).
-__device__ __forceinline__ uint32_t half_signs(uint32_t x, uint32_t y) {
-    uint32_t d;
-    asm("prmt.b32 %0, %1, %2, 0xFDB9;" : "=r"(d) : "r"(x), "r"(y));
-    return d;
-}
-
-__device__ __noinline__ uint32_t emit8(const TcParams &P, uint32_t slots, uint32_t n, uint32_t col0, int64_t p,
-                                       uint32_t a0, uint32_t a1, uint32_t a2, uint32_t a3,
-                                       uint32_t a4, uint32_t a5, uint32_t a6, uint32_t a7) {
-    // half_signs(x, y) = the sign bits of the four f16 values of (x, y), each replicated over one byte
-    // (columns +0, +1, +2, +3).  Keeping bit b + k of byte b for register pair k gives one word with
-    // a distinct bit per clear sign among the 16 accumulators.
-    uint32_t m = (~half_signs(a0, a1) & 0x08040201u) | (~half_signs(a2, a3) & 0x10080402u) |
-                 (~half_signs(a4, a5) & 0x20100804u) | (~half_signs(a6, a7) & 0x40201008u);
-    while (m) {
-        const uint32_t pos = __ffs(m) - 1;
-        m &= m - 1;
-        const uint32_t b = pos >> 3, k = (pos & 7u) - b;
-        n = stage_push(P, slots, n, col0 + 4 * k + b, p);
-    }
-    return n;
-}
-
-// All 32 lanes.
-__device__ __noinline__ void stage_flush(const TcParams &P, const Stage st, int lane) {
-    uint32_t incl = st.n;
+// All 32 lanes: move the oldest min(n, 64) staged keys into the reserved block (padding it with
+// kTcNoKey when fewer are staged), then reserve the next block unless this is the final flush.
+__device__ __forceinline__ void stage_flush(const TcParams &P, Stage &st, int lane, bool last) {
+    const unsigned long long base = __shfl_sync(0xffffffffu, st.resv, 0);
+    const uint32_t cnt = st.n < (uint32_t) kTcFlushKeys ? st.n : (uint32_t) kTcFlushKeys;
 #pragma unroll
-    for (int d = 1; d < 32; d <<= 1) {
-        const uint32_t v = __shfl_up_sync(0xffffffffu, incl, d);
-        if (lane >= d) incl += v;
-    }
-    const uint32_t total = __shfl_sync(0xffffffffu, incl, 31);
-    if (total == 0) return;
-    unsigned long long base = 0;
-    if (lane == 0) base = atom_add_global(P.counters + 0, (unsigned long long) total);
-    base = __shfl_sync(0xffffffffu, base, 0) + (incl - st.n);
-#pragma unroll 1
-    for (uint32_t i = 0; i < st.n; i++) {
-        uint64_t key;
-        asm volatile("ld.shared.b64 %0, [%1];" : "=l"(key) : "r"(st.slots + 8 * i) : "memory");
+    for (int h = 0; h < kTcFlushKeys / 32; h++) {
+        const uint32_t i = 32 * h + lane;
+        uint64_t key = kTcNoKey;
+        if (i < cnt) asm volatile("ld.shared.b64 %0, [%1];" : "=l"(key) : "r"(st.keys + 8 * ((st.head + i) & (kTcStageCap - 1))) : "memory");
         if ((int64_t) (base + i) < P.cand_cap) st_global(P.cand + base + i, key);
+    }
+    st.head += cnt;
+    st.n -= cnt;
+    __syncwarp();
+    if (last) {
+        if (lane == 0 && cnt < (uint32_t) kTcFlushKeys) atom_add_global(P.counters + 3, (unsigned long long) (kTcFlushKeys - cnt));   // padding written
+    } else if (lane == st.leader) {
+        st.resv = reserve_block(P, st);
     }
 }
 
 // One packed 64-column load of this lane's window: r[j] holds columns col0 + 2j (low half) and
-// col0 + 2j + 1 (high half).
+// col0 + 2j + 1 (high half).  p0 = packed position of lane 0's window; lane l's is p0 + 4 l.
 __device__ __forceinline__ void scan_chunk(const TcParams &P, Stage &st, const uint32_t (&r)[32], bool live,
-                                           uint32_t col0, int64_t p) {
+                                           uint32_t col0, int64_t p0, int lane) {
     constexpr uint32_t M = 0x80008000u;
-    const uint32_t g0 = and8(r, 0), g1 = and8(r, 1), g2 = and8(r, 2), g3 = and8(r, 3);
-    if (live && ((g0 & g1 & g2 & g3) & M) != M) {
-        if ((g0 & M) != M) st.n = emit8(P, st.slots, st.n, col0, p, r[0], r[1], r[2], r[3], r[4], r[5], r[6], r[7]);
-        if ((g1 & M) != M) st.n = emit8(P, st.slots, st.n, col0 + 16, p, r[8], r[9], r[10], r[11], r[12], r[13], r[14], r[15]);
-        if ((g2 & M) != M) st.n = emit8(P, st.slots, st.n, col0 + 32, p, r[16], r[17], r[18], r[19], r[20], r[21], r[22], r[23]);
-        if ((g3 & M) != M) st.n = emit8(P, st.slots, st.n, col0 + 48, p, r[24], r[25], r[26], r[27], r[28], r[29], r[30], r[31]);
+    const uint32_t g = and8(r, 0) & and8(r, 1) & and8(r, 2) & and8(r, 3);
+    uint32_t bal = __ballot_sync(0xffffffffu, live && (g & M) != M);
+#if MSB_TC_EXP >= 1 && MSB_TC_EXP <= 3
+    bal = 0;
+#endif
+    while (bal) {                                       // warp-uniform
+        const int src = __ffs(bal) - 1;
+        bal &= bal - 1;
+        if (lane == src) {
+#pragma unroll
+            for (int k = 0; k < 8; k++)
+                asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(st.scratch + 16 * k), "r"(r[4 * k]),
+                             "r"(r[4 * k + 1]), "r"(r[4 * k + 2]), "r"(r[4 * k + 3]) : "memory");
+        }
+        __syncwarp();
+#if MSB_TC_EXP == 4
+        continue;                                       // ablation: vote + dump only
+#endif
+        uint32_t w;
+        asm volatile("ld.shared.b32 %0, [%1];" : "=r"(w) : "r"(st.scratch + 4 * lane) : "memory");
+        __syncwarp();
+        const uint32_t b_lo = __ballot_sync(0xffffffffu, !(w & 0x00008000u));
+        const uint32_t b_hi = __ballot_sync(0xffffffffu, !(w & 0x80000000u));
+        const uint32_t below = (1u << lane) - 1u;
+        const int64_t p = p0 + 4 * src;
+        const uint32_t n_lo = __popc(b_lo);
+        const uint32_t tail = st.head + st.n;
+#if MSB_TC_EXP == 5
+        st.head += n_lo + __popc(b_hi);                 // ablation: decode, no key stores, no flush
+        continue;
+#endif
+        if (!(w & 0x00008000u)) {
+            const uint64_t key = make_key(col0 + 2 * lane, p, 0);
+            asm volatile("st.shared.b64 [%0], %1;" ::"r"(st.keys + 8 * ((tail + __popc(b_lo & below)) & (kTcStageCap - 1))), "l"(key) : "memory");
+        }
+        if (!(w & 0x80000000u)) {
+            const uint64_t key = make_key(col0 + 2 * lane + 1, p, 0);
+            asm volatile("st.shared.b64 [%0], %1;" ::"r"(st.keys + 8 * ((tail + n_lo + __popc(b_hi & below)) & (kTcStageCap - 1))), "l"(key) : "memory");
+        }
+        st.n += n_lo + __popc(b_hi);
+#if MSB_TC_EXP == 6
+        if (st.n >= (uint32_t) kTcFlushKeys) { st.head += kTcFlushKeys; st.n -= kTcFlushKeys; }   // ablation: keys staged, never written
+        continue;
+#endif
+        if (st.n >= (uint32_t) kTcFlushKeys) {   // <= 63 staged before, <= 64 added: the ring of 128 never overflows
+            __syncwarp();
+            stage_flush(P, st, lane, false);
+        }
     }
 }
 
@@ -288,6 +323,8 @@ prefilter_tc_kernel(const __grid_constant__ TcParams P) {
     uint8_t *s_b = smem + kTcBOff;
     __shared__ uint64_t bar_stream_full[kTcSlots], bar_stream_empty[kTcSlots], bar_tmem_full[2], bar_tmem_empty[2];
     __shared__ uint32_t s_tmem_base;
+    __shared__ int s_leader;
+    __shared__ unsigned long long s_flush_keys[32];   // all kTcFlushKeys; indexed by lane so that ptxas sees a divergent value
     __shared__ uint32_t s_skip[kTcSlots];
     __shared__ uint2 s_tile[kTcMaxTiles];   // per tile: B descriptor low word, K steps
 
@@ -302,6 +339,8 @@ prefilter_tc_kernel(const __grid_constant__ TcParams P) {
         for (int i = 0; i < 2; i++) { mbar_init(&bar_tmem_full[i], 1); mbar_init(&bar_tmem_empty[i], kTcEpiWarps / 2); }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
+    if (threadIdx.x < 32) s_flush_keys[threadIdx.x] = kTcFlushKeys;
+    if (threadIdx.x == 0) s_leader = 0;
     if (threadIdx.x < P.batch.n_tiles) {
         const uint32_t bt = smem_u32(s_b) + (uint32_t) P.batch.unit_off[threadIdx.x] * kTcUnitBytes;
         s_tile[threadIdx.x] = make_uint2(((bt & 0x3FFFFu) >> 4) | ((4096u >> 4) << 16), P.batch.ks[threadIdx.x]);
@@ -455,8 +494,17 @@ prefilter_tc_kernel(const __grid_constant__ TcParams P) {
         const int q = warp & 3, h = ((warp - 4) >> 2) & 1, set = (warp - 4) >> 3;
         const int row = q * 32 + lane;
         Stage stg;
-        stg.slots = smem_u32(smem + kTcStageOff) + ((warp - 4) * kTcStageCap + lane * kTcLaneSlots) * 8;
+        stg.keys = smem_u32(smem + kTcStageOff) + (warp - 4) * kTcStageCap * 8;
+        stg.scratch = smem_u32(smem + kTcScratchOff) + (warp - 4) * kTcScratchBytes;
+        stg.head = 0;
         stg.n = 0;
+        stg.resv = 0;
+        {   // a per-lane offset that is always 0 but comes out of memory: the address stays opaque even where lane == leader is known
+            const uint32_t z = (uint32_t) (*reinterpret_cast<volatile unsigned long long *>(&s_flush_keys[lane]) >> 32);
+            stg.addend = smem_u32(&s_flush_keys[(lane + z) & 31]);
+        }
+        stg.leader = s_leader;                                   // 0, but not to the compiler (see reserve_block)
+        if (lane == stg.leader) stg.resv = reserve_block(P, stg);   // first block; used at the first flush
         const uint32_t taddr0 = tmem + set * kTcCols + h * kTcWarpCols + ((uint32_t) (q * 32) << 16);
         const uint32_t colid0 = P.batch.first_tile * kTcCols + h * kTcWarpCols;
         uint32_t u = 0, it = 0;
@@ -480,7 +528,7 @@ prefilter_tc_kernel(const __grid_constant__ TcParams P) {
             for (uint32_t v = (uint32_t) set; v < 4 * NT; v += 2) {
                 const uint32_t uu = u + v;
                 const bool live = !((ign4 >> sh) & 1u);
-                const int64_t p = tile_start + 4 * row + sh;
+                const int64_t p0 = tile_start + 4 * (q * 32) + sh;   // lane 0's window; lane l's is p0 + 4 l
                 const uint32_t colid = colid0 + nt * kTcCols;
                 const long long c0 = now();
                 mbar_wait_a(B.tmem_full + 8 * set, (uu >> 1) & 1);
@@ -488,22 +536,27 @@ prefilter_tc_kernel(const __grid_constant__ TcParams P) {
                 t_wf += c1 - c0;
                 fence_after();
                 uint32_t r0[32], r1[32];
+#if MSB_TC_EXP != 3
                 MSB_TC_LD32P(r0, taddr0);        // columns [0, 64) of this warp's share, two per register
                 MSB_TC_LD32P(r1, taddr0 + 64);
                 asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#else
+                r0[0] = r0[31] = 0;
+#endif
                 fence_before();
                 __syncwarp();
                 if (lane == 0) mbar_arrive_a(B.tmem_empty + 8 * set);   // accumulators are in registers
                 const long long c2 = now() + ((r0[0] ^ r0[31]) == 0x12345679u);   // depends on the loaded data
                 t_ld += c2 - c1;
                 const uint32_t n_before = stg.n;
-                scan_chunk(P, stg, r0, live, colid, p);
-                scan_chunk(P, stg, r1, live, colid + 64, p);
-                if (__any_sync(0xffffffffu, stg.n >= kTcLaneSlots - 1)) { stage_flush(P, stg, lane); stg.n = 0; }
+#if MSB_TC_EXP != 2 && MSB_TC_EXP != 3
+                scan_chunk(P, stg, r0, live, colid, p0, lane);
+                scan_chunk(P, stg, r1, live, colid + 64, p0, lane);
+#endif
                 if (kProf) {
                     const long long c3 = now();
                     t_pr += c3 - c2;
-                    if (__any_sync(0xffffffffu, stg.n != n_before)) { t_slow += c3 - c2; n_slow++; }
+                    if (stg.n != n_before) { t_slow += c3 - c2; n_slow++; }
                     if (P.prof && blockIdx.x == 0 && lane == 0 && (warp == 4 || warp == 12) && uu >= 2000 && uu < 2012) {
                         long long *o = P.prof + gridDim.x * 16 + (uu - 2000) * 8;
                         o[2] = c0; o[3] = c1; o[4] = c2; o[5] = c3; o[6] = warp;
@@ -514,7 +567,8 @@ prefilter_tc_kernel(const __grid_constant__ TcParams P) {
             }
             u += 4 * NT;
         }
-        stage_flush(P, stg, lane);
+        __syncwarp();
+        stage_flush(P, stg, lane, true);   // the rest (< 64 keys) + padding: every reserved block is written in full
         if (kProf && P.prof && warp == 4 && lane == 0) {
             long long *o = P.prof + blockIdx.x * 16;
             o[8] = t_wf; o[9] = t_ld; o[10] = t_pr; o[11] = t_wsf; o[12] = u; o[13] = t_slow; o[14] = n_slow;
