@@ -4,12 +4,12 @@
 set -e
 cd "$(dirname "$0")/.."
 if [ "$1" = "run" ]; then
-  for e in ${EXPS:-0 1 2 3 4 5 6}; do
+  for e in ${EXPS:-0 1 2 3}; do
     MSB200_LIB=$PWD/bench_micro/libmsb200_exp$e.so python bench.py --steps 5 --warmup 3 --no-cpu 2>/dev/null | python -c "
 import json,sys; d=json.loads(sys.stdin.read()); print('MSB_TC_EXP=$e', 'prefilter_ms', round(d['phase_ms']['prefilter'],3), 'step_ms', round(d['ms_per_step'],3))"
   done
 else
-  for e in ${EXPS:-0 1 2 3 4 5 6}; do
+  for e in ${EXPS:-0 1 2 3}; do
     python -c "from motifscan_b200 import build; build.build(out='bench_micro/libmsb200_exp$e.so', defines=('MSB_TC_EXP=$e',))"
   done
 fi

@@ -357,7 +357,6 @@ exact_candidates_kernel(ExactParams E, const uint64_t *__restrict__ cand, int64_
     int64_t i = (int64_t) blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n_cand) return;
     const uint64_t k = cand[i];
-    if (k == ~0ull) return;   // padding of a partly filled candidate block (prefilter_tc.cuh, kTcNoKey)
     const int64_t p = key_pos(k);
     uint32_t sorted = key_motif(k);
     int rev = (int) key_rev(k);
@@ -377,6 +376,87 @@ exact_candidates_kernel(ExactParams E, const uint64_t *__restrict__ cand, int64_
     }
     const double *pw = E.mot.pwm + 4 * (int64_t) __ldg(E.mot.col_off + m);
     test_and_emit(E, m, p, rev, exact_raw_w(load_window32(E.seq, p), pw, L, rev));   // prefilter motifs have L <= 32
+}
+
+// The tensor-core prefilter leaves its candidate records in one buffer per epilogue lane
+// (prefilter_tc.cuh, "Candidate emission").  lane_prefix_kernel (one block): exclusive prefix sum of
+// the per-lane record counts, clamped to the buffer capacity -> offsets[n_lanes + 1];
+// counters[0] = total records, counters[3] = largest unclamped count (> capacity: the host retries).
+__global__ void __launch_bounds__(1024)
+lane_prefix_kernel(const uint32_t *__restrict__ lane_count, int32_t n_lanes, int64_t cap,
+                   int64_t *__restrict__ offsets, unsigned long long *__restrict__ counters) {
+    __shared__ long long s_sum[1024];
+    __shared__ unsigned int s_max[1024];
+    const int t = threadIdx.x;
+    const int per = (n_lanes + 1023) / 1024;
+    const int a = min(t * per, n_lanes), e = min(a + per, n_lanes);
+    long long sum = 0;
+    unsigned int mx = 0;
+    for (int i = a; i < e; i++) {
+        const unsigned int c = lane_count[i];
+        mx = max(mx, c);
+        sum += min((long long) c, (long long) cap);
+    }
+    s_sum[t] = sum;
+    s_max[t] = mx;
+    __syncthreads();
+    for (int d = 1; d < 1024; d <<= 1) {   // inclusive scan of the per-thread sums, running maximum
+        const long long v = t >= d ? s_sum[t - d] : 0;
+        const unsigned int m = t >= d ? s_max[t - d] : 0u;
+        __syncthreads();
+        s_sum[t] += v;
+        s_max[t] = max(s_max[t], m);
+        __syncthreads();
+    }
+    long long at = s_sum[t] - sum;
+    for (int i = a; i < e; i++) {
+        offsets[i] = at;
+        at += min((long long) lane_count[i], (long long) cap);
+    }
+    if (t == 1023) {
+        offsets[n_lanes] = s_sum[1023];
+        counters[0] = (unsigned long long) s_sum[1023];
+        counters[3] = s_max[1023];
+    }
+}
+
+// One thread per record = one window; its bases are loaded once and every flagged column of the
+// chunk's 64 is decoded (col_info: tile column -> sorted motif, strand) and re-scored.
+__global__ void __launch_bounds__(256)
+exact_records_kernel(ExactParams E, const uint4 *__restrict__ rec, int64_t rec_cap,
+                     const int64_t *__restrict__ offsets, int32_t n_lanes, int64_t n_rec,
+                     const int32_t *__restrict__ order, const uint32_t *__restrict__ col_info) {
+    const int64_t i = (int64_t) blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n_rec) return;
+    int lo = 0, hi = n_lanes;   // the lane buffer that holds record i: largest b with offsets[b] <= i
+    while (hi - lo > 1) {
+        const int mid = (lo + hi) >> 1;
+        if (__ldg(offsets + mid) <= i) lo = mid; else hi = mid;
+    }
+    const uint4 r = __ldg(rec + (int64_t) lo * rec_cap + (i - __ldg(offsets + lo)));
+    const int64_t p = (int64_t) (((uint64_t) (r.y & 0x1ffu) << 32) | r.x);
+    const uint32_t col0 = r.y >> 9;
+    const int64_t s = __ldg(E.seq.blk_seq + (p >> 5));
+    const int64_t j = p - __ldg(E.seq.poff + s);
+    const int64_t slen = __ldg(E.seq.len + s);
+    if (E.seq.limit && j >= (int64_t) __ldg(E.seq.limit + s)) return;   // the next chunk owns this start
+    const Window32 w = load_window32(E.seq, p);
+#pragma unroll 1
+    for (int half = 0; half < 2; half++) {
+        uint32_t bits = half ? r.w : r.z;
+        while (bits) {
+            const int b = __ffs(bits) - 1;   // bit 8 q + k <=> column 32 half + 4 k + q
+            bits &= bits - 1;
+            const uint32_t info = __ldg(col_info + col0 + 32 * half + 4 * (b & 7) + (b >> 3));
+            if (info == 0xffffffffu) continue;   // padding column of a tile
+            const uint32_t m = (uint32_t) __ldg(order + (info >> 1));
+            const int rev = (int) (info & 1u);
+            const int L = __ldg(E.mot.len + m);
+            if (j + L > slen) continue;   // cscore.c:340
+            const double *pw = E.mot.pwm + 4 * (int64_t) __ldg(E.mot.col_off + m);
+            test_and_emit(E, m, p, rev, exact_raw_w(w, pw, L, rev));   // prefilter motifs have L <= 32
+        }
+    }
 }
 
 // One thread per (listed position, motif); consecutive threads take consecutive motifs of the

@@ -73,6 +73,7 @@ struct msb_ctx {
     DevBuf ascii, seq_off, cand, dirty, hit_key, hit_score, key_alt, score_alt, sort_tmp, counters;
     DevBuf out_seq, out_start, out_strand, out_counts, scores, scores_sorted, seg_off, ranks, sel;
     DevBuf keep, keep_pos, out2_seq, out2_start, out2_strand;
+    DevBuf lane_count, lane_off;   // tensor-core prefilter: records per epilogue lane, their prefix sums
     // final site arrays of the last scan (point into the buffers above)
     uint64_t *fin_key = nullptr;
     double *fin_score = nullptr;
@@ -314,7 +315,7 @@ int msb_ctx_destroy(msb_ctx *ctx) {
                       &ctx->key_alt, &ctx->score_alt, &ctx->sort_tmp, &ctx->counters, &ctx->out_seq,
                       &ctx->out_start, &ctx->out_strand, &ctx->out_counts, &ctx->scores,
                       &ctx->scores_sorted, &ctx->seg_off, &ctx->ranks, &ctx->sel, &ctx->keep, &ctx->keep_pos,
-                      &ctx->out2_seq, &ctx->out2_start, &ctx->out2_strand})
+                      &ctx->out2_seq, &ctx->out2_start, &ctx->out2_strand, &ctx->lane_count, &ctx->lane_off})
         b->release();
     for (auto &b : ctx->pinned_free) cudaFreeHost(b.p);
     for (auto &b : ctx->dev_free) b.release();
@@ -1026,6 +1027,7 @@ static int launch_positions(msb_ctx *ctx, const ExactParams &E, const int64_t *p
 
 static int g_prefilter_w = 4;   // windows per thread of the table prefilter (4 or 8)
 static int g_tc_prof = std::getenv("MSB_TC_PROF") ? 1 : 0;   // 1: print per-role cycle counters of the tensor-core prefilter to stderr
+static int g_tc_first_lane_cap = 0;  // tests: records per lane buffer on the first attempt (0 = sized from the input)
 static int g_prefilter_tc = 1;  // 1: tensor-core prefilter (prefilter_tc.cuh), 0: shared-memory table prefilter
 
 // Packed-position ranges [lo, hi) of a range scan; nullptr = the whole sequence set.
@@ -1088,11 +1090,17 @@ static int scan_device(msb_ctx *ctx, msb_motifs *M, const msb_seqs *S, int stran
 
     // ---- stage 1: prefilter ------------------------------------------------------------------
     const double cells = (double) span * (double) std::max<int32_t>(n_fast, 1);
-    int64_t cand_cap = (int64_t) std::min<double>(std::max<double>(cells / 512.0, 1 << 20), (double) (1ll << 30));
+    int64_t cand_cap = (int64_t) std::min<double>(std::max<double>(cells / 512.0, 1 << 22), (double) (1ll << 30));   // in 8-byte units
     int64_t dirty_cap = std::max<int64_t>(1 << 16, span / 64);
     if (ctx->cand.cap / 8 > (size_t) cand_cap) cand_cap = (int64_t) (ctx->cand.cap / 8);
     if (ctx->dirty.cap / 8 > (size_t) dirty_cap) dirty_cap = (int64_t) (ctx->dirty.cap / 8);
-    int64_t n_cand = 0, n_dirty = 0;
+    // tensor-core prefilter: one record buffer per epilogue lane of the largest grid launched
+    int64_t tc_grid = 1;
+    for (auto &r : *ranges)
+        tc_grid = std::max<int64_t>(tc_grid, std::min<int64_t>(ctx->sm_count, (r.second + kTcTileBases - 1) / kTcTileBases - r.first / kTcTileBases));
+    const int32_t n_lanes = (int32_t) (tc_grid * kTcLanesPerCta);
+    int64_t lane_cap = 0;
+    int64_t n_cand = 0, n_dirty = 0, n_rec = 0;
     MSB_CUDA(cudaEventRecord(ctx->ev[0], st));
     for (int attempt = 0;; attempt++) {
         MSB_TRY(ctx->cand.ensure((size_t) cand_cap * 8));
@@ -1104,8 +1112,14 @@ static int scan_device(msb_ctx *ctx, msb_motifs *M, const msb_seqs *S, int stran
             P.btab = TT->d_btab.as<uint8_t>();
             P.lmax_all = std::max(lmax_fast, 1);
             P.any_zero_hit = any_zero_hit;
-            P.cand = ctx->cand.as<uint64_t>();
-            P.cand_cap = cand_cap;
+            lane_cap = std::max<int64_t>(cand_cap / 2 / n_lanes, 1);   // 16-byte records per lane buffer
+            if (attempt == 0 && g_tc_first_lane_cap > 0) lane_cap = std::min<int64_t>(lane_cap, g_tc_first_lane_cap);
+            MSB_TRY(ctx->lane_count.ensure((size_t) n_lanes * 4));
+            MSB_TRY(ctx->lane_off.ensure((size_t) (n_lanes + 1) * 8));
+            MSB_CUDA(cudaMemsetAsync(ctx->lane_count.p, 0, (size_t) n_lanes * 4, st));
+            P.cand = ctx->cand.as<uint4>();
+            P.cand_cap = lane_cap;
+            P.lane_count = ctx->lane_count.as<uint32_t>();
             P.dirty = ctx->dirty.as<int64_t>();
             P.dirty_cap = dirty_cap;
             P.counters = ctx->counters.as<unsigned long long>();
@@ -1133,6 +1147,10 @@ static int scan_device(msb_ctx *ctx, msb_motifs *M, const msb_seqs *S, int stran
                     ctx->c[MSB_C_PREFILTER_LAUNCHES]++;
                 }
             }
+            lane_prefix_kernel<<<1, 1024, 0, st>>>(ctx->lane_count.as<uint32_t>(), n_lanes, lane_cap, ctx->lane_off.as<int64_t>(),
+                                                   ctx->counters.as<unsigned long long>());
+            MSB_CUDA(cudaGetLastError());
+            ctx->c[MSB_C_LAUNCHES]++;
             if (g_tc_prof) {
                 std::vector<long long> h((size_t) (ctx->sm_count + 16) * 16);
                 MSB_CUDA(cudaMemcpyAsync(h.data(), prof.p, h.size() * 8, cudaMemcpyDeviceToHost, st));
@@ -1180,20 +1198,30 @@ static int scan_device(msb_ctx *ctx, msb_motifs *M, const msb_seqs *S, int stran
         }
         MSB_CUDA(cudaEventRecord(ctx->ev[1], st));
         MSB_TRY(read_counters(ctx));
-        n_cand = (int64_t) ctx->h_counters[0];
+        n_cand = (int64_t) ctx->h_counters[0];   // keys (table prefilter) or records (tensor-core prefilter)
         n_dirty = (int64_t) ctx->h_counters[1];
-        if (n_cand <= cand_cap && n_dirty <= dirty_cap) break;
+        bool overflow = n_cand > cand_cap;
+        int64_t need = n_cand + n_cand / 16 + 1024;
+        if (use_tc) {
+            // a lane that ran out of room only counted: grow every lane buffer to the largest count seen
+            n_rec = n_cand;
+            const int64_t worst = (int64_t) ctx->h_counters[3];
+            overflow = worst > lane_cap;
+            need = (worst + worst / 8 + 16) * 2 * n_lanes;
+        }
+        if (!overflow && n_dirty <= dirty_cap) break;
         if (attempt >= 2) { set_error("msb_scan: candidate buffers kept overflowing"); return MSB_ENOMEM; }
         ctx->c[MSB_C_RETRIES]++;
-        cand_cap = std::max(cand_cap, n_cand + n_cand / 16 + 1024);
+        if (overflow) cand_cap = std::max(cand_cap, need);
         dirty_cap = std::max(dirty_cap, n_dirty + n_dirty / 16 + 1024);
         MSB_CUDA(cudaEventRecord(ctx->ev[0], st));
     }
-    ctx->c[MSB_C_CANDIDATES] = n_cand - (int64_t) ctx->h_counters[3];   // slots minus the padding of partly filled blocks
+    if (use_tc) n_cand = n_rec;   // records: (window, 64-column chunk) pairs with at least one flagged accumulator
+    ctx->c[MSB_C_CANDIDATES] = n_cand;
     ctx->c[MSB_C_DIRTY] = n_dirty;
 
     // ---- stage 2: exact fp64 re-score ----------------------------------------------------------
-    int64_t hit_cap = std::max<int64_t>(n_cand + 1024, 1 << 16);
+    int64_t hit_cap = std::max<int64_t>(n_cand + (use_tc ? n_cand / 4 : 0) + 1024, 1 << 16);   // a record can flag several columns
     if (n_dirty) hit_cap += std::min<int64_t>(n_dirty * 2 * std::max(n_fast, 1), 1 << 24);
     if (n_slow) hit_cap += 1 << 20;
     if (ctx->hit_key.cap / 8 > (size_t) hit_cap) hit_cap = (int64_t) (ctx->hit_key.cap / 8);
@@ -1210,9 +1238,15 @@ static int scan_device(msb_ctx *ctx, msb_motifs *M, const msb_seqs *S, int stran
         E.hit_score = ctx->hit_score.as<double>();
         E.hit_cap = hit_cap;
         E.counters = ctx->counters.as<unsigned long long>();
-        if (n_cand) {
+        if (use_tc && n_rec) {
+            exact_records_kernel<<<(unsigned) ((n_rec + 255) / 256), 256, 0, st>>>(
+                E, ctx->cand.as<uint4>(), lane_cap, ctx->lane_off.as<int64_t>(), n_lanes, n_rec, d_order,
+                TT->d_col_info.as<uint32_t>());
+            MSB_CUDA(cudaGetLastError());
+            ctx->c[MSB_C_LAUNCHES]++;
+        } else if (!use_tc && n_cand) {
             exact_candidates_kernel<<<(unsigned) ((n_cand + 255) / 256), 256, 0, st>>>(
-                E, ctx->cand.as<uint64_t>(), n_cand, d_order, use_tc ? TT->d_col_info.as<uint32_t>() : nullptr);
+                E, ctx->cand.as<uint64_t>(), n_cand, d_order, nullptr);
             MSB_CUDA(cudaGetLastError());
             ctx->c[MSB_C_LAUNCHES]++;
         }
@@ -1320,6 +1354,7 @@ int msb_set_option(const char *name, int value) {
     if (name && !std::strcmp(name, "prefilter_w") && (value == 4 || value == 8)) { g_prefilter_w = value; return MSB_OK; }
     if (name && !std::strcmp(name, "prefilter_tc") && (value == 0 || value == 1)) { g_prefilter_tc = value; return MSB_OK; }
     if (name && !std::strcmp(name, "tc_prof") && (value == 0 || value == 1)) { g_tc_prof = value; return MSB_OK; }
+    if (name && !std::strcmp(name, "tc_first_lane_cap") && value >= 0) { g_tc_first_lane_cap = value; return MSB_OK; }
     set_error("msb_set_option: unknown option or value");
     return MSB_EINVAL;
 }

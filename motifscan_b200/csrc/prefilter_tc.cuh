@@ -29,8 +29,7 @@
 
 // Compile-time experiment switch (bench_micro/tc_ablate.sh builds one library per value; results in
 // profiles/): 0 = product, 1 = no candidate emission, 2 = no accumulator scan either, 3 = no TMEM
-// read-back either (tensor pipe alone); 4/5/6 = emission cut after the register dump / after the
-// decode / before the global flush.  Anything but 0 gives wrong results by design.
+// read-back either (tensor pipe alone).  Anything but 0 gives wrong results by design.
 #ifndef MSB_TC_EXP
 #define MSB_TC_EXP 0
 #endif
@@ -47,15 +46,13 @@ constexpr int kTcBOff = 27 * 1024;                      // B tiles start here (1
 constexpr int kTcUnitBytes = 8192;                      // one K=32 step of a 256-column tile
 constexpr int kTcMaxUnits = 22;                         // 8 KB K-steps of B per batch (180 KB of shared memory)
 constexpr int kTcMaxTiles = kTcMaxUnits;                // tiles per batch
-constexpr int kTcStageOff = kTcBOff + kTcMaxUnits * kTcUnitBytes;   // candidate staging, per epilogue warp
-constexpr int kTcStageCap = 128;                        // staged candidate keys per warp (8 B each), a power of two
-constexpr int kTcScratchBytes = 128;                    // per epilogue warp: one chunk's 32 registers
 constexpr int kTcCols = 256;                            // motif-strand columns per tile
 constexpr int kTcEpiWarps = 16;                         // two sets of 8: set g reads the units that land in TMEM buffer g
-constexpr int kTcThreads = (4 + kTcEpiWarps) * 32;
+constexpr int kTcProducerWarps = 3;                     // warps 1-3 expand the one-hot streams
+constexpr int kTcThreads = (4 + kTcEpiWarps) * 32;      // 640 threads x 96 registers
 constexpr int kTcWarpCols = 128;                        // accumulator columns one epilogue warp reads per unit
-constexpr int kTcScratchOff = kTcStageOff + kTcEpiWarps * kTcStageCap * 8;
-constexpr int kTcSmemBytes = kTcScratchOff + kTcEpiWarps * kTcScratchBytes;   // dynamic shared memory of the kernel
+constexpr int kTcSmemBytes = kTcBOff + kTcMaxUnits * kTcUnitBytes;   // dynamic shared memory of the kernel
+constexpr int kTcLanesPerCta = kTcEpiWarps * 32;        // epilogue lanes, each with its own candidate-record buffer
 constexpr int kTcStaticSmemReserve = 1024;             // static __shared__ (barriers) + alignment slack
 
 struct TcBatch {
@@ -75,11 +72,12 @@ struct TcParams {
     int32_t emit_dirty;
     int32_t any_zero_hit;
     int64_t pos_lo, pos_hi;    // only windows starting at packed positions [pos_lo, pos_hi) are scored (range scans)
-    uint64_t *cand;            // raw candidates: key(tile * 256 + column, packed position, 0)
-    int64_t cand_cap;
+    uint4 *cand;               // candidate records: buffer of epilogue lane g (= (CTA * 16 + epilogue warp) * 32 + lane) at cand + g * cand_cap
+    int64_t cand_cap;          // records per lane buffer
+    uint32_t *lane_count;      // [grid * kTcLanesPerCta] records written by each lane so far (carried across launches)
     int64_t *dirty;
     int64_t dirty_cap;
-    unsigned long long *counters;
+    unsigned long long *counters;   // [1] dirty positions (the record totals are reduced from lane_count by lane_prefix_kernel)
     long long *prof;           // optional [grid][16] cycle counters (msb_set_option("tc_prof", 1)); nullptr = off
 };
 
@@ -142,34 +140,27 @@ __device__ __forceinline__ uint32_t and8(const uint32_t (&r)[32], int g) {
     return (r[8 * g] & r[8 * g + 1] & r[8 * g + 2]) & (r[8 * g + 3] & r[8 * g + 4] & r[8 * g + 5]) & (r[8 * g + 6] & r[8 * g + 7]);
 }
 
-// Candidate staging.  A unit's accumulators are in registers when its TMEM buffer is released, but
-// the warp cannot start on its next unit before it is done with this one, and a set of eight warps
-// recycles a buffer only when all eight have read it -- with ~0.3 candidates per warp and unit,
-// nearly every unit has SOME warp on the rare path, so the rare path's latency, not its share of
-// the work, sets the pace.  It is therefore warp-uniform and call-free: the lanes vote; for each
-// lane with a clear sign bit in the 64-column chunk (usually one) that lane spills the chunk's 32
-// registers to a 128 B scratch line, every lane picks up one register = two accumulators, the
-// sign tests are two ballots, and the keys go to a per-warp staging queue in shared memory
-// (a ring of kTcStageCap keys, warp-uniform head and count in registers).  Whenever the ring holds
-// kTcFlushKeys keys they go to a block of the candidate buffer that the warp RESERVED EARLIER: the
-// atomic that reserves the next block is issued right after a flush and its result is not touched
-// until the next one, so no epilogue warp ever waits for a global round trip (a ~1000-cycle stall
-// of one warp holds up its TMEM buffer, and with it the tensor pipe).  Blocks are always written in
-// full; the tail of a warp's last block is padded with kTcNoKey, which the exact stage skips.
-// Column -> (motif, strand) decoding and the sequence-end check happen in the exact stage.
-constexpr int kTcFlushKeys = 64;
-constexpr uint64_t kTcNoKey = ~0ull;
-
-struct Stage {
-    uint32_t keys;        // shared-memory address of this warp's ring of kTcStageCap keys
-    uint32_t scratch;     // shared-memory address of this warp's 32-word scratch line
-    uint32_t addend;      // shared-memory address of this lane's 64-bit word holding kTcFlushKeys (see reserve_block)
-    int leader;           // 0, read from shared memory: the lane that reserves blocks
-    uint32_t head;        // ring index of the oldest staged key (warp-uniform, not wrapped)
-    uint32_t n;           // keys staged (warp-uniform)
-    unsigned long long resv;   // lane 0: first slot of the reserved block of kTcFlushKeys candidate slots
-};
-
+// Candidate emission.  A unit's accumulators are in registers when its TMEM buffer is released, but
+// a warp cannot start on its next unit before it is done with this one, and a set of eight warps
+// recycles a buffer only when all eight have read it.  With ~0.3 candidates per warp and unit nearly
+// every unit has SOME warp on the rare path, so whatever the rare path costs is paid by the tensor
+// pipe.  Measured with bench_micro/tc_ablate.sh (profiles/r1_c_ablation.txt): 3.9 ms with emission
+// compiled out; 6.3-6.8 ms with every variant that staged keys in shared memory from the epilogue
+// warps (per-lane slots + out-of-line decode, a warp-uniform ballot path, pre-reserved blocks), and
+// 7-13 ms with a shared-memory dump queue drained by a decoder warp: shared memory is ~75 % busy
+// feeding the tensor core, so anything that makes round trips through it on the rare path is slow,
+// and so is anything that waits for an atomic.  What is left is register-only:
+// a lane that sees a clear sign bit in its 64-column chunk folds the chunk's 64 sign bits into two
+// words (16 PRMT in sign-replication mode + 16 LOP3) and stores ONE 16-byte record
+// {position, first column, 64 flag bits} to ITS OWN buffer in global memory: no shared memory, no
+// atomic, no vote, nothing to wait for.  The exact stage expands the flag bits
+// (exact_records_kernel); lane_prefix_kernel turns the per-lane counts into offsets.
+//
+// Record: x = position bits 0..31, y = position bits 32..40 | first column (tile * 256 + column) << 9,
+//         z / w = flag words of columns +0..31 / +32..63: within a word, bit 8 b + k <=> column 4 k + b.
+__device__ __forceinline__ void st_global_v4(uint4 *p, uint32_t x, uint32_t y, uint32_t z, uint32_t w) {
+    asm volatile("st.global.v4.b32 [%0], {%1, %2, %3, %4};" ::"l"(p), "r"(x), "r"(y), "r"(z), "r"(w) : "memory");
+}
 __device__ __forceinline__ unsigned long long atom_add_global(unsigned long long *p, unsigned long long v) {
     unsigned long long old;
     asm volatile("atom.global.add.u64 %0, [%1], %2;" : "=l"(old) : "l"(p), "l"(v) : "memory");
@@ -178,93 +169,42 @@ __device__ __forceinline__ unsigned long long atom_add_global(unsigned long long
 __device__ __forceinline__ void st_global(uint64_t *p, uint64_t v) {
     asm volatile("st.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
 }
-
-// Lane 0 only.  ptxas rewrites an atomic add of a warp-uniform value into its warp-aggregated form
-// (vote, leader atomic, SHFL of the result), and that SHFL would wait for the round trip on the
-// spot.  So the addend comes from a per-lane word of shared memory (always kTcFlushKeys) and the
-// reserving lane from another (always 0): values the compiler cannot prove uniform keep the plain
-// ATOMG, whose result register is first read at the next flush.
-__device__ __forceinline__ unsigned long long reserve_block(const TcParams &P, const Stage &st) {
-    unsigned long long add;
-    asm volatile("ld.shared.b64 %0, [%1];" : "=l"(add) : "r"(st.addend) : "memory");
-    return atom_add_global(P.counters + 0, add);
+// prmt.b32 with selector 0xFDB9: bytes 1 and 3 of x, then bytes 1 and 3 of y, each replaced by its
+// sign bit replicated over the byte (selector nibble msb = sign mode): the signs of the four f16
+// accumulators of (x, y), one per byte.
+__device__ __forceinline__ uint32_t half_signs(uint32_t x, uint32_t y) {
+    uint32_t d;
+    asm("prmt.b32 %0, %1, %2, 0xFDB9;" : "=r"(d) : "r"(x), "r"(y));
+    return d;
 }
-
-// All 32 lanes: move the oldest min(n, 64) staged keys into the reserved block (padding it with
-// kTcNoKey when fewer are staged), then reserve the next block unless this is the final flush.
-__device__ __forceinline__ void stage_flush(const TcParams &P, Stage &st, int lane, bool last) {
-    const unsigned long long base = __shfl_sync(0xffffffffu, st.resv, 0);
-    const uint32_t cnt = st.n < (uint32_t) kTcFlushKeys ? st.n : (uint32_t) kTcFlushKeys;
+// flag word of 16 registers = 32 columns: bit 8 b + k set <=> accumulator 4 k + b has a clear sign
+__device__ __forceinline__ uint32_t flag_word(const uint32_t (&r)[32], int half) {
+    uint32_t f = 0;
 #pragma unroll
-    for (int h = 0; h < kTcFlushKeys / 32; h++) {
-        const uint32_t i = 32 * h + lane;
-        uint64_t key = kTcNoKey;
-        if (i < cnt) asm volatile("ld.shared.b64 %0, [%1];" : "=l"(key) : "r"(st.keys + 8 * ((st.head + i) & (kTcStageCap - 1))) : "memory");
-        if ((int64_t) (base + i) < P.cand_cap) st_global(P.cand + base + i, key);
-    }
-    st.head += cnt;
-    st.n -= cnt;
-    __syncwarp();
-    if (last) {
-        if (lane == 0 && cnt < (uint32_t) kTcFlushKeys) atom_add_global(P.counters + 3, (unsigned long long) (kTcFlushKeys - cnt));   // padding written
-    } else if (lane == st.leader) {
-        st.resv = reserve_block(P, st);
-    }
+    for (int k = 0; k < 8; k++) f |= ~half_signs(r[16 * half + 2 * k], r[16 * half + 2 * k + 1]) & (0x01010101u << k);
+    return f;
 }
+
+struct LaneOut {
+    uint4 *buf;        // this lane's record buffer
+    uint32_t n;        // records written (may exceed the capacity: the host then retries with a larger one)
+};
 
 // One packed 64-column load of this lane's window: r[j] holds columns col0 + 2j (low half) and
-// col0 + 2j + 1 (high half).  p0 = packed position of lane 0's window; lane l's is p0 + 4 l.
-__device__ __forceinline__ void scan_chunk(const TcParams &P, Stage &st, const uint32_t (&r)[32], bool live,
-                                           uint32_t col0, int64_t p0, int lane) {
+// col0 + 2j + 1 (high half) of the window at packed position p.
+__device__ __forceinline__ void scan_chunk(const TcParams &P, LaneOut &out, const uint32_t (&r)[32], bool live,
+                                           uint32_t col0, int64_t p) {
     constexpr uint32_t M = 0x80008000u;
     const uint32_t g = and8(r, 0) & and8(r, 1) & and8(r, 2) & and8(r, 3);
-    uint32_t bal = __ballot_sync(0xffffffffu, live && (g & M) != M);
+    bool hit = live && (g & M) != M;
 #if MSB_TC_EXP >= 1 && MSB_TC_EXP <= 3
-    bal = 0;
+    hit = false;
 #endif
-    while (bal) {                                       // warp-uniform
-        const int src = __ffs(bal) - 1;
-        bal &= bal - 1;
-        if (lane == src) {
-#pragma unroll
-            for (int k = 0; k < 8; k++)
-                asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(st.scratch + 16 * k), "r"(r[4 * k]),
-                             "r"(r[4 * k + 1]), "r"(r[4 * k + 2]), "r"(r[4 * k + 3]) : "memory");
-        }
-        __syncwarp();
-#if MSB_TC_EXP == 4
-        continue;                                       // ablation: vote + dump only
-#endif
-        uint32_t w;
-        asm volatile("ld.shared.b32 %0, [%1];" : "=r"(w) : "r"(st.scratch + 4 * lane) : "memory");
-        __syncwarp();
-        const uint32_t b_lo = __ballot_sync(0xffffffffu, !(w & 0x00008000u));
-        const uint32_t b_hi = __ballot_sync(0xffffffffu, !(w & 0x80000000u));
-        const uint32_t below = (1u << lane) - 1u;
-        const int64_t p = p0 + 4 * src;
-        const uint32_t n_lo = __popc(b_lo);
-        const uint32_t tail = st.head + st.n;
-#if MSB_TC_EXP == 5
-        st.head += n_lo + __popc(b_hi);                 // ablation: decode, no key stores, no flush
-        continue;
-#endif
-        if (!(w & 0x00008000u)) {
-            const uint64_t key = make_key(col0 + 2 * lane, p, 0);
-            asm volatile("st.shared.b64 [%0], %1;" ::"r"(st.keys + 8 * ((tail + __popc(b_lo & below)) & (kTcStageCap - 1))), "l"(key) : "memory");
-        }
-        if (!(w & 0x80000000u)) {
-            const uint64_t key = make_key(col0 + 2 * lane + 1, p, 0);
-            asm volatile("st.shared.b64 [%0], %1;" ::"r"(st.keys + 8 * ((tail + n_lo + __popc(b_hi & below)) & (kTcStageCap - 1))), "l"(key) : "memory");
-        }
-        st.n += n_lo + __popc(b_hi);
-#if MSB_TC_EXP == 6
-        if (st.n >= (uint32_t) kTcFlushKeys) { st.head += kTcFlushKeys; st.n -= kTcFlushKeys; }   // ablation: keys staged, never written
-        continue;
-#endif
-        if (st.n >= (uint32_t) kTcFlushKeys) {   // <= 63 staged before, <= 64 added: the ring of 128 never overflows
-            __syncwarp();
-            stage_flush(P, st, lane, false);
-        }
+    if (hit) {   // divergent, rare
+        const uint32_t z = flag_word(r, 0), w = flag_word(r, 1);
+        if ((int64_t) out.n < P.cand_cap)
+            st_global_v4(out.buf + out.n, (uint32_t) p, (uint32_t) ((uint64_t) p >> 32) | (col0 << 9), z, w);
+        out.n++;
     }
 }
 
@@ -323,8 +263,6 @@ prefilter_tc_kernel(const __grid_constant__ TcParams P) {
     uint8_t *s_b = smem + kTcBOff;
     __shared__ uint64_t bar_stream_full[kTcSlots], bar_stream_empty[kTcSlots], bar_tmem_full[2], bar_tmem_empty[2];
     __shared__ uint32_t s_tmem_base;
-    __shared__ int s_leader;
-    __shared__ unsigned long long s_flush_keys[32];   // all kTcFlushKeys; indexed by lane so that ptxas sees a divergent value
     __shared__ uint32_t s_skip[kTcSlots];
     __shared__ uint2 s_tile[kTcMaxTiles];   // per tile: B descriptor low word, K steps
 
@@ -335,12 +273,10 @@ prefilter_tc_kernel(const __grid_constant__ TcParams P) {
     const int64_t n_ptiles = (P.pos_hi + kTcTileBases - 1) / kTcTileBases;
 
     if (threadIdx.x == 0) {
-        for (int i = 0; i < kTcSlots; i++) { mbar_init(&bar_stream_full[i], 3); mbar_init(&bar_stream_empty[i], 1 + kTcEpiWarps); }
+        for (int i = 0; i < kTcSlots; i++) { mbar_init(&bar_stream_full[i], kTcProducerWarps); mbar_init(&bar_stream_empty[i], 1 + kTcEpiWarps); }
         for (int i = 0; i < 2; i++) { mbar_init(&bar_tmem_full[i], 1); mbar_init(&bar_tmem_empty[i], kTcEpiWarps / 2); }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
-    if (threadIdx.x < 32) s_flush_keys[threadIdx.x] = kTcFlushKeys;
-    if (threadIdx.x == 0) s_leader = 0;
     if (threadIdx.x < P.batch.n_tiles) {
         const uint32_t bt = smem_u32(s_b) + (uint32_t) P.batch.unit_off[threadIdx.x] * kTcUnitBytes;
         s_tile[threadIdx.x] = make_uint2(((bt & 0x3FFFFu) >> 4) | ((4096u >> 4) << 16), P.batch.ks[threadIdx.x]);
@@ -422,7 +358,7 @@ prefilter_tc_kernel(const __grid_constant__ TcParams P) {
             long long *o = P.prof + blockIdx.x * 16;
             o[0] = now() - t_begin; o[1] = t_ws; o[2] = t_we; o[3] = t_is; o[4] = u;
         }
-    } else if (warp < 4) {
+    } else if (warp <= kTcProducerWarps) {
         // ---- producers: packed codes -> 4 shifted one-hot streams, ignore bits, dirty windows -----
         const int tid_p = (warp - 1) * 32 + lane;
         const uint32_t horizon = P.lmax_all >= 32 ? 0xffffffffu : ((1u << P.lmax_all) - 1u);
@@ -432,7 +368,7 @@ prefilter_tc_kernel(const __grid_constant__ TcParams P) {
             mbar_wait_a(B.stream_empty + 8 * slot, ((it / kTcSlots) & 1) ^ 1);
             const int64_t tile_start = t * kTcTileBases;
             uint32_t *dst = reinterpret_cast<uint32_t *>(s_stream + slot * kTcSlotBytes);
-            for (int a = tid_p; a < kTcStreamBases + 3; a += 96) {
+            for (int a = tid_p; a < kTcStreamBases + 3; a += 32 * kTcProducerWarps) {
                 const int64_t p = tile_start + a;
                 uint32_t word = 0;
                 if (p < S.total_packed) {
@@ -493,18 +429,10 @@ prefilter_tc_kernel(const __grid_constant__ TcParams P) {
         // ---- epilogue: warp reads TMEM lanes 32 q .. 32 q + 31 (its 32 windows), 128 of the 256 columns
         const int q = warp & 3, h = ((warp - 4) >> 2) & 1, set = (warp - 4) >> 3;
         const int row = q * 32 + lane;
-        Stage stg;
-        stg.keys = smem_u32(smem + kTcStageOff) + (warp - 4) * kTcStageCap * 8;
-        stg.scratch = smem_u32(smem + kTcScratchOff) + (warp - 4) * kTcScratchBytes;
-        stg.head = 0;
-        stg.n = 0;
-        stg.resv = 0;
-        {   // a per-lane offset that is always 0 but comes out of memory: the address stays opaque even where lane == leader is known
-            const uint32_t z = (uint32_t) (*reinterpret_cast<volatile unsigned long long *>(&s_flush_keys[lane]) >> 32);
-            stg.addend = smem_u32(&s_flush_keys[(lane + z) & 31]);
-        }
-        stg.leader = s_leader;                                   // 0, but not to the compiler (see reserve_block)
-        if (lane == stg.leader) stg.resv = reserve_block(P, stg);   // first block; used at the first flush
+        LaneOut out;
+        const size_t lane_id = ((size_t) blockIdx.x * kTcEpiWarps + (warp - 4)) * 32 + lane;
+        out.buf = P.cand + lane_id * (size_t) P.cand_cap;
+        out.n = P.lane_count[lane_id];
         const uint32_t taddr0 = tmem + set * kTcCols + h * kTcWarpCols + ((uint32_t) (q * 32) << 16);
         const uint32_t colid0 = P.batch.first_tile * kTcCols + h * kTcWarpCols;
         uint32_t u = 0, it = 0;
@@ -528,7 +456,7 @@ prefilter_tc_kernel(const __grid_constant__ TcParams P) {
             for (uint32_t v = (uint32_t) set; v < 4 * NT; v += 2) {
                 const uint32_t uu = u + v;
                 const bool live = !((ign4 >> sh) & 1u);
-                const int64_t p0 = tile_start + 4 * (q * 32) + sh;   // lane 0's window; lane l's is p0 + 4 l
+                const int64_t p = tile_start + 4 * row + sh;
                 const uint32_t colid = colid0 + nt * kTcCols;
                 const long long c0 = now();
                 mbar_wait_a(B.tmem_full + 8 * set, (uu >> 1) & 1);
@@ -548,15 +476,15 @@ prefilter_tc_kernel(const __grid_constant__ TcParams P) {
                 if (lane == 0) mbar_arrive_a(B.tmem_empty + 8 * set);   // accumulators are in registers
                 const long long c2 = now() + ((r0[0] ^ r0[31]) == 0x12345679u);   // depends on the loaded data
                 t_ld += c2 - c1;
-                const uint32_t n_before = stg.n;
+                const uint32_t n_before = out.n;
 #if MSB_TC_EXP != 2 && MSB_TC_EXP != 3
-                scan_chunk(P, stg, r0, live, colid, p0, lane);
-                scan_chunk(P, stg, r1, live, colid + 64, p0, lane);
+                scan_chunk(P, out, r0, live, colid, p);
+                scan_chunk(P, out, r1, live, colid + 64, p);
 #endif
                 if (kProf) {
                     const long long c3 = now();
                     t_pr += c3 - c2;
-                    if (stg.n != n_before) { t_slow += c3 - c2; n_slow++; }
+                    if (__any_sync(0xffffffffu, out.n != n_before)) { t_slow += c3 - c2; n_slow++; }
                     if (P.prof && blockIdx.x == 0 && lane == 0 && (warp == 4 || warp == 12) && uu >= 2000 && uu < 2012) {
                         long long *o = P.prof + gridDim.x * 16 + (uu - 2000) * 8;
                         o[2] = c0; o[3] = c1; o[4] = c2; o[5] = c3; o[6] = warp;
@@ -567,8 +495,7 @@ prefilter_tc_kernel(const __grid_constant__ TcParams P) {
             }
             u += 4 * NT;
         }
-        __syncwarp();
-        stage_flush(P, stg, lane, true);   // the rest (< 64 keys) + padding: every reserved block is written in full
+        P.lane_count[lane_id] = out.n;
         if (kProf && P.prof && warp == 4 && lane == 0) {
             long long *o = P.prof + blockIdx.x * 16;
             o[8] = t_wf; o[9] = t_ld; o[10] = t_pr; o[11] = t_wsf; o[12] = u; o[13] = t_slow; o[14] = n_slow;

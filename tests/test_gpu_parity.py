@@ -227,6 +227,33 @@ def test_dense_hits_overflow_retry(eng):
     res.close(), sset.close(), motifs.close(), ctx.close()
 
 
+def test_lane_record_buffer_overflow_retry(eng):
+    """Tensor-core prefilter: every epilogue lane appends candidate records to its own buffer; a lane
+    that runs out of room only counts, and the scan is repeated with buffers sized for the largest
+    count.  Forced here with a first-attempt capacity of 2 records per lane."""
+    from motifscan_b200 import _lib
+    rng = np.random.default_rng(113)
+    pwms = synth_pwms(rng, 200)
+    seqs = synth_seqs(rng, 40, 900, 1100, p_n=0.001)
+    cutoffs = cutoffs_for(pwms, seqs, 2e-3)
+    ctx = eng.default_context(0)
+    motifs = eng.MotifSet(ctx, pwms, cutoffs)
+    sset = eng.SequenceSet(ctx, seqs)
+    expect = oracle.scan_arrays(pwms, cutoffs, seqs, 3, n_threads=8)
+    try:
+        _lib.check(_lib.load().msb_set_option(b"tc_first_lane_cap", 2))
+        res = eng.scan(ctx, motifs, sset, 3)
+        assert ctx.counters()["retries"] >= 1
+        assert_scan_equal(res, expect)
+        res.close()
+    finally:
+        _lib.check(_lib.load().msb_set_option(b"tc_first_lane_cap", 0))
+    res = eng.scan(ctx, motifs, sset, 3)
+    assert ctx.counters()["retries"] == 0
+    assert_scan_equal(res, expect)
+    res.close(), sset.close(), motifs.close()
+
+
 def test_set_cutoffs_rebuilds_tables(eng):
     rng = np.random.default_rng(14)
     pwms = synth_pwms(rng, 12)
