@@ -379,61 +379,43 @@ exact_candidates_kernel(ExactParams E, const uint64_t *__restrict__ cand, int64_
 }
 
 // The tensor-core prefilter leaves its candidate records in one buffer per epilogue lane
-// (prefilter_tc.cuh, "Candidate emission").  lane_prefix_kernel (one block): exclusive prefix sum of
-// the per-lane record counts, clamped to the buffer capacity -> offsets[n_lanes + 1];
-// counters[0] = total records, counters[3] = largest unclamped count (> capacity: the host retries).
+// (prefilter_tc.cuh, "Candidate emission").  lane_totals_kernel (one block): counters[0] = records
+// held (counts clamped to the buffer capacity), counters[3] = largest unclamped count -- beyond the
+// capacity the host repeats the prefilter with larger buffers.
 __global__ void __launch_bounds__(1024)
-lane_prefix_kernel(const uint32_t *__restrict__ lane_count, int32_t n_lanes, int64_t cap,
-                   int64_t *__restrict__ offsets, unsigned long long *__restrict__ counters) {
-    __shared__ long long s_sum[1024];
-    __shared__ unsigned int s_max[1024];
-    const int t = threadIdx.x;
-    const int per = (n_lanes + 1023) / 1024;
-    const int a = min(t * per, n_lanes), e = min(a + per, n_lanes);
-    long long sum = 0;
+lane_totals_kernel(const uint32_t *__restrict__ lane_count, int32_t n_lanes, int64_t cap,
+                   unsigned long long *__restrict__ counters) {
+    __shared__ unsigned long long s_sum[32];
+    __shared__ unsigned int s_max[32];
+    unsigned long long sum = 0;
     unsigned int mx = 0;
-    for (int i = a; i < e; i++) {
-        const unsigned int c = lane_count[i];
+    for (int i = threadIdx.x; i < n_lanes; i += blockDim.x) {
+        const unsigned int c = __ldg(lane_count + i);
         mx = max(mx, c);
-        sum += min((long long) c, (long long) cap);
+        sum += min((unsigned long long) c, (unsigned long long) cap);
     }
-    s_sum[t] = sum;
-    s_max[t] = mx;
+    for (int d = 16; d; d >>= 1) {
+        sum += __shfl_xor_sync(0xffffffffu, sum, d);
+        mx = max(mx, __shfl_xor_sync(0xffffffffu, mx, d));
+    }
+    if ((threadIdx.x & 31) == 0) { s_sum[threadIdx.x >> 5] = sum; s_max[threadIdx.x >> 5] = mx; }
     __syncthreads();
-    for (int d = 1; d < 1024; d <<= 1) {   // inclusive scan of the per-thread sums, running maximum
-        const long long v = t >= d ? s_sum[t - d] : 0;
-        const unsigned int m = t >= d ? s_max[t - d] : 0u;
-        __syncthreads();
-        s_sum[t] += v;
-        s_max[t] = max(s_max[t], m);
-        __syncthreads();
-    }
-    long long at = s_sum[t] - sum;
-    for (int i = a; i < e; i++) {
-        offsets[i] = at;
-        at += min((long long) lane_count[i], (long long) cap);
-    }
-    if (t == 1023) {
-        offsets[n_lanes] = s_sum[1023];
-        counters[0] = (unsigned long long) s_sum[1023];
-        counters[3] = s_max[1023];
+    if (threadIdx.x < 32) {
+        sum = s_sum[threadIdx.x];
+        mx = s_max[threadIdx.x];
+        for (int d = 16; d; d >>= 1) {
+            sum += __shfl_xor_sync(0xffffffffu, sum, d);
+            mx = max(mx, __shfl_xor_sync(0xffffffffu, mx, d));
+        }
+        if (threadIdx.x == 0) { counters[0] = sum; counters[3] = mx; }
     }
 }
 
-// One thread per record = one window; its bases are loaded once and every flagged column of the
-// chunk's 64 is decoded (col_info: tile column -> sorted motif, strand) and re-scored.
-__global__ void __launch_bounds__(256)
-exact_records_kernel(ExactParams E, const uint4 *__restrict__ rec, int64_t rec_cap,
-                     const int64_t *__restrict__ offsets, int32_t n_lanes, int64_t n_rec,
-                     const int32_t *__restrict__ order, const uint32_t *__restrict__ col_info) {
-    const int64_t i = (int64_t) blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= n_rec) return;
-    int lo = 0, hi = n_lanes;   // the lane buffer that holds record i: largest b with offsets[b] <= i
-    while (hi - lo > 1) {
-        const int mid = (lo + hi) >> 1;
-        if (__ldg(offsets + mid) <= i) lo = mid; else hi = mid;
-    }
-    const uint4 r = __ldg(rec + (int64_t) lo * rec_cap + (i - __ldg(offsets + lo)));
+// One warp per lane buffer, one thread per record = one window: its bases are loaded once and every
+// flagged column of the chunk's 64 is decoded (col_info: tile column -> sorted motif, strand) and
+// re-scored.  A warp's 32 records are contiguous (512 B).
+__device__ __forceinline__ void exact_record(const ExactParams &E, const uint4 r, const int32_t *__restrict__ order,
+                                             const uint32_t *__restrict__ col_info) {
     const int64_t p = (int64_t) (((uint64_t) (r.y & 0x1ffu) << 32) | r.x);
     const uint32_t col0 = r.y >> 9;
     const int64_t s = __ldg(E.seq.blk_seq + (p >> 5));
@@ -459,6 +441,17 @@ exact_records_kernel(ExactParams E, const uint4 *__restrict__ rec, int64_t rec_c
     }
 }
 
+__global__ void __launch_bounds__(256)
+exact_records_kernel(ExactParams E, const uint4 *__restrict__ rec, int64_t rec_cap,
+                     const uint32_t *__restrict__ lane_count, int32_t n_lanes,
+                     const int32_t *__restrict__ order, const uint32_t *__restrict__ col_info) {
+    const int64_t b = ((int64_t) blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    if (b >= n_lanes) return;
+    const int64_t n = min((int64_t) __ldg(lane_count + b), rec_cap);
+    const uint4 *buf = rec + b * rec_cap;
+    for (int64_t k = threadIdx.x & 31; k < n; k += 32) exact_record(E, __ldg(buf + k), order, col_info);
+}
+
 // One thread per (listed position, motif); consecutive threads take consecutive motifs of the
 // same position.  `motif_ids` == nullptr means all motifs.
 __global__ void __launch_bounds__(256)
@@ -481,27 +474,50 @@ exact_positions_kernel(ExactParams E, const int64_t *__restrict__ pos, int64_t n
     if (E.strand & 2) test_and_emit(E, m, p, 1, exact_raw(E.seq, pw, L, p, 1));
 }
 
-// Dirty windows (they touch a non-ACGT base) x the table-path motifs: one warp per listed
-// position, the window's bases loaded once, lanes stride over the motifs.
+// Dirty windows (they touch a non-ACGT base) x the prefilter-path motifs.  A warp takes 32 listed
+// positions (one per lane, the window's bases in registers) and a chunk of kDirtyMotifs motifs, and
+// walks the motifs together: the motif, its length and the column are warp-uniform, so the 32
+// lanes' PWM reads of one column fall into ONE 32-byte sector (the four rows of a column), instead
+// of 32 sectors when each lane scores a different motif.
+constexpr int kDirtyMotifs = 64;
 __global__ void __launch_bounds__(256)
 exact_dirty_kernel(ExactParams E, const int64_t *__restrict__ pos, int64_t n_pos,
                    const int32_t *__restrict__ motif_ids, int32_t n_ids) {
-    const int64_t d = ((int64_t) blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-    if (d >= n_pos) return;
-    const int lane = threadIdx.x & 31;
-    const int64_t p = __ldg(pos + d);
-    const int64_t s = __ldg(E.seq.blk_seq + (p >> 5));
-    const int64_t left = (int64_t) __ldg(E.seq.len + s) - (p - __ldg(E.seq.poff + s));
-    if (left <= 0) return;
-    if (E.seq.limit && p - __ldg(E.seq.poff + s) >= (int64_t) __ldg(E.seq.limit + s)) return;
-    const Window32 w = load_window32(E.seq, p);
-    for (int32_t k = lane; k < n_ids; k += 32) {
+    const int64_t warp = ((int64_t) blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int32_t n_chunks = (n_ids + kDirtyMotifs - 1) / kDirtyMotifs;
+    const int64_t group = warp / n_chunks;
+    const int32_t chunk = (int32_t) (warp - group * n_chunks);
+    if (group * 32 >= n_pos) return;
+    const int64_t d = group * 32 + (threadIdx.x & 31);
+    int64_t p = 0, left = 0;
+    Window32 w;
+    w.codes = 0;
+    w.nmask = 0;
+    if (d < n_pos) {
+        p = __ldg(pos + d);
+        const int64_t s = __ldg(E.seq.blk_seq + (p >> 5));
+        const int64_t j = p - __ldg(E.seq.poff + s);
+        left = (int64_t) __ldg(E.seq.len + s) - j;
+        if (E.seq.limit && j >= (int64_t) __ldg(E.seq.limit + s)) left = 0;   // the next chunk owns this start
+        if (left > 0) w = load_window32(E.seq, p);
+    }
+    const int32_t k_end = min(n_ids, (chunk + 1) * kDirtyMotifs);
+    for (int32_t k = chunk * kDirtyMotifs; k < k_end; k++) {
         const uint32_t m = (uint32_t) __ldg(motif_ids + k);
         const int L = __ldg(E.mot.len + m);
-        if (L > left) continue;   // cscore.c:337,340
         const double *pw = E.mot.pwm + 4 * (int64_t) __ldg(E.mot.col_off + m);
-        if (E.strand & 1) test_and_emit(E, m, p, 0, exact_raw_w(w, pw, L, 0));
-        if (E.strand & 2) test_and_emit(E, m, p, 1, exact_raw_w(w, pw, L, 1));
+        // both strands in one pass over the columns: the same additions in the same order as
+        // exact_raw_w (ascending c, non-ACGT bases skipped), two independent chains
+        double f = 0.0, r = 0.0;
+        for (int c = 0; c < L; c++) {
+            if ((w.nmask >> c) & 1u) continue;
+            const int row = (int) ((w.codes >> (2 * c)) & 3u);
+            if (E.strand & 1) f = __dadd_rn(f, __ldg(pw + 4 * c + row));
+            if (E.strand & 2) r = __dadd_rn(r, __ldg(pw + 4 * (L - 1 - c) + (3 - row)));
+        }
+        if (L > left) continue;   // cscore.c:337,340 (also lanes without a position: left = 0)
+        if (E.strand & 1) test_and_emit(E, m, p, 0, f);
+        if (E.strand & 2) test_and_emit(E, m, p, 1, r);
     }
 }
 

@@ -73,7 +73,7 @@ struct msb_ctx {
     DevBuf ascii, seq_off, cand, dirty, hit_key, hit_score, key_alt, score_alt, sort_tmp, counters;
     DevBuf out_seq, out_start, out_strand, out_counts, scores, scores_sorted, seg_off, ranks, sel;
     DevBuf keep, keep_pos, out2_seq, out2_start, out2_strand;
-    DevBuf lane_count, lane_off;   // tensor-core prefilter: records per epilogue lane, their prefix sums
+    DevBuf lane_count;   // tensor-core prefilter: records per epilogue lane
     // final site arrays of the last scan (point into the buffers above)
     uint64_t *fin_key = nullptr;
     double *fin_score = nullptr;
@@ -315,7 +315,7 @@ int msb_ctx_destroy(msb_ctx *ctx) {
                       &ctx->key_alt, &ctx->score_alt, &ctx->sort_tmp, &ctx->counters, &ctx->out_seq,
                       &ctx->out_start, &ctx->out_strand, &ctx->out_counts, &ctx->scores,
                       &ctx->scores_sorted, &ctx->seg_off, &ctx->ranks, &ctx->sel, &ctx->keep, &ctx->keep_pos,
-                      &ctx->out2_seq, &ctx->out2_start, &ctx->out2_strand, &ctx->lane_count, &ctx->lane_off})
+                      &ctx->out2_seq, &ctx->out2_start, &ctx->out2_strand, &ctx->lane_count})
         b->release();
     for (auto &b : ctx->pinned_free) cudaFreeHost(b.p);
     for (auto &b : ctx->dev_free) b.release();
@@ -1115,7 +1115,6 @@ static int scan_device(msb_ctx *ctx, msb_motifs *M, const msb_seqs *S, int stran
             lane_cap = std::max<int64_t>(cand_cap / 2 / n_lanes, 1);   // 16-byte records per lane buffer
             if (attempt == 0 && g_tc_first_lane_cap > 0) lane_cap = std::min<int64_t>(lane_cap, g_tc_first_lane_cap);
             MSB_TRY(ctx->lane_count.ensure((size_t) n_lanes * 4));
-            MSB_TRY(ctx->lane_off.ensure((size_t) (n_lanes + 1) * 8));
             MSB_CUDA(cudaMemsetAsync(ctx->lane_count.p, 0, (size_t) n_lanes * 4, st));
             P.cand = ctx->cand.as<uint4>();
             P.cand_cap = lane_cap;
@@ -1147,7 +1146,7 @@ static int scan_device(msb_ctx *ctx, msb_motifs *M, const msb_seqs *S, int stran
                     ctx->c[MSB_C_PREFILTER_LAUNCHES]++;
                 }
             }
-            lane_prefix_kernel<<<1, 1024, 0, st>>>(ctx->lane_count.as<uint32_t>(), n_lanes, lane_cap, ctx->lane_off.as<int64_t>(),
+            lane_totals_kernel<<<1, 1024, 0, st>>>(ctx->lane_count.as<uint32_t>(), n_lanes, lane_cap,
                                                    ctx->counters.as<unsigned long long>());
             MSB_CUDA(cudaGetLastError());
             ctx->c[MSB_C_LAUNCHES]++;
@@ -1239,8 +1238,8 @@ static int scan_device(msb_ctx *ctx, msb_motifs *M, const msb_seqs *S, int stran
         E.hit_cap = hit_cap;
         E.counters = ctx->counters.as<unsigned long long>();
         if (use_tc && n_rec) {
-            exact_records_kernel<<<(unsigned) ((n_rec + 255) / 256), 256, 0, st>>>(
-                E, ctx->cand.as<uint4>(), lane_cap, ctx->lane_off.as<int64_t>(), n_lanes, n_rec, d_order,
+            exact_records_kernel<<<(unsigned) (((int64_t) n_lanes * 32 + 255) / 256), 256, 0, st>>>(
+                E, ctx->cand.as<uint4>(), lane_cap, ctx->lane_count.as<uint32_t>(), n_lanes, d_order,
                 TT->d_col_info.as<uint32_t>());
             MSB_CUDA(cudaGetLastError());
             ctx->c[MSB_C_LAUNCHES]++;
@@ -1251,8 +1250,8 @@ static int scan_device(msb_ctx *ctx, msb_motifs *M, const msb_seqs *S, int stran
             ctx->c[MSB_C_LAUNCHES]++;
         }
         if (n_dirty && n_fast) {
-            const int64_t threads = n_dirty * 32;
-            exact_dirty_kernel<<<(unsigned) ((threads + 255) / 256), 256, 0, st>>>(E, ctx->dirty.as<int64_t>(), n_dirty, d_order, n_fast);
+            const int64_t warps = ((n_dirty + 31) / 32) * ((n_fast + kDirtyMotifs - 1) / kDirtyMotifs);
+            exact_dirty_kernel<<<(unsigned) ((warps * 32 + 255) / 256), 256, 0, st>>>(E, ctx->dirty.as<int64_t>(), n_dirty, d_order, n_fast);
             MSB_CUDA(cudaGetLastError());
             ctx->c[MSB_C_LAUNCHES]++;
         }

@@ -77,7 +77,7 @@ struct TcParams {
     uint32_t *lane_count;      // [grid * kTcLanesPerCta] records written by each lane so far (carried across launches)
     int64_t *dirty;
     int64_t dirty_cap;
-    unsigned long long *counters;   // [1] dirty positions (the record totals are reduced from lane_count by lane_prefix_kernel)
+    unsigned long long *counters;   // [1] dirty positions (the record totals are reduced from lane_count by lane_totals_kernel)
     long long *prof;           // optional [grid][16] cycle counters (msb_set_option("tc_prof", 1)); nullptr = off
 };
 
@@ -154,7 +154,7 @@ __device__ __forceinline__ uint32_t and8(const uint32_t (&r)[32], int g) {
 // words (16 PRMT in sign-replication mode + 16 LOP3) and stores ONE 16-byte record
 // {position, first column, 64 flag bits} to ITS OWN buffer in global memory: no shared memory, no
 // atomic, no vote, nothing to wait for.  The exact stage expands the flag bits
-// (exact_records_kernel); lane_prefix_kernel turns the per-lane counts into offsets.
+// (exact_records_kernel, one warp per lane buffer); lane_totals_kernel reduces the per-lane counts.
 //
 // Record: x = position bits 0..31, y = position bits 32..40 | first column (tile * 256 + column) << 9,
 //         z / w = flag words of columns +0..31 / +32..63: within a word, bit 8 b + k <=> column 4 k + b.
