@@ -121,6 +121,13 @@ int msb_scan(msb_ctx *ctx, const msb_motifs *motifs, const msb_seqs *seqs, int s
 #define MSB_SCAN_DEDUP 1
 int msb_scan_ex(msb_ctx *ctx, const msb_motifs *motifs, const msb_seqs *seqs, int strand,
                 int flags, msb_result **out);
+/* c_scan_motif in one call with persistent motifs (cscore.c:399-476: strings in, sites out):
+ * msb_seqs_from_ascii + msb_scan_ex, with the host-to-device copy of the sequence bytes cut into
+ * slices of whole sequences so that the copy of one slice overlaps the scan of the previous one.
+ * `seq_bytes` should be pinned (msb_pinned_alloc) for the copies to be asynchronous.  The encoded
+ * sequence set is returned through `seqs_out` unless that is NULL. */
+int msb_scan_ascii(msb_ctx *ctx, const msb_motifs *motifs, int64_t n_seqs, const char *seq_bytes,
+                   const int64_t *seq_off, int strand, int flags, msb_seqs **seqs_out, msb_result **out);
 /* Range scan over a resident sequence set (genome-wide scans, configs[3]): only windows that START
  * in [start[k], end[k]) of sequence seq_idx[k] are scored; a window may run past `end` into the rest
  * of its sequence, exactly as if the whole sequence had been scanned (cscore.c:336-340), so the

@@ -51,6 +51,8 @@ SIGNATURES = {
     "msb_seqs_destroy": (ctypes.c_int, [c_vp]),
     "msb_scan": (ctypes.c_int, [c_vp, c_vp, c_vp, ctypes.c_int, ctypes.POINTER(c_vp)]),
     "msb_scan_ex": (ctypes.c_int, [c_vp, c_vp, c_vp, ctypes.c_int, ctypes.c_int, ctypes.POINTER(c_vp)]),
+    "msb_scan_ascii": (ctypes.c_int, [c_vp, c_vp, ctypes.c_int64, c_vp, c_i64p, ctypes.c_int, ctypes.c_int,
+                                      ctypes.POINTER(c_vp), ctypes.POINTER(c_vp)]),
     "msb_scan_ranges": (ctypes.c_int, [c_vp, c_vp, c_vp, ctypes.c_int, ctypes.c_int, ctypes.c_int64, c_i64p, c_i64p,
                                        c_i64p, ctypes.POINTER(c_vp)]),
     "msb_scan_ranges_device": (ctypes.c_int, [c_vp, c_vp, c_vp, ctypes.c_int, ctypes.c_int, ctypes.c_int64, c_i64p,

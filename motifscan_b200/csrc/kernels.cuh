@@ -41,9 +41,9 @@ __device__ __forceinline__ int base_code(const SeqView &S, int64_t q) {
 __global__ void __launch_bounds__(256)
 encode_pack_kernel(const uint8_t *__restrict__ ascii, const int64_t *__restrict__ seq_off,
                    const int64_t *__restrict__ poff, const int32_t *__restrict__ len,
-                   int64_t n_seqs, int64_t n_blocks, uint32_t *__restrict__ codes,
+                   int64_t n_seqs, int64_t first_block, int64_t n_blocks, uint32_t *__restrict__ codes,
                    uint32_t *__restrict__ nmask, int32_t *__restrict__ blk_seq) {
-    int64_t b = (int64_t) blockIdx.x * blockDim.x + threadIdx.x;
+    int64_t b = first_block + (int64_t) blockIdx.x * blockDim.x + threadIdx.x;   // blocks [first_block, n_blocks)
     if (b >= n_blocks) return;
     int64_t p = b * kPadBases;
     int64_t s = find_seq(poff, n_seqs, p);

@@ -13,6 +13,7 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <functional>
 #include <limits>
 #include <mutex>
 #include <new>
@@ -67,6 +68,8 @@ struct msb_ctx {
     int sm_count = 0;
     size_t smem_optin = 0;
     cudaEvent_t ev[8] = {};
+    cudaStream_t copy_stream = nullptr;   // msb_scan_ascii: host-to-device slices overlap the scan (created on first use)
+    cudaEvent_t slice_ev[8] = {};
     double t[MSB_T_COUNT] = {};
     int64_t c[MSB_C_COUNT] = {};
     // scratch (grow-only, reused across calls)
@@ -321,6 +324,8 @@ int msb_ctx_destroy(msb_ctx *ctx) {
     for (auto &b : ctx->dev_free) b.release();
     if (ctx->h_counters) cudaFreeHost(ctx->h_counters);
     for (auto &evt : ctx->ev) if (evt) cudaEventDestroy(evt);
+    for (auto &evt : ctx->slice_ev) if (evt) cudaEventDestroy(evt);
+    if (ctx->copy_stream) cudaStreamDestroy(ctx->copy_stream);
     if (ctx->own_stream) cudaStreamDestroy(ctx->stream);
     delete ctx;
     return MSB_OK;
@@ -541,7 +546,7 @@ int msb_seqs_from_ascii(msb_ctx *ctx, int64_t n_seqs, const char *bytes, const i
         const int64_t grid = (n_blocks + 255) / 256;
         encode_pack_kernel<<<(unsigned) grid, 256, 0, st>>>(
             ctx->ascii.as<uint8_t>(), S->d_seq_off.as<int64_t>(), S->d_poff.as<int64_t>(), S->d_len.as<int32_t>(),
-            n_seqs, n_blocks, S->d_codes.as<uint32_t>(), S->d_nmask.as<uint32_t>(), S->d_blk_seq.as<int32_t>());
+            n_seqs, 0, n_blocks, S->d_codes.as<uint32_t>(), S->d_nmask.as<uint32_t>(), S->d_blk_seq.as<int32_t>());
         step(cudaGetLastError());
     }
     step(cudaEventRecord(ctx->ev[2], st));
@@ -1050,8 +1055,12 @@ static int make_ranges(const msb_seqs *S, int64_t n_ranges, const int64_t *r_seq
     return MSB_OK;
 }
 
+// `before_range(k)`: called on the host right before the prefilter launches of range k are enqueued
+// (msb_scan_ascii makes the stream wait for that slice's bytes and encodes them there).
+typedef std::function<int(size_t)> RangeHook;
+
 static int scan_device(msb_ctx *ctx, msb_motifs *M, const msb_seqs *S, int strand, int flags,
-                       const RangeList *ranges = nullptr) {
+                       const RangeList *ranges = nullptr, const RangeHook *before_range = nullptr) {
     if (!ctx || !M || !S) { set_error("msb_scan: null argument"); return MSB_EINVAL; }
     if (strand < 1 || strand > 3) { set_error("msb_scan: strand must be 1, 2 or 3"); return MSB_EINVAL; }
     if (M->ctx != ctx || S->ctx != ctx) { set_error("msb_scan: motifs/seqs belong to another context"); return MSB_EINVAL; }
@@ -1131,7 +1140,9 @@ static int scan_device(msb_ctx *ctx, msb_motifs *M, const msb_seqs *S, int stran
             }
             const size_t smem = kTcSmemBytes;  // > half an SM's shared memory: one CTA per SM, which owns the TMEM
             unsigned grid = 1;
-            for (auto &r : *ranges) {
+            for (size_t ri = 0; ri < ranges->size(); ri++) {
+                const auto &r = (*ranges)[ri];
+                if (before_range) MSB_TRY((*before_range)(ri));
                 P.pos_lo = r.first;
                 P.pos_hi = r.second;
                 const int64_t n_ptiles = (r.second + kTcTileBases - 1) / kTcTileBases - r.first / kTcTileBases;
@@ -1399,6 +1410,93 @@ int msb_scan_ranges(msb_ctx *ctx, const msb_motifs *M, const msb_seqs *S, int st
     return collect_result(ctx, M, out);
 }
 
+int msb_scan_ascii(msb_ctx *ctx, const msb_motifs *M, int64_t n_seqs, const char *bytes, const int64_t *seq_off,
+                   int strand, int flags, msb_seqs **seqs_out, msb_result **out) {
+    if (!ctx || !M || !out || n_seqs < 0 || !seq_off || (seq_off[n_seqs] > 0 && !bytes)) {
+        set_error("msb_scan_ascii: bad argument");
+        return MSB_EINVAL;
+    }
+    *out = nullptr;
+    if (seqs_out) *seqs_out = nullptr;
+    if (seq_off[0] != 0) { set_error("seq_off[0] must be 0"); return MSB_EINVAL; }
+    for (int64_t i = 0; i < n_seqs; i++) {
+        const int64_t len = seq_off[i + 1] - seq_off[i];
+        if (len < 0 || len > (int64_t) 0x7fffffff - 64) {
+            set_error("msb_scan_ascii: sequence offsets not ascending or sequence >= 2^31 bases");
+            return MSB_EINVAL;
+        }
+    }
+    MSB_CUDA(cudaSetDevice(ctx->device));
+    const int64_t total_bp = seq_off[n_seqs];
+    // Small inputs, the table prefilter (no range launches) and an unusable copy stream take the plain path.
+    const int kSlices = 4;
+    bool sliced = g_prefilter_tc != 0 && total_bp >= (8 << 20) && n_seqs >= kSlices;
+    if (sliced && !ctx->copy_stream) {
+        if (cudaStreamCreateWithFlags(&ctx->copy_stream, cudaStreamNonBlocking) != cudaSuccess) { cudaGetLastError(); sliced = false; }
+        for (auto &evt : ctx->slice_ev)
+            if (sliced && cudaEventCreateWithFlags(&evt, cudaEventDisableTiming) != cudaSuccess) { cudaGetLastError(); sliced = false; }
+    }
+    msb_seqs *S = nullptr;
+    int rc = MSB_OK;
+    if (!sliced) {
+        MSB_TRY(msb_seqs_from_ascii(ctx, n_seqs, bytes, seq_off, &S));
+        rc = msb_scan_ex(ctx, M, S, strand, flags, out);
+    } else {
+        cudaStream_t st = ctx->stream;
+        MSB_CUDA(cudaEventRecord(ctx->ev[6], st));
+        std::vector<int32_t> lens;
+        MSB_TRY(seqs_prepare(ctx, n_seqs, seq_off, &S, lens));
+        rc = ctx->ascii.ensure((size_t) total_bp);
+        // slices of whole sequences with about the same number of bytes
+        int64_t cut[kSlices + 1];
+        cut[0] = 0;
+        for (int k = 1; k <= kSlices; k++) {
+            const int64_t want = total_bp * k / kSlices;
+            cut[k] = k == kSlices ? n_seqs : std::lower_bound(seq_off + cut[k - 1], seq_off + n_seqs, want) - seq_off;
+        }
+        RangeList ranges;
+        std::vector<int> slice_of;
+        cudaError_t e = cudaEventRecord(ctx->slice_ev[kSlices], st);   // the tables of seqs_prepare are on their way
+        if (e == cudaSuccess) e = cudaStreamWaitEvent(ctx->copy_stream, ctx->slice_ev[kSlices], 0);
+        for (int k = 0; k < kSlices && e == cudaSuccess && rc == MSB_OK; k++) {
+            const int64_t a = seq_off[cut[k]], b = seq_off[cut[k + 1]];
+            if (b > a) e = cudaMemcpyAsync((char *) ctx->ascii.p + a, bytes + a, (size_t) (b - a), cudaMemcpyHostToDevice, ctx->copy_stream);
+            if (e == cudaSuccess) e = cudaEventRecord(ctx->slice_ev[k], ctx->copy_stream);
+            if (S->poff[cut[k + 1]] > S->poff[cut[k]]) {
+                ranges.push_back({S->poff[cut[k]], S->poff[cut[k + 1]]});
+                slice_of.push_back(k);
+            }
+        }
+        if (rc == MSB_OK && e != cudaSuccess) rc = cuda_fail(e, "msb_scan_ascii H2D", __FILE__, __LINE__);
+        std::vector<char> encoded(kSlices, 0);
+        RangeHook hook = [&](size_t ri) -> int {
+            const int k = slice_of[ri];
+            if (encoded[k]) return MSB_OK;   // a retry after a buffer overflow: the codes are already there
+            MSB_CUDA(cudaStreamWaitEvent(st, ctx->slice_ev[k], 0));
+            const int64_t b0 = ranges[ri].first / kPadBases, b1 = ranges[ri].second / kPadBases;
+            encode_pack_kernel<<<(unsigned) ((b1 - b0 + 255) / 256), 256, 0, st>>>(
+                ctx->ascii.as<uint8_t>(), S->d_seq_off.as<int64_t>(), S->d_poff.as<int64_t>(), S->d_len.as<int32_t>(),
+                n_seqs, b0, b1, S->d_codes.as<uint32_t>(), S->d_nmask.as<uint32_t>(), S->d_blk_seq.as<int32_t>());
+            MSB_CUDA(cudaGetLastError());
+            encoded[k] = 1;
+            return MSB_OK;
+        };
+        if (rc == MSB_OK) rc = scan_device(ctx, const_cast<msb_motifs *>(M), S, strand, flags, &ranges, &hook);
+        if (rc == MSB_OK) rc = collect_result(ctx, M, out);
+        cudaStreamSynchronize(ctx->copy_stream);   // `bytes` may go away after return, also on failure
+        cudaStreamSynchronize(st);
+        ctx->t[MSB_T_H2D] = 0;                      // hidden behind the scan; not separable
+        ctx->t[MSB_T_ENCODE] = 0;
+    }
+    if (rc != MSB_OK) {
+        if (*out) { msb_result_destroy(*out); *out = nullptr; }
+        msb_seqs_destroy(S);
+        return rc;
+    }
+    if (seqs_out) *seqs_out = S; else msb_seqs_destroy(S);
+    return MSB_OK;
+}
+
 int msb_scan_ex(msb_ctx *ctx, const msb_motifs *M, const msb_seqs *S, int strand, int flags, msb_result **out) {
     if (!out) { set_error("msb_scan: null out"); return MSB_EINVAL; }
     *out = nullptr;
@@ -1588,8 +1686,7 @@ int msb_c_scan_motif(int device, int32_t n_motifs, const int32_t *lens, const do
     msb_motifs *M = nullptr;
     msb_seqs *S = nullptr;
     int rc = msb_motifs_create(ctx, n_motifs, lens, mats, mat_off, cutoffs, &M);
-    if (rc == MSB_OK) rc = msb_seqs_from_ascii(ctx, n_seqs, seq_bytes, seq_off, &S);
-    if (rc == MSB_OK) rc = msb_scan(ctx, M, S, strand, out);
+    if (rc == MSB_OK) rc = msb_scan_ascii(ctx, M, n_seqs, seq_bytes, seq_off, strand, 0, nullptr, out);
     msb_seqs_destroy(S);
     msb_motifs_destroy(M);
     return rc;

@@ -239,6 +239,41 @@ def scan(ctx, motifs, seqs, strand, remove_dup=False):
     return ScanResult(ctx, h, motifs.n)
 
 
+def scan_ascii(ctx, motifs, blob, seq_off, strand, remove_dup=False):
+    """Host ASCII in, host sites out in one call (msb_scan_ascii): the upload of the sequence bytes
+    is cut into slices that overlap with the scan.  `blob` should live in pinned memory
+    (`pinned_array`) for the overlap to happen; any uint8 array works."""
+    blob = np.ascontiguousarray(blob, dtype=np.uint8) if not isinstance(blob, np.ndarray) else blob
+    seq_off = np.ascontiguousarray(seq_off, dtype=np.int64)
+    h = ctypes.c_void_p()
+    flags = _lib.MSB_SCAN_DEDUP if remove_dup else 0
+    data = blob.ctypes.data if blob.size else None
+    check(ctx._lib.msb_scan_ascii(ctx._h, motifs._h, len(seq_off) - 1, ctypes.c_void_p(data), ptr(seq_off, ctypes.c_int64),
+                                  int(strand), flags, None, ctypes.byref(h)))
+    return ScanResult(ctx, h, motifs.n)
+
+
+class PinnedArray:
+    """A uint8 numpy view of page-locked host memory (msb_pinned_alloc); `.array` is the view."""
+
+    def __init__(self, nbytes):
+        self._lib = _lib.load()
+        self._p = ctypes.c_void_p()
+        check(self._lib.msb_pinned_alloc(int(nbytes), ctypes.byref(self._p)))
+        self.array = np.ctypeslib.as_array(ctypes.cast(self._p, ctypes.POINTER(ctypes.c_uint8)), shape=(max(int(nbytes), 1),))[:int(nbytes)]
+
+    def close(self):
+        if self._p:
+            self._lib.msb_pinned_free(self._p)
+            self._p = ctypes.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
 def scan_device(ctx, motifs, seqs, strand, remove_dup=False):
     """Kernels only (results stay on the device); returns the number of sites."""
     n = ctypes.c_int64(0)

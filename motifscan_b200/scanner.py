@@ -105,13 +105,13 @@ class Scanner:
         try:
             if self._resident is not None:
                 sset = self._resident.extract(self._chroms, self.seq_starts, self.seq_ends)
+                try:
+                    res = engine.scan(ctx, motifs, sset, _STRAND_ARG[self.strand], remove_dup=self.remove_dup)
+                finally:
+                    sset.close()
             else:
                 blob, off = self._flat()
-                sset = engine.SequenceSet(ctx, blob=blob, seq_off=off)
-            try:
-                res = engine.scan(ctx, motifs, sset, _STRAND_ARG[self.strand], remove_dup=self.remove_dup)
-            finally:
-                sset.close()
+                res = engine.scan_ascii(ctx, motifs, blob, off, _STRAND_ARG[self.strand], remove_dup=self.remove_dup)
         finally:
             motifs.close()
         return MotifSites(res.detach(), len(matrices), self.seq_starts, lengths)

@@ -353,3 +353,36 @@ def test_score_select_matches_sorted_order_statistics(eng):
     want = np.sort(want, axis=1)[:, ::-1][:, ranks]
     assert np.array_equal(got.view(np.uint64), np.ascontiguousarray(want).view(np.uint64))
     sset.close(), motifs.close()
+
+
+def test_scan_ascii_sliced_upload_equals_two_step_scan(eng):
+    """msb_scan_ascii (upload cut into slices that overlap the scan; >= 8 MB takes the sliced path)
+    == msb_seqs_from_ascii + msb_scan, from pinned and from pageable memory, with and without
+    de-duplication; ragged sequences so that slice boundaries fall at odd packed positions."""
+    rng = np.random.default_rng(77)
+    pwms = synth_pwms(rng, 24)
+    seqs = synth_seqs(rng, 6000, 900, 2100, p_n=0.0005, n_blocks=True)
+    seqs += ["", "ACGT", "N" * 50]
+    cutoffs = cutoffs_for(pwms, seqs, 2e-4)
+    from motifscan_b200 import _lib
+    blob, off = _lib.flatten_seqs(seqs)
+    assert blob.size >= (8 << 20)
+    ctx = eng.default_context(0)
+    motifs = eng.MotifSet(ctx, pwms, cutoffs)
+    sset = eng.SequenceSet(ctx, blob=blob, seq_off=off)
+    pinned = eng.PinnedArray(blob.size)
+    pinned.array[:] = blob
+    for dedup in (False, True):
+        want = eng.scan(ctx, motifs, sset, 3, remove_dup=dedup)
+        for src in (pinned.array, blob):
+            got = eng.scan_ascii(ctx, motifs, src, off, 3, remove_dup=dedup)
+            assert got.n_sites == want.n_sites > 1000
+            assert np.array_equal(got.counts, want.counts) and np.array_equal(got.seq_idx, want.seq_idx)
+            assert np.array_equal(got.start, want.start) and np.array_equal(got.strand, want.strand)
+            assert np.array_equal(got.score.view(np.uint64), want.score.view(np.uint64))
+            got.close()
+        want.close()
+    small = eng.scan_ascii(ctx, motifs, blob[:off[40]], off[:41], 3)     # below the slicing threshold
+    ref = oracle.scan_arrays(pwms, cutoffs, seqs[:40], 3, n_threads=4)
+    assert_scan_equal(small, ref)
+    small.close(), pinned.close(), sset.close(), motifs.close()
