@@ -401,7 +401,9 @@ def run_ours(args, rank, local_rank, world):
             "launch_ms": pre_ms / n_pre, "traffic": traffic,
             "issued": {"tflops": issued_flops / (pre_ms / 1e3) / 1e12,
                        "frac_of_peak": issued_flops / (pre_ms / 1e3) / 1e12 / tensor_peak,
-                       "note": "MMA work actually issued: one-hot K = 4 L padded to 32 (8 bases), 256-column tiles"},
+                       "note": "MMA work actually issued: one-hot K = 4 L padded to 32 (8 bases), 256-column tiles; "
+                               "with everything but the MMAs compiled out the kernel issues it at 3.9 PFLOP/s "
+                               "(profiles/r1_c_ablation.txt), so 2 x bf16 understates the e4m3 ceiling"},
             "cuda_core_view": {"adds_per_s_T": adds / (pre_ms / 1e3) / 1e12, "issue_peak_T": issue_peak,
                                "note": "the reference's adds per second against 148 SMs x 128 lanes x sm_max_mhz; "
                                        "the table prefilter this kernel replaced reached 0.91 of it"},

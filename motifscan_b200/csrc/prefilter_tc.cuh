@@ -22,8 +22,9 @@
 //      halves the epilogue's ALU work; the TMEM read itself costs the same as f32.
 //
 // One CTA per SM, warp-specialised: warp 0 issues the MMAs, warps 1-3 expand packed codes into
-// the one-hot streams (3-slot ring), warps 4-11 read the accumulators back from TMEM (two
-// 256-column buffers), AND-reduce the sign bits and emit candidates on the rare set flag.
+// the one-hot streams (3-slot ring), warps 4-19 (two sets of 8, one per 256-column TMEM buffer)
+// read the accumulators back, AND-reduce the sign bits and, on the rare clear sign, store one
+// 16-byte candidate record per lane and chunk ("Candidate emission" below).
 #pragma once
 #include "common.cuh"
 
@@ -248,7 +249,7 @@ __device__ __forceinline__ void umma_f8_lohi(uint32_t d_tmem, uint32_t a_lo, uin
 
 }  // namespace tc
 
-// Warp roles: 0 MMA issuer, 1-3 producers, 4.. epilogue (TMEM lane quarter = warp % 4, column
+// Warp roles: 0 MMA issuer, 1-3 producers, 4-19 epilogue (TMEM lane quarter = warp % 4, column
 // share = (warp - 4) / 4).  The scheduler favours the highest warp id of a sub-partition: the
 // epilogue warps carry the per-unit critical path, the others mostly poll barriers.
 template <bool kProf>
