@@ -287,6 +287,7 @@ struct ExactParams {
     SeqView seq;
     MotifView mot;
     int strand;
+    int key_shift;        // make_site_key's motif shift for this sequence set
     uint64_t *hit_key;    // motif id in the motif field
     double *hit_score;
     int64_t hit_cap;
@@ -314,7 +315,7 @@ __device__ __forceinline__ void test_and_emit(const ExactParams &E, uint32_t m, 
     if (__dsub_rn(score, __ldg(E.mot.cutoff + m)) >= -1e-10) {           // cscore.c:358,375
         unsigned long long slot = atomicAdd(E.counters + 2, 1ull);
         if ((int64_t) slot < E.hit_cap) {
-            E.hit_key[slot] = make_key(m, p, (uint32_t) rev);
+            E.hit_key[slot] = make_site_key(m, p, (uint32_t) rev, E.key_shift);
             E.hit_score[slot] = score;
         }
     }
@@ -522,13 +523,13 @@ exact_dirty_kernel(ExactParams E, const int64_t *__restrict__ pos, int64_t n_pos
 }
 
 __global__ void __launch_bounds__(256)
-decode_sites_kernel(SeqView S, const uint64_t *__restrict__ key, int64_t n,
+decode_sites_kernel(SeqView S, const uint64_t *__restrict__ key, int64_t n, int key_shift,
                     int32_t *__restrict__ seq_idx, int32_t *__restrict__ start,
                     int8_t *__restrict__ strand) {
     int64_t i = (int64_t) blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
     const uint64_t k = key[i];
-    const int64_t p = key_pos(k);
+    const int64_t p = site_pos(k, key_shift);
     const int64_t s = find_seq(S.poff, S.n_seqs, p);
     seq_idx[i] = (int32_t) s;
     start[i] = (int32_t) (p - __ldg(S.poff + s));
@@ -537,14 +538,14 @@ decode_sites_kernel(SeqView S, const uint64_t *__restrict__ key, int64_t n,
 
 // offsets[m] = first sorted site whose motif id is >= m  (m = 0..n_motifs): CSR over motifs.
 __global__ void __launch_bounds__(256)
-motif_offsets_kernel(const uint64_t *__restrict__ key, int64_t n, int32_t n_motifs,
+motif_offsets_kernel(const uint64_t *__restrict__ key, int64_t n, int32_t n_motifs, int key_shift,
                      int64_t *__restrict__ offsets) {
     const int32_t m = blockIdx.x * blockDim.x + threadIdx.x;
     if (m > n_motifs) return;
-    int64_t lo = 0, hi = n;  // first i with key_motif(key[i]) >= m
+    int64_t lo = 0, hi = n;  // first i with site_motif(key[i]) >= m
     while (lo < hi) {
         const int64_t mid = (lo + hi) >> 1;
-        if ((int64_t) key_motif(__ldg(key + mid)) < (int64_t) m) lo = mid + 1; else hi = mid;
+        if ((int64_t) site_motif(__ldg(key + mid), key_shift) < (int64_t) m) lo = mid + 1; else hi = mid;
     }
     offsets[m] = lo;
 }
@@ -561,15 +562,15 @@ motif_offsets_kernel(const uint64_t *__restrict__ key, int64_t n, int32_t n_moti
 __global__ void __launch_bounds__(256)
 dedup_flags_kernel(const uint64_t *__restrict__ key, const int32_t *__restrict__ seq_idx,
                    const int32_t *__restrict__ start, const int8_t *__restrict__ strand,
-                   const double *__restrict__ score, int64_t n, const int32_t *__restrict__ mlen,
+                   const double *__restrict__ score, int64_t n, const int32_t *__restrict__ mlen, int key_shift,
                    int32_t *__restrict__ keep) {
     const int64_t i = (int64_t) blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
-    const uint32_t m = key_motif(key[i]);
+    const uint32_t m = site_motif(key[i], key_shift);
     const int32_t s = seq_idx[i];
-    if (i > 0 && key_motif(key[i - 1]) == m && seq_idx[i - 1] == s) return;  // not a segment head
+    if (i > 0 && site_motif(key[i - 1], key_shift) == m && seq_idx[i - 1] == s) return;  // not a segment head
     int64_t e = i + 1;
-    while (e < n && key_motif(key[e]) == m && seq_idx[e] == s) e++;
+    while (e < n && site_motif(key[e], key_shift) == m && seq_idx[e] == s) e++;
     const int32_t L = __ldg(mlen + m);
     for (int8_t which = 1; which <= 2; which++) {
         int64_t cur = -1;

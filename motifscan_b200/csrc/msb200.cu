@@ -1032,6 +1032,7 @@ static int launch_positions(msb_ctx *ctx, const ExactParams &E, const int64_t *p
 
 static int g_prefilter_w = 4;   // windows per thread of the table prefilter (4 or 8)
 static int g_tc_prof = std::getenv("MSB_TC_PROF") ? 1 : 0;   // 1: print per-role cycle counters of the tensor-core prefilter to stderr
+static int g_ascii_slices = 4;       // msb_scan_ascii: upload slices (1..7)
 static int g_tc_first_lane_cap = 0;  // tests: records per lane buffer on the first attempt (0 = sized from the input)
 static int g_prefilter_tc = 1;  // 1: tensor-core prefilter (prefilter_tc.cuh), 0: shared-memory table prefilter
 
@@ -1096,6 +1097,11 @@ static int scan_device(msb_ctx *ctx, msb_motifs *M, const msb_seqs *S, int stran
     }
     const SeqView sv = S->view();
     const MotifView mv = M->view();
+    // site key = motif << key_shift | packed position << 1 | strand (make_site_key)
+    int pos_bits = 1, motif_bits = 1;
+    while ((1ll << pos_bits) < S->total_packed) pos_bits++;
+    while ((1ll << motif_bits) < (int64_t) M->n) motif_bits++;
+    const int key_shift = pos_bits + 1;
 
     // ---- stage 1: prefilter ------------------------------------------------------------------
     const double cells = (double) span * (double) std::max<int32_t>(n_fast, 1);
@@ -1244,6 +1250,7 @@ static int scan_device(msb_ctx *ctx, msb_motifs *M, const msb_seqs *S, int stran
         E.seq = sv;
         E.mot = mv;
         E.strand = strand;
+        E.key_shift = key_shift;
         E.hit_key = ctx->hit_key.as<uint64_t>();
         E.hit_score = ctx->hit_score.as<double>();
         E.hit_cap = hit_cap;
@@ -1288,9 +1295,7 @@ static int scan_device(msb_ctx *ctx, msb_motifs *M, const msb_seqs *S, int stran
         MSB_TRY(ctx->out_seq.ensure((size_t) n_hits * 4));
         MSB_TRY(ctx->out_start.ensure((size_t) n_hits * 4));
         MSB_TRY(ctx->out_strand.ensure((size_t) n_hits));
-        int motif_bits = 1;
-        while ((1ll << motif_bits) < (int64_t) M->n) motif_bits++;
-        const int end_bit = std::min(64, kMotifShift + motif_bits);
+        const int end_bit = key_shift + motif_bits;
         size_t tmp_bytes = 0;
         MSB_CUDA(cub::DeviceRadixSort::SortPairs(nullptr, tmp_bytes, ctx->hit_key.as<uint64_t>(), ctx->key_alt.as<uint64_t>(),
                                                  ctx->hit_score.as<double>(), ctx->score_alt.as<double>(), n_hits, 0, end_bit, st));
@@ -1298,7 +1303,7 @@ static int scan_device(msb_ctx *ctx, msb_motifs *M, const msb_seqs *S, int stran
         MSB_CUDA(cub::DeviceRadixSort::SortPairs(ctx->sort_tmp.p, tmp_bytes, ctx->hit_key.as<uint64_t>(), ctx->key_alt.as<uint64_t>(),
                                                  ctx->hit_score.as<double>(), ctx->score_alt.as<double>(), n_hits, 0, end_bit, st));
         const unsigned grid = (unsigned) ((n_hits + 255) / 256);
-        decode_sites_kernel<<<grid, 256, 0, st>>>(sv, ctx->key_alt.as<uint64_t>(), n_hits, ctx->out_seq.as<int32_t>(),
+        decode_sites_kernel<<<grid, 256, 0, st>>>(sv, ctx->key_alt.as<uint64_t>(), n_hits, key_shift, ctx->out_seq.as<int32_t>(),
                                                   ctx->out_start.as<int32_t>(), ctx->out_strand.as<int8_t>());
         MSB_CUDA(cudaGetLastError());
         ctx->c[MSB_C_LAUNCHES] += 2;  // sort (several CUB kernels, counted once) + decode
@@ -1315,7 +1320,7 @@ static int scan_device(msb_ctx *ctx, msb_motifs *M, const msb_seqs *S, int stran
             MSB_TRY(ctx->out2_start.ensure((size_t) n_hits * 4));
             MSB_TRY(ctx->out2_strand.ensure((size_t) n_hits));
             dedup_flags_kernel<<<grid, 256, 0, st>>>(ctx->fin_key, ctx->fin_seq, ctx->fin_start, ctx->fin_strand, ctx->fin_score,
-                                                     n_hits, mv.len, ctx->keep.as<int32_t>());
+                                                     n_hits, mv.len, key_shift, ctx->keep.as<int32_t>());
             MSB_CUDA(cudaGetLastError());
             size_t scan_bytes = 0;
             MSB_CUDA(cub::DeviceScan::ExclusiveSum(nullptr, scan_bytes, ctx->keep.as<int32_t>(), ctx->keep_pos.as<int64_t>(), n_hits, st));
@@ -1341,7 +1346,7 @@ static int scan_device(msb_ctx *ctx, msb_motifs *M, const msb_seqs *S, int stran
             ctx->fin_start = ctx->out2_start.as<int32_t>();
             ctx->fin_strand = ctx->out2_strand.as<int8_t>();
         }
-        motif_offsets_kernel<<<(unsigned) ((M->n + 1 + 255) / 256), 256, 0, st>>>(ctx->fin_key, n_final, M->n,
+        motif_offsets_kernel<<<(unsigned) ((M->n + 1 + 255) / 256), 256, 0, st>>>(ctx->fin_key, n_final, M->n, key_shift,
                                                                                   ctx->out_counts.as<int64_t>());
         MSB_CUDA(cudaGetLastError());
         ctx->c[MSB_C_LAUNCHES] += 1;
@@ -1365,6 +1370,7 @@ int msb_set_option(const char *name, int value) {
     if (name && !std::strcmp(name, "prefilter_tc") && (value == 0 || value == 1)) { g_prefilter_tc = value; return MSB_OK; }
     if (name && !std::strcmp(name, "tc_prof") && (value == 0 || value == 1)) { g_tc_prof = value; return MSB_OK; }
     if (name && !std::strcmp(name, "tc_first_lane_cap") && value >= 0) { g_tc_first_lane_cap = value; return MSB_OK; }
+    if (name && !std::strcmp(name, "ascii_slices") && value >= 1 && value <= 7) { g_ascii_slices = value; return MSB_OK; }
     set_error("msb_set_option: unknown option or value");
     return MSB_EINVAL;
 }
@@ -1429,7 +1435,7 @@ int msb_scan_ascii(msb_ctx *ctx, const msb_motifs *M, int64_t n_seqs, const char
     MSB_CUDA(cudaSetDevice(ctx->device));
     const int64_t total_bp = seq_off[n_seqs];
     // Small inputs, the table prefilter (no range launches) and an unusable copy stream take the plain path.
-    const int kSlices = 4;
+    const int kSlices = g_ascii_slices;
     bool sliced = g_prefilter_tc != 0 && total_bp >= (8 << 20) && n_seqs >= kSlices;
     if (sliced && !ctx->copy_stream) {
         if (cudaStreamCreateWithFlags(&ctx->copy_stream, cudaStreamNonBlocking) != cudaSuccess) { cudaGetLastError(); sliced = false; }
@@ -1448,7 +1454,7 @@ int msb_scan_ascii(msb_ctx *ctx, const msb_motifs *M, int64_t n_seqs, const char
         MSB_TRY(seqs_prepare(ctx, n_seqs, seq_off, &S, lens));
         rc = ctx->ascii.ensure((size_t) total_bp);
         // slices of whole sequences with about the same number of bytes
-        int64_t cut[kSlices + 1];
+        int64_t cut[8];
         cut[0] = 0;
         for (int k = 1; k <= kSlices; k++) {
             const int64_t want = total_bp * k / kSlices;
