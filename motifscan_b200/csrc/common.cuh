@@ -82,6 +82,8 @@ struct MotifView {
     const int32_t *len;      // [n_motifs]
     const double *cutoff;    // [n_motifs]
     const double *max_raw;   // [n_motifs]  cscore.c:36-48
+    const float *pwm32;      // the same matrices rounded to fp32, same layout (screening only)
+    const float *floor32;    // [n_motifs] an fp32-accumulated raw score below this cannot be a site
     int32_t n_motifs;
 };
 

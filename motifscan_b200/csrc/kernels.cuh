@@ -478,8 +478,9 @@ exact_positions_kernel(ExactParams E, const int64_t *__restrict__ pos, int64_t n
 // Dirty windows (they touch a non-ACGT base) x the prefilter-path motifs.  A warp takes 32 listed
 // positions (one per lane, the window's bases in registers) and a chunk of kDirtyMotifs motifs, and
 // walks the motifs together: the motif, its length and the column are warp-uniform, so the 32
-// lanes' PWM reads of one column fall into ONE 32-byte sector (the four rows of a column), instead
-// of 32 sectors when each lane scores a different motif.
+// lanes' PWM reads of one column fall into ONE sector (the four rows of a column), instead of 32
+// sectors when each lane scores a different motif.  Windows are screened in fp32 first; the few
+// that can reach the cutoff are re-scored with the reference's fp64 arithmetic.
 constexpr int kDirtyMotifs = 64;
 __global__ void __launch_bounds__(256)
 exact_dirty_kernel(ExactParams E, const int64_t *__restrict__ pos, int64_t n_pos,
@@ -506,19 +507,22 @@ exact_dirty_kernel(ExactParams E, const int64_t *__restrict__ pos, int64_t n_pos
     for (int32_t k = chunk * kDirtyMotifs; k < k_end; k++) {
         const uint32_t m = (uint32_t) __ldg(motif_ids + k);
         const int L = __ldg(E.mot.len + m);
-        const double *pw = E.mot.pwm + 4 * (int64_t) __ldg(E.mot.col_off + m);
-        // both strands in one pass over the columns: the same additions in the same order as
-        // exact_raw_w (ascending c, non-ACGT bases skipped), two independent chains
-        double f = 0.0, r = 0.0;
+        const int64_t col0 = 4 * (int64_t) __ldg(E.mot.col_off + m);
+        // fp32 screen of both strands (FP64 issues at a fraction of the FP32 rate and the division in
+        // test_and_emit is a subroutine): a score below floor32 cannot pass, see upload_floors
+        const float *pw32 = E.mot.pwm32 + col0;
+        const float floor32 = __ldg(E.mot.floor32 + m);
+        float f32 = 0.f, r32 = 0.f;
         for (int c = 0; c < L; c++) {
             if ((w.nmask >> c) & 1u) continue;
             const int row = (int) ((w.codes >> (2 * c)) & 3u);
-            if (E.strand & 1) f = __dadd_rn(f, __ldg(pw + 4 * c + row));
-            if (E.strand & 2) r = __dadd_rn(r, __ldg(pw + 4 * (L - 1 - c) + (3 - row)));
+            f32 += __ldg(pw32 + 4 * c + row);
+            r32 += __ldg(pw32 + 4 * (L - 1 - c) + (3 - row));
         }
         if (L > left) continue;   // cscore.c:337,340 (also lanes without a position: left = 0)
-        if (E.strand & 1) test_and_emit(E, m, p, 0, f);
-        if (E.strand & 2) test_and_emit(E, m, p, 1, r);
+        const double *pw = E.mot.pwm + col0;
+        if ((E.strand & 1) && !(f32 < floor32)) test_and_emit(E, m, p, 0, exact_raw_w(w, pw, L, 0));
+        if ((E.strand & 2) && !(r32 < floor32)) test_and_emit(E, m, p, 1, exact_raw_w(w, pw, L, 1));
     }
 }
 

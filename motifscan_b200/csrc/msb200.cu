@@ -126,7 +126,7 @@ struct msb_motifs {
     std::vector<double> cutoffs, max_raw;
     uint64_t cutoff_version = 1;
     int32_t lmax = 0;
-    DevBuf d_pwm, d_col_off, d_len, d_cutoff, d_max_raw;
+    DevBuf d_pwm, d_col_off, d_len, d_cutoff, d_max_raw, d_pwm32, d_floor32;
     TableSet tables[4];
     TcTableSet tc_tables[4];
     MotifView view() const {
@@ -136,6 +136,8 @@ struct msb_motifs {
         v.len = d_len.as<int32_t>();
         v.cutoff = d_cutoff.as<double>();
         v.max_raw = d_max_raw.as<double>();
+        v.pwm32 = d_pwm32.as<float>();
+        v.floor32 = d_floor32.as<float>();
         v.n_motifs = n;
         return v;
     }
@@ -349,6 +351,40 @@ int msb_ctx_counters(const msb_ctx *ctx, int64_t *v, int n) {
 }
 
 // ---- motifs ------------------------------------------------------------------------------------
+// fp32 screening threshold of every motif for the exact stage's dirty-window kernel: a window whose
+// raw score accumulated in fp32 from the fp32-rounded matrix is below floor32[m] cannot satisfy the
+// reference's predicate.  T is the conservative bound on the exact raw score that the prefilter
+// tables use (see "Prefilter tables" below); the fp32 path is off by at most
+// sum_c |v_c| 2^-24 (rounding the entries) + (L - 1) 2^-24 max|partial sum| <= L 2^-23 abs_sum, and
+// the margin taken here is 2^-17 (abs_sum + |T| + 1), 64 times that for L = 32.
+static int upload_floors(msb_motifs *M) {
+    std::vector<float> floors((size_t) std::max<int32_t>(M->n, 1), std::numeric_limits<float>::infinity());
+    for (int32_t m = 0; m < M->n; m++) {
+        const int L = M->lens[m];
+        const double max_raw = M->max_raw[m], cutoff = M->cutoffs[m];
+        if (L < 1 || !(max_raw > 0) || std::isnan(cutoff) || (std::isinf(cutoff) && cutoff > 0)) continue;   // never a site
+        if (std::isinf(cutoff)) { floors[m] = -std::numeric_limits<float>::infinity(); continue; }
+        const double *mat = M->mats.data() + M->mat_off[m];
+        double abs_sum = 0;
+        bool finite = true;
+        for (int c = 0; c < L; c++) {
+            double a = 0;
+            for (int r = 0; r < 4; r++) { a = std::max(a, std::fabs(mat[(size_t) r * L + c])); finite = finite && std::isfinite(mat[(size_t) r * L + c]); }
+            abs_sum += a;
+        }
+        if (!finite || abs_sum > 1e30) { floors[m] = -std::numeric_limits<float>::infinity(); continue; }   // no screening (fp32 would overflow; a NaN sum also passes the screen)
+        const double T = max_raw * (cutoff - 1e-10) - 1e-12 * (max_raw * (std::fabs(cutoff) + 1.0) + abs_sum);
+        const double f = T - std::ldexp(abs_sum + std::fabs(T) + 1.0, -17);
+        float ff = (float) f;
+        if ((double) ff > f) ff = std::nextafterf(ff, -std::numeric_limits<float>::infinity());
+        floors[m] = ff;
+    }
+    MSB_TRY(M->d_floor32.ensure(floors.size() * sizeof(float)));
+    MSB_CUDA(cudaMemcpyAsync(M->d_floor32.p, floors.data(), floors.size() * sizeof(float), cudaMemcpyHostToDevice, M->ctx->stream));
+    MSB_CUDA(cudaStreamSynchronize(M->ctx->stream));
+    return MSB_OK;
+}
+
 int msb_motifs_create(msb_ctx *ctx, int32_t n, const int32_t *lens, const double *mats,
                       const int64_t *mat_off, const double *cutoffs, msb_motifs **out) {
     if (!ctx || !out || n < 0 || (n > 0 && (!lens || !mats || !mat_off))) {
@@ -408,6 +444,9 @@ int msb_motifs_create(msb_ctx *ctx, int32_t n, const int32_t *lens, const double
         }
     };
     up(M->d_pwm, dev_pwm.data(), dev_pwm.size() * sizeof(double));
+    std::vector<float> dev_pwm32(dev_pwm.size());
+    for (size_t i = 0; i < dev_pwm.size(); i++) dev_pwm32[i] = (float) dev_pwm[i];
+    up(M->d_pwm32, dev_pwm32.data(), dev_pwm32.size() * sizeof(float));
     up(M->d_col_off, M->col_off.data(), M->col_off.size() * sizeof(int32_t));
     up(M->d_len, M->lens.data(), (size_t) n * sizeof(int32_t));
     up(M->d_cutoff, M->cutoffs.data(), (size_t) n * sizeof(double));
@@ -416,6 +455,7 @@ int msb_motifs_create(msb_ctx *ctx, int32_t n, const int32_t *lens, const double
         cudaError_t e = cudaStreamSynchronize(ctx->stream);
         if (e != cudaSuccess) rc = cuda_fail(e, "cudaStreamSynchronize", __FILE__, __LINE__);
     }
+    if (rc == MSB_OK) rc = upload_floors(M);
     if (rc != MSB_OK) { msb_motifs_destroy(M); return rc; }
     *out = M;
     return MSB_OK;
@@ -430,7 +470,7 @@ int msb_motifs_set_cutoffs(msb_motifs *M, const double *cutoffs) {
         MSB_CUDA(cudaMemcpyAsync(M->d_cutoff.p, M->cutoffs.data(), (size_t) M->n * sizeof(double),
                                  cudaMemcpyHostToDevice, M->ctx->stream));
     MSB_CUDA(cudaStreamSynchronize(M->ctx->stream));
-    return MSB_OK;
+    return upload_floors(M);
 }
 
 int msb_motifs_count(const msb_motifs *M, int32_t *n) {
@@ -447,7 +487,7 @@ int msb_motifs_destroy(msb_motifs *M) {
     if (!M) return MSB_OK;
     cudaSetDevice(M->ctx->device);
     cudaStreamSynchronize(M->ctx->stream);
-    for (DevBuf *b : {&M->d_pwm, &M->d_col_off, &M->d_len, &M->d_cutoff, &M->d_max_raw}) b->release();
+    for (DevBuf *b : {&M->d_pwm, &M->d_col_off, &M->d_len, &M->d_cutoff, &M->d_max_raw, &M->d_pwm32, &M->d_floor32}) b->release();
     for (auto &t : M->tables) { t.d_tab.release(); t.d_order.release(); t.d_slow.release(); }
     for (auto &t : M->tc_tables) {
         t.d_btab.release(); t.d_col_info.release(); t.d_len.release(); t.d_order.release(); t.d_slow.release();
