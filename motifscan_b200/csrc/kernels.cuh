@@ -424,21 +424,18 @@ __device__ __forceinline__ void exact_record(const ExactParams &E, const uint4 r
     const int64_t slen = __ldg(E.seq.len + s);
     if (E.seq.limit && j >= (int64_t) __ldg(E.seq.limit + s)) return;   // the next chunk owns this start
     const Window32 w = load_window32(E.seq, p);
-#pragma unroll 1
-    for (int half = 0; half < 2; half++) {
-        uint32_t bits = half ? r.w : r.z;
-        while (bits) {
-            const int b = __ffs(bits) - 1;   // bit 8 q + k <=> column 32 half + 4 k + q
-            bits &= bits - 1;
-            const uint32_t info = __ldg(col_info + col0 + 32 * half + 4 * (b & 7) + (b >> 3));
-            if (info == 0xffffffffu) continue;   // padding column of a tile
-            const uint32_t m = (uint32_t) __ldg(order + (info >> 1));
-            const int rev = (int) (info & 1u);
-            const int L = __ldg(E.mot.len + m);
-            if (j + L > slen) continue;   // cscore.c:340
-            const double *pw = E.mot.pwm + 4 * (int64_t) __ldg(E.mot.col_off + m);
-            test_and_emit(E, m, p, rev, exact_raw_w(w, pw, L, rev));   // prefilter motifs have L <= 32
-        }
+    unsigned long long bits = ((unsigned long long) r.w << 32) | r.z;   // one flat loop: less divergence than word by word
+    while (bits) {
+        const int i = __ffsll((long long) bits) - 1;   // bit 32 h + 8 q + k <=> column 32 h + 4 k + q
+        bits &= bits - 1;
+        const uint32_t info = __ldg(col_info + col0 + (i & 32) + 4 * (i & 7) + ((i >> 3) & 3));
+        if (info == 0xffffffffu) continue;   // padding column of a tile
+        const uint32_t m = (uint32_t) __ldg(order + (info >> 1));
+        const int rev = (int) (info & 1u);
+        const int L = __ldg(E.mot.len + m);
+        if (j + L > slen) continue;   // cscore.c:340
+        const double *pw = E.mot.pwm + 4 * (int64_t) __ldg(E.mot.col_off + m);
+        test_and_emit(E, m, p, rev, exact_raw_w(w, pw, L, rev));   // prefilter motifs have L <= 32
     }
 }
 

@@ -30,7 +30,8 @@
 
 // Compile-time experiment switch (bench_micro/tc_ablate.sh builds one library per value; results in
 // profiles/): 0 = product, 1 = no candidate emission, 2 = no accumulator scan either, 3 = no TMEM
-// read-back either (tensor pipe alone).  Anything but 0 gives wrong results by design.
+// read-back either (tensor pipe alone), 8 = records stored without computing the flag words,
+// 9 = flag words computed but nothing stored.  Anything but 0 gives wrong results by design.
 #ifndef MSB_TC_EXP
 #define MSB_TC_EXP 0
 #endif
@@ -196,13 +197,21 @@ struct LaneOut {
 __device__ __forceinline__ void scan_chunk(const TcParams &P, LaneOut &out, const uint32_t (&r)[32], bool live,
                                            uint32_t col0, int64_t p) {
     constexpr uint32_t M = 0x80008000u;
-    const uint32_t g = and8(r, 0) & and8(r, 1) & and8(r, 2) & and8(r, 3);
-    bool hit = live && (g & M) != M;
+    const uint32_t g_lo = and8(r, 0) & and8(r, 1), g_hi = and8(r, 2) & and8(r, 3);
+    bool hit = live && ((g_lo & g_hi) & M) != M;
 #if MSB_TC_EXP >= 1 && MSB_TC_EXP <= 3
     hit = false;
 #endif
-    if (hit) {   // divergent, rare
-        const uint32_t z = flag_word(r, 0), w = flag_word(r, 1);
+    if (hit) {   // divergent, rare; usually one lane and one half: only that half's flag word is computed
+        uint32_t z = 0, w = 0;
+#if MSB_TC_EXP != 8
+        if ((g_lo & M) != M) z = flag_word(r, 0);
+        if ((g_hi & M) != M) w = flag_word(r, 1);
+#endif
+#if MSB_TC_EXP == 9
+        out.n += (z ^ w) & 1u;   // ablation: flags computed, nothing stored
+        return;
+#endif
         if ((int64_t) out.n < P.cand_cap)
             st_global_v4(out.buf + out.n, (uint32_t) p, (uint32_t) ((uint64_t) p >> 32) | (col0 << 9), z, w);
         out.n++;
