@@ -56,29 +56,90 @@ def load_peaks():
 
 
 class ClockSampler:
-    """nvidia-smi clocks / throttle reasons sampled every 200 ms during the timed region."""
+    """SM clock, power and throttle reasons of one GPU sampled through NVML every ~2 ms on a thread for
+    the whole timed region (a run is ~0.1 s: nvidia-smi's own loop would return one sample); falls
+    back to `nvidia-smi -lms` when the NVML binding is missing."""
     FIELDS = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
               "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
               "clocks_event_reasons.sw_power_cap")
 
-    def __init__(self, index):
+    def __init__(self, index, uuid=None):
         self.index = index
+        self.uuid = uuid
         self.proc = None
         self.path = None
+        self.thread = None
+        self.stop_flag = threading.Event()
+        self.samples = []          # (sm_mhz, power_w, reasons bitmask)
+        self.max_mhz = None
+        self.nvml = None
+
+    def _nvml_loop(self, handle):
+        nv = self.nvml
+        get_reasons = getattr(nv, "nvmlDeviceGetCurrentClocksEventReasons", None) or nv.nvmlDeviceGetCurrentClocksThrottleReasons
+        while not self.stop_flag.is_set():
+            try:
+                self.samples.append((nv.nvmlDeviceGetClockInfo(handle, nv.NVML_CLOCK_SM),
+                                     nv.nvmlDeviceGetPowerUsage(handle) / 1e3, int(get_reasons(handle))))
+            except Exception:
+                break
+            time.sleep(0.002)
 
     def start(self):
+        try:
+            import pynvml as nv
+            nv.nvmlInit()
+            handle = None
+            if self.uuid:   # CUDA_VISIBLE_DEVICES may renumber the devices: find ours by UUID
+                name = self.uuid if str(self.uuid).startswith("GPU-") else f"GPU-{self.uuid}"
+                for cand in (name, name.encode()):
+                    try:
+                        handle = nv.nvmlDeviceGetHandleByUUID(cand)
+                        break
+                    except Exception:
+                        handle = None
+            if handle is None:
+                handle = nv.nvmlDeviceGetHandleByIndex(self.index)
+            self.nvml = nv
+            self.max_mhz = nv.nvmlDeviceGetMaxClockInfo(handle, nv.NVML_CLOCK_SM)
+            self.thread = threading.Thread(target=self._nvml_loop, args=(handle,), daemon=True)
+            self.thread.start()
+            return
+        except Exception:
+            self.nvml = None
         try:
             fd, self.path = tempfile.mkstemp(suffix=".csv")
             os.close(fd)
             self.proc = subprocess.Popen(
                 ["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.FIELDS}",
-                 "--format=csv,noheader,nounits", "-lms", "200"],
+                 "--format=csv,noheader,nounits", "-lms", "20"],
                 stdout=open(self.path, "w"), stderr=subprocess.DEVNULL)
         except Exception:
             self.proc = None
 
     def stop(self):
         out = {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
+        if self.thread is not None:
+            self.stop_flag.set()
+            self.thread.join(timeout=2)
+            nv = self.nvml
+            names = {"hw_slowdown": "HwSlowdown", "hw_thermal_slowdown": "HwThermalSlowdown",
+                     "sw_thermal_slowdown": "SwThermalSlowdown", "sw_power_cap": "SwPowerCap"}
+            bits = {}
+            for key, suffix in names.items():
+                for prefix in ("nvmlClocksEventReason", "nvmlClocksThrottleReason"):
+                    if hasattr(nv, prefix + suffix):
+                        bits[key] = getattr(nv, prefix + suffix)
+                        break
+            if self.samples:
+                mask = 0
+                for _, _, r in self.samples:
+                    mask |= r
+                out.update(sm_mhz=statistics.median(x[0] for x in self.samples), sm_max_mhz=self.max_mhz,
+                           sm_min_mhz=min(x[0] for x in self.samples), power_w_max=max(x[1] for x in self.samples),
+                           reasons=sorted(k for k, b in bits.items() if mask & b), samples=len(self.samples),
+                           source="NVML, 2 ms period")
+            return out
         if self.proc is None:
             return out
         self.proc.terminate()
@@ -106,7 +167,7 @@ class ClockSampler:
             pass
         if sm:
             out.update(sm_mhz=statistics.median(sm), sm_max_mhz=max(mx), reasons=sorted(reasons),
-                       samples=len(sm))
+                       samples=len(sm), source="nvidia-smi -lms 20")
         return out
 
 
@@ -321,7 +382,11 @@ def run_ours(args, rank, local_rank, world):
     n_sites = 0
     for _ in range(args.warmup):
         n_sites = engine.scan_device(ctx, motifs, resident, 3)
-    sampler = ClockSampler(local_rank)
+    try:
+        gpu_uuid = str(torch.cuda.get_device_properties(local_rank).uuid)
+    except Exception:
+        gpu_uuid = None
+    sampler = ClockSampler(local_rank, gpu_uuid)
     step_ms, phase = [], {"prefilter": [], "exact": [], "order": []}
     launches = 0
     barrier()
