@@ -146,6 +146,10 @@ int msb_scan_device(msb_ctx *ctx, const msb_motifs *motifs, const msb_seqs *seqs
 /* Per-motif site counts of the last msb_scan_device on this context (n_motifs entries): the only
  * thing a counts-only genome-wide scan copies back. */
 int msb_scan_device_counts(msb_ctx *ctx, int64_t *counts, int32_t n_motifs);
+/* Per motif, the number of sequences with at least one site in the last msb_scan_device /
+ * msb_scan_ranges_device on this context: the only thing motif_enrichment needs from a scan
+ * (stats.py:29-31 counts the regions whose site list is non-empty), reduced on the device. */
+int msb_scan_device_region_counts(msb_ctx *ctx, int64_t *counts, int32_t n_motifs);
 int msb_result_total(const msb_result *res, int64_t *n_sites);
 int msb_result_counts(const msb_result *res, int64_t *counts /* n_motifs */);
 /* Borrowed pointers into the result (valid until msb_result_destroy): n_sites entries each. */

@@ -59,6 +59,7 @@ SIGNATURES = {
                                               c_i64p, c_i64p, c_i64p]),
     "msb_scan_device": (ctypes.c_int, [c_vp, c_vp, c_vp, ctypes.c_int, ctypes.c_int, c_i64p]),
     "msb_scan_device_counts": (ctypes.c_int, [c_vp, c_i64p, ctypes.c_int32]),
+    "msb_scan_device_region_counts": (ctypes.c_int, [c_vp, c_i64p, ctypes.c_int32]),
     "msb_result_total": (ctypes.c_int, [c_vp, c_i64p]),
     "msb_result_counts": (ctypes.c_int, [c_vp, c_i64p]),
     "msb_result_arrays": (ctypes.c_int, [c_vp, ctypes.POINTER(c_i32p), ctypes.POINTER(c_i32p),

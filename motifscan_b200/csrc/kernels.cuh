@@ -551,6 +551,18 @@ motif_offsets_kernel(const uint64_t *__restrict__ key, int64_t n, int32_t n_moti
     offsets[m] = lo;
 }
 
+// Per motif, the number of sequences with at least one site (what motif_enrichment counts,
+// stats.py:29-31), from the sorted site list: a site opens a new (motif, sequence) cell if it is the
+// first of its motif or its sequence differs from the previous site's.
+__global__ void __launch_bounds__(256)
+region_counts_kernel(const uint64_t *__restrict__ key, const int32_t *__restrict__ seq_idx, int64_t n,
+                     int key_shift, unsigned long long *__restrict__ out) {
+    const int64_t i = (int64_t) blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const uint32_t m = site_motif(key[i], key_shift);
+    if (i == 0 || site_motif(key[i - 1], key_shift) != m || seq_idx[i - 1] != seq_idx[i]) atomicAdd(out + m, 1ull);
+}
+
 // ---------------------------------------------------------------------------------------------
 // De-duplication of adjacent sites (scanner.py:156-193), on the sorted site list.
 // Per (motif, sequence) segment and per strand separately, walking sites by ascending start with

@@ -90,6 +90,7 @@ struct msb_ctx {
     // results of the last msb_scan_device, still on the device
     int64_t last_sites = 0;
     int32_t last_n_motifs = 0;
+    int last_key_shift = 0;
 };
 
 struct TableSet {
@@ -1142,6 +1143,7 @@ static int scan_device(msb_ctx *ctx, msb_motifs *M, const msb_seqs *S, int stran
     while ((1ll << pos_bits) < S->total_packed) pos_bits++;
     while ((1ll << motif_bits) < (int64_t) M->n) motif_bits++;
     const int key_shift = pos_bits + 1;
+    ctx->last_key_shift = key_shift;
 
     // ---- stage 1: prefilter ------------------------------------------------------------------
     const double cells = (double) span * (double) std::max<int32_t>(n_fast, 1);
@@ -1431,6 +1433,24 @@ int msb_scan_device_counts(msb_ctx *ctx, int64_t *counts, int32_t n_motifs) {
         MSB_CUDA(cudaMemcpyAsync(offsets.data(), ctx->out_counts.p, offsets.size() * 8, cudaMemcpyDeviceToHost, ctx->stream));
     MSB_CUDA(cudaStreamSynchronize(ctx->stream));
     for (int32_t m = 0; m < n_motifs; m++) counts[m] = offsets[m + 1] - offsets[m];
+    return MSB_OK;
+}
+
+int msb_scan_device_region_counts(msb_ctx *ctx, int64_t *counts, int32_t n_motifs) {
+    if (!ctx || (!counts && n_motifs)) { set_error("msb_scan_device_region_counts: null"); return MSB_EINVAL; }
+    if (n_motifs != ctx->last_n_motifs) { set_error("msb_scan_device_region_counts: no scan with that many motifs"); return MSB_EINVAL; }
+    if (n_motifs == 0) return MSB_OK;
+    MSB_CUDA(cudaSetDevice(ctx->device));
+    std::fill(counts, counts + n_motifs, (int64_t) 0);
+    if (ctx->last_sites == 0) return MSB_OK;
+    cudaStream_t st = ctx->stream;
+    MSB_TRY(ctx->sel.ensure((size_t) n_motifs * 8));
+    MSB_CUDA(cudaMemsetAsync(ctx->sel.p, 0, (size_t) n_motifs * 8, st));
+    region_counts_kernel<<<(unsigned) ((ctx->last_sites + 255) / 256), 256, 0, st>>>(
+        ctx->fin_key, ctx->fin_seq, ctx->last_sites, ctx->last_key_shift, ctx->sel.as<unsigned long long>());
+    MSB_CUDA(cudaGetLastError());
+    MSB_CUDA(cudaMemcpyAsync(counts, ctx->sel.p, (size_t) n_motifs * 8, cudaMemcpyDeviceToHost, st));
+    MSB_CUDA(cudaStreamSynchronize(st));
     return MSB_OK;
 }
 

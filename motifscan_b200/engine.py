@@ -50,6 +50,13 @@ class Context:
         check(self._lib.msb_scan_device_counts(self._h, ptr(out, ctypes.c_int64), int(n_motifs)))
         return out[:n_motifs]
 
+    def region_counts(self, n_motifs):
+        """Per motif, the number of sequences with at least one site in the last `scan_device` on this
+        context (what stats.motif_enrichment counts), reduced on the device."""
+        out = np.zeros(max(n_motifs, 1), dtype=np.int64)
+        check(self._lib.msb_scan_device_region_counts(self._h, ptr(out, ctypes.c_int64), int(n_motifs)))
+        return out[:n_motifs]
+
     def counters(self):
         a = np.zeros(len(_lib.C_NAMES), dtype=np.int64)
         check(self._lib.msb_ctx_counters(self._h, ptr(a, ctypes.c_int64), len(a)))

@@ -197,10 +197,18 @@ class MotifSites:
     def regions_with_sites(self):
         """Per motif, the number of regions with at least one site (stats.py:29-31)."""
         out = np.zeros(self.n_pwms, dtype=np.int64)
-        for m in range(self.n_pwms):
-            seq = self._seq_idx[self._off[m]:self._off[m + 1]]
-            if len(seq):
-                out[m] = 1 + np.count_nonzero(np.diff(seq))
+        seq = self._seq_idx
+        if len(seq) == 0:
+            return out
+        # a site opens a new (motif, region) cell if it is the first of its motif or its region differs
+        # from the previous site's; cells per motif = segment sums (sites are sorted by motif, region)
+        first = np.empty(len(seq), dtype=bool)
+        first[0] = True
+        np.not_equal(seq[1:], seq[:-1], out=first[1:])
+        nonempty = np.flatnonzero(np.diff(self._off) > 0)
+        starts = np.asarray(self._off)[nonempty]
+        first[starts] = True
+        out[nonempty] = np.add.reduceat(first, starts, dtype=np.int64)
         return out
 
 
