@@ -1513,11 +1513,12 @@ int msb_scan_ascii(msb_ctx *ctx, const msb_motifs *M, int64_t n_seqs, const char
         std::vector<int32_t> lens;
         MSB_TRY(seqs_prepare(ctx, n_seqs, seq_off, &S, lens));
         rc = ctx->ascii.ensure((size_t) total_bp);
-        // slices of whole sequences with about the same number of bytes
+        // slices of whole sequences, each about twice the bytes of the one before: the first copy, which
+        // nothing can hide, is short, and every later one lands while a longer scan is running
         int64_t cut[8];
         cut[0] = 0;
         for (int k = 1; k <= kSlices; k++) {
-            const int64_t want = total_bp * k / kSlices;
+            const int64_t want = (int64_t) ((double) total_bp * (double) ((1 << k) - 1) / (double) ((1 << kSlices) - 1));
             cut[k] = k == kSlices ? n_seqs : std::lower_bound(seq_off + cut[k - 1], seq_off + n_seqs, want) - seq_off;
         }
         RangeList ranges;
