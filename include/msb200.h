@@ -94,6 +94,12 @@ int msb_seqs_from_ascii(msb_ctx *ctx, int64_t n_seqs, const char *seq_bytes,
  * Only the 20 n bytes of the interval table cross PCIe. */
 int msb_seqs_extract(msb_ctx *ctx, const msb_seqs *src, int64_t n, const int32_t *src_idx,
                      const int64_t *start, const int64_t *end, msb_seqs **out);
+/* Number of non-ACGT bases in each of n windows [start[i], start[i] + length) of sequence src_idx[i] of a
+ * resident set (clipped at the sequence end): the device half of the background sampler's acceptance
+ * test `seq.count('N') + seq.count('n') <= max_n` (genome/__init__.py:172-175) -- a window without
+ * any non-ACGT base is accepted without being fetched. */
+int msb_seqs_window_ncount(msb_ctx *ctx, const msb_seqs *src, int64_t n, const int32_t *src_idx,
+                           const int64_t *start, int32_t length, int32_t *counts);
 int msb_seqs_count(const msb_seqs *seqs, int64_t *n_seqs, int64_t *total_bp);
 /* True length in bases of every sequence (n_seqs entries). */
 int msb_seqs_lengths(const msb_seqs *seqs, int64_t *lens);

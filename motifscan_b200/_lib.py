@@ -45,6 +45,7 @@ SIGNATURES = {
     "msb_seqs_from_ascii": (ctypes.c_int, [c_vp, ctypes.c_int64, c_vp, c_i64p, ctypes.POINTER(c_vp)]),
     "msb_seqs_extract": (ctypes.c_int, [c_vp, c_vp, ctypes.c_int64, c_i32p, c_i64p, c_i64p, ctypes.POINTER(c_vp)]),
     "msb_seqs_lengths": (ctypes.c_int, [c_vp, c_i64p]),
+    "msb_seqs_window_ncount": (ctypes.c_int, [c_vp, c_vp, ctypes.c_int64, c_i32p, c_i64p, ctypes.c_int32, c_i32p]),
     "msb_seqs_set_start_limit": (ctypes.c_int, [c_vp, c_i32p]),
     "msb_seqs_count": (ctypes.c_int, [c_vp, c_i64p, c_i64p]),
     "msb_seqs_codes": (ctypes.c_int, [c_vp, c_vp, c_i8p]),

@@ -110,6 +110,30 @@ extract_pack_kernel(SeqView src, const int32_t *__restrict__ src_idx, const int6
     blk_seq[b] = (int32_t) s;
 }
 
+// Number of non-ACGT bases in each of n windows [start, start + length) of a resident set (the
+// acceptance test of the background sampler, genome/__init__.py:172-175, counts the N of a sample).
+// One thread per window; the window is clipped at its sequence's end.
+__global__ void __launch_bounds__(256)
+window_ncount_kernel(SeqView src, const int32_t *__restrict__ src_idx, const int64_t *__restrict__ start,
+                     int32_t length, int64_t n, int32_t *__restrict__ counts) {
+    const int64_t i = (int64_t) blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const int64_t s = __ldg(src_idx + i), a = __ldg(start + i);
+    const int64_t left = (int64_t) __ldg(src.len + s) - a;
+    int64_t todo = left < length ? left : length;
+    int64_t q = __ldg(src.poff + s) + a;
+    int32_t c = 0;
+    while (todo > 0) {
+        const int off = (int) (q & 31);
+        const int take = (int) (todo < 32 - off ? todo : 32 - off);
+        const uint32_t w = __ldg(src.nmask + (q >> 5)) >> off;
+        c += __popc(take >= 32 ? w : (w & ((1u << take) - 1u)));
+        q += take;
+        todo -= take;
+    }
+    counts[i] = c;
+}
+
 // Parity accessor: packed -> int8 codes laid out like the ASCII input.
 __global__ void __launch_bounds__(256)
 unpack_codes_kernel(SeqView S, const int64_t *__restrict__ seq_off, int8_t *__restrict__ out) {

@@ -659,6 +659,32 @@ int msb_seqs_extract(msb_ctx *ctx, const msb_seqs *src, int64_t n, const int32_t
     return MSB_OK;
 }
 
+int msb_seqs_window_ncount(msb_ctx *ctx, const msb_seqs *src, int64_t n, const int32_t *src_idx, const int64_t *start,
+                           int32_t length, int32_t *counts) {
+    if (!ctx || !src || n < 0 || length < 0 || (n > 0 && (!src_idx || !start || !counts))) {
+        set_error("msb_seqs_window_ncount: bad argument");
+        return MSB_EINVAL;
+    }
+    if (src->ctx != ctx) { set_error("msb_seqs_window_ncount: source belongs to another context"); return MSB_EINVAL; }
+    for (int64_t i = 0; i < n; i++)
+        if (src_idx[i] < 0 || src_idx[i] >= src->n || start[i] < 0) { set_error("msb_seqs_window_ncount: window out of range"); return MSB_EINVAL; }
+    if (n == 0) return MSB_OK;
+    MSB_CUDA(cudaSetDevice(ctx->device));
+    cudaStream_t st = ctx->stream;
+    // tables ride in the ASCII scratch: src_idx (4n) | start (8n) | counts (4n)
+    const size_t a_off = ((size_t) n * 4 + 15) & ~(size_t) 15, c_off = a_off + (((size_t) n * 8 + 15) & ~(size_t) 15);
+    MSB_TRY(ctx->ascii.ensure(c_off + (size_t) n * 4));
+    char *base = (char *) ctx->ascii.p;
+    MSB_CUDA(cudaMemcpyAsync(base, src_idx, (size_t) n * 4, cudaMemcpyHostToDevice, st));
+    MSB_CUDA(cudaMemcpyAsync(base + a_off, start, (size_t) n * 8, cudaMemcpyHostToDevice, st));
+    window_ncount_kernel<<<(unsigned) ((n + 255) / 256), 256, 0, st>>>(src->view(), (const int32_t *) base, (const int64_t *) (base + a_off),
+                                                                      length, n, (int32_t *) (base + c_off));
+    MSB_CUDA(cudaGetLastError());
+    MSB_CUDA(cudaMemcpyAsync(counts, base + c_off, (size_t) n * 4, cudaMemcpyDeviceToHost, st));
+    MSB_CUDA(cudaStreamSynchronize(st));
+    return MSB_OK;
+}
+
 int msb_seqs_lengths(const msb_seqs *S, int64_t *lens) {
     if (!S || (!lens && S->n)) { set_error("msb_seqs_lengths: null"); return MSB_EINVAL; }
     for (int64_t i = 0; i < S->n; i++) lens[i] = S->seq_off[i + 1] - S->seq_off[i];

@@ -155,6 +155,15 @@ class SequenceSet:
                                          ptr(start, ctypes.c_int64), ptr(end, ctypes.c_int64), ctypes.byref(h)))
         return SequenceSet(self.ctx, _handle=h)
 
+    def window_ncount(self, src_idx, start, length):
+        """Non-ACGT bases in each window [start[i], start[i] + length) of sequence src_idx[i]."""
+        src_idx = np.ascontiguousarray(np.asarray(src_idx, dtype=np.int32))
+        start = np.ascontiguousarray(np.asarray(start, dtype=np.int64))
+        out = np.zeros(max(len(src_idx), 1), dtype=np.int32)
+        check(self._lib.msb_seqs_window_ncount(self.ctx._h, self._h, len(src_idx), ptr(src_idx, ctypes.c_int32),
+                                               ptr(start, ctypes.c_int64), int(length), ptr(out, ctypes.c_int32)))
+        return out[:len(src_idx)]
+
     def set_start_limit(self, limit):
         """Windows may only start at the first limit[i] positions of sequence i (chunked genome
         scans: starts inside the overlap belong to the next chunk).  None restores the default."""

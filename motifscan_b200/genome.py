@@ -172,6 +172,54 @@ class DeviceGenome:
         idx = np.fromiter((self.chrom_index[c] for c in chroms), dtype=np.int32, count=len(chroms))
         return self.seqs.extract(idx, starts, ends)
 
+    def random_windows(self, n_times, length, max_n=0, random_seed=None):
+        """The background sampler (reference genome/__init__.py:159-176) without fetching the samples:
+        the same legacy-numpy RNG calls in the same order -- `np.random.seed`, one `np.random.choice`
+        of `n_times` chromosomes weighted by size, then one `np.random.randint(size - length)` per
+        attempt (drawn as arrays: the legacy generator gives the same stream for an array of bounds
+        as for the scalar calls, checked in tests) -- and the same acceptance rule, with the N count of
+        an attempt taken from the resident N mask.  Only attempts that hold SOME non-ACGT base and
+        could still pass (`max_n` > 0, or IUPAC codes, which the reference does not count) are fetched
+        and counted on the host.  Returns (chromosome indices, starts) of the accepted samples in
+        order; the global RNG is left exactly where the reference leaves it."""
+        if random_seed is not None:
+            np.random.seed(random_seed)
+        sizes = np.array([self.chrom_sizes[c] for c in self.chroms], dtype=np.int64)
+        weights = [s / sizes.sum() for s in sizes.tolist()]          # genome/__init__.py:163-165
+        picks = np.random.choice(self.chroms, size=n_times, p=weights)
+        pick_idx = np.fromiter((self.chrom_index[c] for c in picks), dtype=np.int32, count=n_times)
+        acc_idx, acc_start = [], []
+        got, attempt = 0, 0
+        while got < n_times:
+            m = max(1024, min(2 * (n_times - got), 1 << 22))
+            state = np.random.get_state()
+            idx = pick_idx[(attempt + np.arange(m)) % n_times]
+            starts = np.random.randint(sizes[idx] - length)
+            ncount = self.seqs.window_ncount(idx, starts, length)
+            ok = ncount <= max_n
+            for k in np.flatnonzero(~ok):                            # may still pass by the reference's own count
+                seq = self.genome.fetch_sequence(self.chroms[idx[k]], int(starts[k]), int(starts[k]) + length)
+                ok[k] = seq.count("N") + seq.count("n") <= max_n
+            cum = np.cumsum(ok)
+            need = n_times - got
+            if cum[-1] >= need:
+                used = int(np.searchsorted(cum, need)) + 1            # attempts of this batch the reference makes
+                np.random.set_state(state)
+                np.random.randint(sizes[idx[:used]] - length)         # consume exactly those draws
+                ok[used:] = False
+                m = used
+            acc_idx.append(idx[:m][ok[:m]])
+            acc_start.append(starts[:m][ok[:m]])
+            got += int(ok[:m].sum())
+            attempt += m
+        return np.concatenate(acc_idx), np.concatenate(acc_start).astype(np.int64)
+
+    def random_sequence_set(self, n_times, length, max_n=0, random_seed=None):
+        """`random_sequences` as a device-resident sequence set: sampled with the reference's RNG and cut
+        out of the resident genome, no strings."""
+        idx, starts = self.random_windows(n_times, length, max_n, random_seed)
+        return self.seqs.extract(idx, starts, starts + length)
+
     def close(self):
         self.seqs.close()
 
