@@ -46,7 +46,7 @@ constexpr int kTcSlots = 3;
 constexpr int kTcIgnoreOff = kTcSlots * kTcSlotBytes;   // 26112: 3 x 16 ignore words
 constexpr int kTcBOff = 27 * 1024;                      // B tiles start here (1024-aligned)
 constexpr int kTcUnitBytes = 8192;                      // one K=32 step of a 256-column tile
-constexpr int kTcMaxUnits = 22;                         // 8 KB K-steps of B per batch (180 KB of shared memory)
+constexpr int kTcMaxUnits = 24;                         // 8 KB K-steps of B per batch (192 KB of shared memory)
 constexpr int kTcMaxTiles = kTcMaxUnits;                // tiles per batch
 constexpr int kTcCols = 256;                            // motif-strand columns per tile
 constexpr int kTcEpiWarps = 16;                         // two sets of 8: set g reads the units that land in TMEM buffer g
