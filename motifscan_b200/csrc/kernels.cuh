@@ -496,22 +496,38 @@ exact_positions_kernel(ExactParams E, const int64_t *__restrict__ pos, int64_t n
     if (E.strand & 2) test_and_emit(E, m, p, 1, exact_raw(E.seq, pw, L, p, 1));
 }
 
-// Dirty windows (they touch a non-ACGT base) x the prefilter-path motifs.  A warp takes 32 listed
-// positions (one per lane, the window's bases in registers) and a chunk of kDirtyMotifs motifs, and
-// walks the motifs together: the motif, its length and the column are warp-uniform, so the 32
-// lanes' PWM reads of one column fall into ONE sector (the four rows of a column), instead of 32
-// sectors when each lane scores a different motif.  Windows are screened in fp32 first; the few
-// that can reach the cutoff are re-scored with the reference's fp64 arithmetic.
+// Dirty windows (they touch a non-ACGT base) x the prefilter-path motifs.  A block takes a chunk of
+// kDirtyMotifs motifs, whose fp32 matrices it stages in shared memory, and 8 x 32 listed positions:
+// one position per lane (the window's bases in registers), each warp walking the chunk's motifs
+// together, so the motif, its length and the column are warp-uniform and the 32 lanes' reads of one
+// column hit at most 4 words of one 16-byte line.  (Reading the matrices straight from global memory
+// left one sector in flight per warp: 0.71 ms for 26.6 k positions x 750 motifs; staged: see
+// profiles/.)  Windows are screened in fp32 (upload_floors in msb200.cu); the few that can reach the
+// cutoff are re-scored with the reference's fp64 arithmetic from global memory.
 constexpr int kDirtyMotifs = 64;
+constexpr int kDirtyStride = 4 * kMaxFastLen;   // floats per staged motif
 __global__ void __launch_bounds__(256)
 exact_dirty_kernel(ExactParams E, const int64_t *__restrict__ pos, int64_t n_pos,
                    const int32_t *__restrict__ motif_ids, int32_t n_ids) {
-    const int64_t warp = ((int64_t) blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    __shared__ float s_pw[kDirtyMotifs * kDirtyStride];
+    __shared__ float s_floor[kDirtyMotifs];
+    __shared__ int32_t s_len[kDirtyMotifs];
+    __shared__ uint32_t s_motif[kDirtyMotifs];
+    const int wib = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int32_t n_chunks = (n_ids + kDirtyMotifs - 1) / kDirtyMotifs;
-    const int64_t group = warp / n_chunks;
-    const int32_t chunk = (int32_t) (warp - group * n_chunks);
+    const int32_t chunk = (int32_t) (blockIdx.x % (unsigned) n_chunks);
+    const int64_t group = (int64_t) (blockIdx.x / (unsigned) n_chunks) * 8 + wib;
+    const int32_t k0 = chunk * kDirtyMotifs, n_here = min(n_ids - k0, kDirtyMotifs);
+    for (int32_t kl = wib; kl < n_here; kl += 8) {
+        const uint32_t m = (uint32_t) __ldg(motif_ids + k0 + kl);
+        const int L = __ldg(E.mot.len + m);
+        const float *src = E.mot.pwm32 + 4 * (int64_t) __ldg(E.mot.col_off + m);
+        for (int i = lane; i < 4 * L; i += 32) s_pw[kl * kDirtyStride + i] = __ldg(src + i);
+        if (lane == 0) { s_len[kl] = L; s_floor[kl] = __ldg(E.mot.floor32 + m); s_motif[kl] = m; }
+    }
+    __syncthreads();
     if (group * 32 >= n_pos) return;
-    const int64_t d = group * 32 + (threadIdx.x & 31);
+    const int64_t d = group * 32 + lane;
     int64_t p = 0, left = 0;
     Window32 w;
     w.codes = 0;
@@ -524,26 +540,33 @@ exact_dirty_kernel(ExactParams E, const int64_t *__restrict__ pos, int64_t n_pos
         if (E.seq.limit && j >= (int64_t) __ldg(E.seq.limit + s)) left = 0;   // the next chunk owns this start
         if (left > 0) w = load_window32(E.seq, p);
     }
-    const int32_t k_end = min(n_ids, (chunk + 1) * kDirtyMotifs);
-    for (int32_t k = chunk * kDirtyMotifs; k < k_end; k++) {
-        const uint32_t m = (uint32_t) __ldg(motif_ids + k);
-        const int L = __ldg(E.mot.len + m);
-        const int64_t col0 = 4 * (int64_t) __ldg(E.mot.col_off + m);
+    for (int32_t kl = 0; kl < n_here; kl++) {
+        const int L = s_len[kl];
+        const float *pw32 = s_pw + kl * kDirtyStride;
         // fp32 screen of both strands (FP64 issues at a fraction of the FP32 rate and the division in
-        // test_and_emit is a subroutine): a score below floor32 cannot pass, see upload_floors
-        const float *pw32 = E.mot.pwm32 + col0;
-        const float floor32 = __ldg(E.mot.floor32 + m);
+        // test_and_emit is a subroutine): a score below the floor cannot pass
+        // Unrolled over the columns with compile-time shifts and offsets: per column and lane one bit
+        // field extract, two address adds, two shared loads and two predicated adds (the kernel is
+        // issue-bound: 7e8 column steps per scan of configs[1]).
         float f32 = 0.f, r32 = 0.f;
-        for (int c = 0; c < L; c++) {
-            if ((w.nmask >> c) & 1u) continue;
-            const int row = (int) ((w.codes >> (2 * c)) & 3u);
-            f32 += __ldg(pw32 + 4 * c + row);
-            r32 += __ldg(pw32 + 4 * (L - 1 - c) + (3 - row));
+        const float *rev_end = pw32 + 4 * (L - 1) + 3;   // reverse strand reads matrix column L - 1 - c, row 3 - row
+        const uint32_t lo = (uint32_t) w.codes, hi = (uint32_t) (w.codes >> 32);
+#pragma unroll
+        for (int c = 0; c < kMaxFastLen; c++) {
+            if (c >= L) break;   // warp-uniform
+            const uint32_t row = ((c < 16 ? lo : hi) >> (2 * (c & 15))) & 3u;
+            const float vf = pw32[4 * c + row], vr = *(rev_end - 4 * c - row);
+            if (!((w.nmask >> c) & 1u)) { f32 += vf; r32 += vr; }
         }
         if (L > left) continue;   // cscore.c:337,340 (also lanes without a position: left = 0)
-        const double *pw = E.mot.pwm + col0;
-        if ((E.strand & 1) && !(f32 < floor32)) test_and_emit(E, m, p, 0, exact_raw_w(w, pw, L, 0));
-        if ((E.strand & 2) && !(r32 < floor32)) test_and_emit(E, m, p, 1, exact_raw_w(w, pw, L, 1));
+        const float floor32 = s_floor[kl];
+        const bool try_f = (E.strand & 1) && !(f32 < floor32), try_r = (E.strand & 2) && !(r32 < floor32);
+        if (try_f || try_r) {   // rare: the reference's arithmetic, matrices from global memory
+            const uint32_t m = s_motif[kl];
+            const double *pw = E.mot.pwm + 4 * (int64_t) __ldg(E.mot.col_off + m);
+            if (try_f) test_and_emit(E, m, p, 0, exact_raw_w(w, pw, L, 0));
+            if (try_r) test_and_emit(E, m, p, 1, exact_raw_w(w, pw, L, 1));
+        }
     }
 }
 

@@ -1336,8 +1336,10 @@ static int scan_device(msb_ctx *ctx, msb_motifs *M, const msb_seqs *S, int stran
             ctx->c[MSB_C_LAUNCHES]++;
         }
         if (n_dirty && n_fast) {
-            const int64_t warps = ((n_dirty + 31) / 32) * ((n_fast + kDirtyMotifs - 1) / kDirtyMotifs);
-            exact_dirty_kernel<<<(unsigned) ((warps * 32 + 255) / 256), 256, 0, st>>>(E, ctx->dirty.as<int64_t>(), n_dirty, d_order, n_fast);
+            // one block = 8 warps x 32 positions x one chunk of kDirtyMotifs motifs
+            const int64_t blocks = ((n_dirty + 255) / 256) * ((n_fast + kDirtyMotifs - 1) / kDirtyMotifs);
+            if (blocks > 0x7fffffffll) { set_error("msb_scan: too many dirty windows for one launch"); return MSB_EINVAL; }
+            exact_dirty_kernel<<<(unsigned) blocks, 256, 0, st>>>(E, ctx->dirty.as<int64_t>(), n_dirty, d_order, n_fast);
             MSB_CUDA(cudaGetLastError());
             ctx->c[MSB_C_LAUNCHES]++;
         }
