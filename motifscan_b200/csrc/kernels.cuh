@@ -578,7 +578,7 @@ decode_sites_kernel(SeqView S, const uint64_t *__restrict__ key, int64_t n, int 
     if (i >= n) return;
     const uint64_t k = key[i];
     const int64_t p = site_pos(k, key_shift);
-    const int64_t s = find_seq(S.poff, S.n_seqs, p);
+    const int64_t s = __ldg(S.blk_seq + (p >> 5));   // a site's position lies inside a sequence, so its block has an owner
     seq_idx[i] = (int32_t) s;
     start[i] = (int32_t) (p - __ldg(S.poff + s));
     strand[i] = (int8_t) (key_rev(k) + 1);  // 1 forward, 2 reverse (cscore.c:359,376)
