@@ -23,6 +23,9 @@ class Context:
         self._h = ctypes.c_void_p()
         check(self._lib.msb_ctx_create(int(device), ctypes.c_void_p(stream or 0), ctypes.byref(self._h)))
         self.device = int(device)
+        # an msb_ctx owns one stream and one set of scratch buffers: calls on it are serialised here so
+        # that host threads sharing a context (e.g. two Scanners on default_context) cannot interleave
+        self._lock = threading.RLock()
 
     def close(self):
         if self._h:
@@ -47,14 +50,16 @@ class Context:
     def site_counts(self, n_motifs):
         """Per-motif site counts of the last `scan_device` on this context."""
         out = np.zeros(max(n_motifs, 1), dtype=np.int64)
-        check(self._lib.msb_scan_device_counts(self._h, ptr(out, ctypes.c_int64), int(n_motifs)))
+        with self._lock:
+            check(self._lib.msb_scan_device_counts(self._h, ptr(out, ctypes.c_int64), int(n_motifs)))
         return out[:n_motifs]
 
     def region_counts(self, n_motifs):
         """Per motif, the number of sequences with at least one site in the last `scan_device` on this
         context (what stats.motif_enrichment counts), reduced on the device."""
         out = np.zeros(max(n_motifs, 1), dtype=np.int64)
-        check(self._lib.msb_scan_device_region_counts(self._h, ptr(out, ctypes.c_int64), int(n_motifs)))
+        with self._lock:
+            check(self._lib.msb_scan_device_region_counts(self._h, ptr(out, ctypes.c_int64), int(n_motifs)))
         return out[:n_motifs]
 
     def counters(self):
@@ -138,8 +143,9 @@ class SequenceSet:
         self.seq_off = seq_off
         self._h = ctypes.c_void_p()
         data = blob.ctypes.data if blob.size else None
-        check(self._lib.msb_seqs_from_ascii(ctx._h, self.n, ctypes.c_void_p(data), ptr(seq_off, ctypes.c_int64),
-                                            ctypes.byref(self._h)))
+        with self.ctx._lock:
+            check(self._lib.msb_seqs_from_ascii(ctx._h, self.n, ctypes.c_void_p(data), ptr(seq_off, ctypes.c_int64),
+                                                ctypes.byref(self._h)))
 
     def extract(self, src_idx, start, end):
         """A new sequence set cut out of this (resident) one on the device: sequence i = bases
@@ -151,8 +157,9 @@ class SequenceSet:
         if not (src_idx.shape == start.shape == end.shape and src_idx.ndim == 1):
             raise ValueError("src_idx, start and end must be 1-d arrays of one length")
         h = ctypes.c_void_p()
-        check(self._lib.msb_seqs_extract(self.ctx._h, self._h, len(src_idx), ptr(src_idx, ctypes.c_int32),
-                                         ptr(start, ctypes.c_int64), ptr(end, ctypes.c_int64), ctypes.byref(h)))
+        with self.ctx._lock:
+            check(self._lib.msb_seqs_extract(self.ctx._h, self._h, len(src_idx), ptr(src_idx, ctypes.c_int32),
+                                             ptr(start, ctypes.c_int64), ptr(end, ctypes.c_int64), ctypes.byref(h)))
         return SequenceSet(self.ctx, _handle=h)
 
     def window_ncount(self, src_idx, start, length):
@@ -160,25 +167,29 @@ class SequenceSet:
         src_idx = np.ascontiguousarray(np.asarray(src_idx, dtype=np.int32))
         start = np.ascontiguousarray(np.asarray(start, dtype=np.int64))
         out = np.zeros(max(len(src_idx), 1), dtype=np.int32)
-        check(self._lib.msb_seqs_window_ncount(self.ctx._h, self._h, len(src_idx), ptr(src_idx, ctypes.c_int32),
-                                               ptr(start, ctypes.c_int64), int(length), ptr(out, ctypes.c_int32)))
+        with self.ctx._lock:
+            check(self._lib.msb_seqs_window_ncount(self.ctx._h, self._h, len(src_idx), ptr(src_idx, ctypes.c_int32),
+                                                   ptr(start, ctypes.c_int64), int(length), ptr(out, ctypes.c_int32)))
         return out[:len(src_idx)]
 
     def set_start_limit(self, limit):
         """Windows may only start at the first limit[i] positions of sequence i (chunked genome
         scans: starts inside the overlap belong to the next chunk).  None restores the default."""
         if limit is None:
-            check(self._lib.msb_seqs_set_start_limit(self._h, None))
+            with self.ctx._lock:
+                check(self._lib.msb_seqs_set_start_limit(self._h, None))
             return
         limit = np.ascontiguousarray(np.asarray(limit, dtype=np.int32))
         if limit.shape != (self.n,):
             raise ValueError("one start limit per sequence is required")
-        check(self._lib.msb_seqs_set_start_limit(self._h, ptr(limit, ctypes.c_int32)))
+        with self.ctx._lock:
+            check(self._lib.msb_seqs_set_start_limit(self._h, ptr(limit, ctypes.c_int32)))
 
     def codes(self):
         """Parity accessor: the reference's int8 codes (cscore.c:81-114) decoded from the device."""
         out = np.empty(max(self.total_bp, 1), dtype=np.int8)
-        check(self._lib.msb_seqs_codes(self.ctx._h, self._h, ptr(out, ctypes.c_int8)))
+        with self.ctx._lock:
+            check(self._lib.msb_seqs_codes(self.ctx._h, self._h, ptr(out, ctypes.c_int8)))
         return out[:self.total_bp]
 
     def close(self):
@@ -251,7 +262,8 @@ def scan(ctx, motifs, seqs, strand, remove_dup=False):
     runs on the device before the sites are copied back."""
     h = ctypes.c_void_p()
     flags = _lib.MSB_SCAN_DEDUP if remove_dup else 0
-    check(ctx._lib.msb_scan_ex(ctx._h, motifs._h, seqs._h, int(strand), flags, ctypes.byref(h)))
+    with ctx._lock:
+        check(ctx._lib.msb_scan_ex(ctx._h, motifs._h, seqs._h, int(strand), flags, ctypes.byref(h)))
     return ScanResult(ctx, h, motifs.n)
 
 
@@ -264,8 +276,9 @@ def scan_ascii(ctx, motifs, blob, seq_off, strand, remove_dup=False):
     h = ctypes.c_void_p()
     flags = _lib.MSB_SCAN_DEDUP if remove_dup else 0
     data = blob.ctypes.data if blob.size else None
-    check(ctx._lib.msb_scan_ascii(ctx._h, motifs._h, len(seq_off) - 1, ctypes.c_void_p(data), ptr(seq_off, ctypes.c_int64),
-                                  int(strand), flags, None, ctypes.byref(h)))
+    with ctx._lock:
+        check(ctx._lib.msb_scan_ascii(ctx._h, motifs._h, len(seq_off) - 1, ctypes.c_void_p(data), ptr(seq_off, ctypes.c_int64),
+                                      int(strand), flags, None, ctypes.byref(h)))
     return ScanResult(ctx, h, motifs.n)
 
 
@@ -294,7 +307,8 @@ def scan_device(ctx, motifs, seqs, strand, remove_dup=False):
     """Kernels only (results stay on the device); returns the number of sites."""
     n = ctypes.c_int64(0)
     flags = _lib.MSB_SCAN_DEDUP if remove_dup else 0
-    check(ctx._lib.msb_scan_device(ctx._h, motifs._h, seqs._h, int(strand), flags, ctypes.byref(n)))
+    with ctx._lock:
+        check(ctx._lib.msb_scan_device(ctx._h, motifs._h, seqs._h, int(strand), flags, ctypes.byref(n)))
     return n.value
 
 
@@ -309,8 +323,9 @@ def scan_ranges(ctx, motifs, seqs, strand, ranges, remove_dup=False):
     n, a, b, c = _ranges(ranges)
     h = ctypes.c_void_p()
     flags = _lib.MSB_SCAN_DEDUP if remove_dup else 0
-    check(ctx._lib.msb_scan_ranges(ctx._h, motifs._h, seqs._h, int(strand), flags, n, ptr(a, ctypes.c_int64),
-                                   ptr(b, ctypes.c_int64), ptr(c, ctypes.c_int64), ctypes.byref(h)))
+    with ctx._lock:
+        check(ctx._lib.msb_scan_ranges(ctx._h, motifs._h, seqs._h, int(strand), flags, n, ptr(a, ctypes.c_int64),
+                                       ptr(b, ctypes.c_int64), ptr(c, ctypes.c_int64), ctypes.byref(h)))
     return ScanResult(ctx, h, motifs.n)
 
 
@@ -319,15 +334,17 @@ def scan_ranges_device(ctx, motifs, seqs, strand, ranges, remove_dup=False):
     n, a, b, c = _ranges(ranges)
     total = ctypes.c_int64(0)
     flags = _lib.MSB_SCAN_DEDUP if remove_dup else 0
-    check(ctx._lib.msb_scan_ranges_device(ctx._h, motifs._h, seqs._h, int(strand), flags, n, ptr(a, ctypes.c_int64),
-                                          ptr(b, ctypes.c_int64), ptr(c, ctypes.c_int64), ctypes.byref(total)))
+    with ctx._lock:
+        check(ctx._lib.msb_scan_ranges_device(ctx._h, motifs._h, seqs._h, int(strand), flags, n, ptr(a, ctypes.c_int64),
+                                              ptr(b, ctypes.c_int64), ptr(c, ctypes.c_int64), ctypes.byref(total)))
     return total.value
 
 
 def score(ctx, motifs, seqs, strand):
     out = np.empty((motifs.n, seqs.n), dtype=np.float64)
     buf = out if out.size else np.zeros(1, dtype=np.float64)
-    check(ctx._lib.msb_score(ctx._h, motifs._h, seqs._h, int(strand), ptr(buf, ctypes.c_double)))
+    with ctx._lock:
+        check(ctx._lib.msb_score(ctx._h, motifs._h, seqs._h, int(strand), ptr(buf, ctypes.c_double)))
     return out
 
 
@@ -335,6 +352,7 @@ def score_select(ctx, motifs, seqs, strand, ranks):
     ranks = np.ascontiguousarray(np.asarray(ranks, dtype=np.int64))
     out = np.empty((motifs.n, len(ranks)), dtype=np.float64)
     buf = out if out.size else np.zeros(1, dtype=np.float64)
-    check(ctx._lib.msb_score_select(ctx._h, motifs._h, seqs._h, int(strand), len(ranks),
-                                    ptr(ranks, ctypes.c_int64), ptr(buf, ctypes.c_double)))
+    with ctx._lock:
+        check(ctx._lib.msb_score_select(ctx._h, motifs._h, seqs._h, int(strand), len(ranks),
+                                        ptr(ranks, ctypes.c_int64), ptr(buf, ctypes.c_double)))
     return out

@@ -386,3 +386,36 @@ def test_scan_ascii_sliced_upload_equals_two_step_scan(eng):
     ref = oracle.scan_arrays(pwms, cutoffs, seqs[:40], 3, n_threads=4)
     assert_scan_equal(small, ref)
     small.close(), pinned.close(), sset.close(), motifs.close()
+
+
+def test_threads_sharing_a_context_are_serialised(eng):
+    """Two host threads scanning on the same context (what two Scanners on the default context do):
+    the engine serialises the calls, results are the oracle's."""
+    import threading
+    rng = np.random.default_rng(91)
+    pwms = synth_pwms(rng, 40)
+    jobs = []
+    for k in range(4):
+        seqs = synth_seqs(rng, 120, 300, 800, p_n=0.002)
+        cutoffs = cutoffs_for(pwms, seqs, 1e-3)
+        jobs.append((seqs, cutoffs, oracle.scan_arrays(pwms, cutoffs, seqs, 3, n_threads=4)))
+    ctx = eng.default_context(0)
+    errors = []
+
+    def work(seqs, cutoffs, expect):
+        try:
+            for _ in range(5):
+                motifs = eng.MotifSet(ctx, pwms, cutoffs)
+                sset = eng.SequenceSet(ctx, seqs)
+                res = eng.scan(ctx, motifs, sset, 3)
+                assert_scan_equal(res, expect)
+                res.close(), sset.close(), motifs.close()
+        except Exception as exc:   # noqa: BLE001
+            errors.append(exc)
+
+    threads = [threading.Thread(target=work, args=j) for j in jobs]
+    for t in threads:
+        t.start()
+    for t in threads:
+        t.join()
+    assert not errors, errors
