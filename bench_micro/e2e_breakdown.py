@@ -18,7 +18,7 @@ bg.close()
 pin = engine.PinnedArray(blob.size)
 pin.array[:] = blob
 lib = _lib.load()
-for slices in (1, 2, 4, 7):
+for slices in (3, 4, 5, 6):
     _lib.check(lib.msb_set_option(b"ascii_slices", slices))
     best = None
     for it in range(6):

@@ -32,7 +32,22 @@ class GenomeSites:
         self.chroms = list(chroms)
         self.n_motifs = n_motifs
         self.counts = counts
-        self.motif, self.chrom_idx, self.start, self.score, self.strand = motif, chrom_idx, start, score, strand
+        self._motif = motif          # None: built from the counts on first use (32 M entries for an hg19 share)
+        self.chrom_idx, self.start, self.score, self.strand = chrom_idx, start, score, strand
+
+    @property
+    def motif(self):
+        """Motif index of every site (the arrays are motif-major: `offsets` delimit the motifs)."""
+        if self._motif is None:
+            self._motif = np.repeat(np.arange(self.n_motifs, dtype=np.int32), self.counts if len(self.start) else 0)
+        return self._motif
+
+    @property
+    def offsets(self):
+        off = np.zeros(self.n_motifs + 1, dtype=np.int64)
+        if len(self.start):
+            np.cumsum(self.counts, out=off[1:])
+        return off
 
     def __len__(self):
         return int(self.counts.sum())
@@ -47,7 +62,7 @@ def _merge_parts(parts, n_motifs):
                 np.zeros(0, np.int8))
     if len(parts) == 1:
         c, cidx, start, score, strand = parts[0]
-        return np.repeat(np.arange(n_motifs, dtype=np.int32), c), cidx, start, score, strand
+        return None, cidx, start, score, strand
     counts = np.stack([p[0] for p in parts])                  # [batch][motif]
     offs = np.zeros((len(parts), n_motifs + 1), dtype=np.int64)
     np.cumsum(counts, axis=1, out=offs[:, 1:])
@@ -64,8 +79,7 @@ def _merge_parts(parts, n_motifs):
             cidx[d:d + e - a], start[d:d + e - a] = c[a:e], s[a:e]
             score[d:d + e - a], strand[d:d + e - a] = sc[a:e], st[a:e]
             at[m] += e - a
-    motif = np.repeat(np.arange(n_motifs, dtype=np.int32), np.diff(out_off))
-    return motif, cidx, start, score, strand
+    return None, cidx, start, score, strand
 
 
 def plan_ranges(chrom_sizes, chunk_bp, world=1, rank=0):
