@@ -419,3 +419,37 @@ def test_threads_sharing_a_context_are_serialised(eng):
     for t in threads:
         t.join()
     assert not errors, errors
+
+
+def test_degenerate_shapes(eng):
+    """Edges of the record path: only motifs the prefilter cannot take (L > 32), no motifs, no
+    sequences, one 1-base sequence, empty result followed by the count accessors."""
+    rng = np.random.default_rng(5)
+    ctx = eng.default_context(0)
+    seqs = synth_seqs(rng, 20, 100, 300, p_n=0.01)
+    # (1) every motif longer than 32: the tensor-core prefilter has nothing to do
+    slow = [rng.normal(0, 1.5, size=(4, L)).round(3).tolist() for L in (33, 40, 64)]
+    cut = [0.2, 0.25, 0.1]
+    motifs, sset = eng.MotifSet(ctx, slow, cut), eng.SequenceSet(ctx, seqs)
+    res = eng.scan(ctx, motifs, sset, 3)
+    assert_scan_equal(res, oracle.scan_arrays(slow, cut, seqs, 3, n_threads=4))
+    assert res.n_sites > 0
+    res.close(), motifs.close()
+    # (2) no motifs
+    none = eng.MotifSet(ctx, [], [])
+    res = eng.scan(ctx, none, sset, 3)
+    assert res.n_sites == 0 and len(res.counts) == 0
+    res.close(), none.close(), sset.close()
+    # (3) no sequences / one single base / only empty strings
+    pwms = synth_pwms(rng, 5)
+    motifs = eng.MotifSet(ctx, pwms, [0.5] * 5)
+    for ss in ([], ["A"], ["", ""], ["N"]):
+        sset = eng.SequenceSet(ctx, ss)
+        res = eng.scan(ctx, motifs, sset, 3)
+        assert res.n_sites == 0 and res.counts.tolist() == [0] * 5
+        assert eng.scan_device(ctx, motifs, sset, 3) == 0
+        assert ctx.site_counts(5).tolist() == [0] * 5 and ctx.region_counts(5).tolist() == [0] * 5
+        a = eng.scan_ascii(ctx, motifs, *__import__("motifscan_b200")._lib.flatten_seqs(ss), 3)
+        assert a.n_sites == 0
+        a.close(), res.close(), sset.close()
+    motifs.close()
