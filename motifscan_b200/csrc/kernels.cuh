@@ -404,9 +404,9 @@ exact_candidates_kernel(ExactParams E, const uint64_t *__restrict__ cand, int64_
 }
 
 // The tensor-core prefilter leaves its candidate records in one buffer per epilogue lane
-// (prefilter_tc.cuh, "Candidate emission").  lane_totals_kernel (one block): counters[0] = records
-// held (counts clamped to the buffer capacity), counters[3] = largest unclamped count -- beyond the
-// capacity the host repeats the prefilter with larger buffers.
+// (prefilter_tc.cuh, "Candidate emission").  lane_totals_kernel: counters[0] += records held (counts
+// clamped to the buffer capacity), counters[3] = max(largest unclamped count) -- beyond the capacity
+// the host repeats the prefilter with larger buffers.  Both counters are zero before the launch.
 __global__ void __launch_bounds__(1024)
 lane_totals_kernel(const uint32_t *__restrict__ lane_count, int32_t n_lanes, int64_t cap,
                    unsigned long long *__restrict__ counters) {
@@ -414,7 +414,7 @@ lane_totals_kernel(const uint32_t *__restrict__ lane_count, int32_t n_lanes, int
     __shared__ unsigned int s_max[32];
     unsigned long long sum = 0;
     unsigned int mx = 0;
-    for (int i = threadIdx.x; i < n_lanes; i += blockDim.x) {
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n_lanes; i += gridDim.x * blockDim.x) {
         const unsigned int c = __ldg(lane_count + i);
         mx = max(mx, c);
         sum += min((unsigned long long) c, (unsigned long long) cap);
@@ -432,7 +432,10 @@ lane_totals_kernel(const uint32_t *__restrict__ lane_count, int32_t n_lanes, int
             sum += __shfl_xor_sync(0xffffffffu, sum, d);
             mx = max(mx, __shfl_xor_sync(0xffffffffu, mx, d));
         }
-        if (threadIdx.x == 0) { counters[0] = sum; counters[3] = mx; }
+        if (threadIdx.x == 0) {
+            atomicAdd(counters + 0, sum);
+            atomicMax(counters + 3, (unsigned long long) mx);
+        }
     }
 }
 

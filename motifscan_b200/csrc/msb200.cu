@@ -1231,7 +1231,7 @@ static int scan_device(msb_ctx *ctx, msb_motifs *M, const msb_seqs *S, int stran
                     ctx->c[MSB_C_PREFILTER_LAUNCHES]++;
                 }
             }
-            lane_totals_kernel<<<1, 1024, 0, st>>>(ctx->lane_count.as<uint32_t>(), n_lanes, lane_cap,
+            lane_totals_kernel<<<(unsigned) std::min<int64_t>((n_lanes + 1023) / 1024, 128), 1024, 0, st>>>(ctx->lane_count.as<uint32_t>(), n_lanes, lane_cap,
                                                    ctx->counters.as<unsigned long long>());
             MSB_CUDA(cudaGetLastError());
             ctx->c[MSB_C_LAUNCHES]++;
