@@ -195,3 +195,62 @@ def test_counts_only_mode(setup):
                         ctx=engine.default_context(0))
     assert np.array_equal(sites.counts, expect[0])
     assert sites.start.size == 0
+
+
+def test_window_ncount_and_empty_extract(setup):
+    """msb_seqs_window_ncount == counting the non-ACGT letters of the fetched window (clipped at the
+    chromosome end); extracting nothing gives an empty set that scans to nothing."""
+    genome, pwms, cutoffs, _ = setup
+    ctx = engine.default_context(0)
+    dg = DeviceGenome(genome, ctx)
+    rng = np.random.default_rng(12)
+    idx = rng.integers(0, len(genome.chroms), size=500).astype(np.int32)
+    starts = np.array([rng.integers(0, genome.chrom_sizes[genome.chroms[i]]) for i in idx], dtype=np.int64)
+    for length in (1, 30, 33, 700):
+        got = dg.seqs.window_ncount(idx, starts, length)
+        want = [sum(ch not in "ACGTacgt" for ch in genome.fetch_sequence(genome.chroms[i], int(a), int(a) + length))
+                for i, a in zip(idx, starts)]
+        assert got.tolist() == want
+    assert sum(want) > 0
+    empty = dg.seqs.extract(np.zeros(0, np.int32), np.zeros(0, np.int64), np.zeros(0, np.int64))
+    assert empty.n == 0 and empty.total_bp == 0
+    motifs = engine.MotifSet(ctx, pwms, cutoffs)
+    res = engine.scan(ctx, motifs, empty, 3)
+    assert res.n_sites == 0
+    res.close(), motifs.close(), empty.close(), dg.close()
+
+
+def test_range_scan_with_several_prefilter_batches(setup):
+    """1,900 motifs need several prefilter launches per range (24 K-step units of B each); ranges and
+    batches multiply, the candidate records of all launches accumulate in the same lane buffers."""
+    genome, _, _, _ = setup
+    rng = np.random.default_rng(77)
+    pwms = synth_pwms(rng, 1900)
+    whole = [genome.seqs[c].decode() for c in genome.chroms]
+    cutoffs = cutoffs_for(pwms, whole[:2], 2e-4)
+    ctx = engine.default_context(0)
+    dg = DeviceGenome(genome, ctx)
+    motifs = engine.MotifSet(ctx, pwms, cutoffs)
+    full = engine.scan(ctx, motifs, dg.seqs, 3)
+    n_batches = ctx.counters()["prefilter_launches"]
+    assert n_batches >= 2
+    i1 = dg.chrom_index["chr1"]
+    ranges = [(i1, 0, 40000), (i1, 40000, 90001), (i1, 90001, 123457), (dg.chrom_index["chr2"], 0, 70001),
+              (dg.chrom_index["chrM"], 0, 1571), (dg.chrom_index["chr10"], 0, 33)]
+    parts = engine.scan_ranges(ctx, motifs, dg.seqs, 3, ranges)
+    assert ctx.counters()["prefilter_launches"] == n_batches * len(ranges)
+    assert parts.n_sites == full.n_sites > 10000
+    assert np.array_equal(parts.counts, full.counts) and np.array_equal(parts.seq_idx, full.seq_idx)
+    assert np.array_equal(parts.start, full.start) and np.array_equal(parts.strand, full.strand)
+    assert np.array_equal(parts.score.view(np.uint64), full.score.view(np.uint64))
+    # and against the oracle for a handful of motifs
+    pick = [0, 7, 950, 1899]
+    want = oracle.scan_arrays([pwms[m] for m in pick], [cutoffs[m] for m in pick], whole, 3, n_threads=8)
+    for k, m in enumerate(pick):
+        a, b = full.offsets[m], full.offsets[m + 1]
+        wa = int(want[0][:k].sum())
+        wb = wa + int(want[0][k])
+        assert np.array_equal(full.seq_idx[a:b], want[1][wa:wb].astype(np.int32))
+        assert np.array_equal(full.start[a:b], want[2][wa:wb].astype(np.int32))
+        assert np.array_equal(full.score[a:b].view(np.uint64), want[3][wa:wb].view(np.uint64))
+    parts.close(), full.close(), motifs.close(), dg.close()
