@@ -19,7 +19,7 @@ pin = engine.PinnedArray(blob.size)
 pin.array[:] = blob
 lib = _lib.load()
 for slices in (3, 4, 5, 6):
-    _lib.check(lib.msb_set_option(b"ascii_slices", slices))
+    ctx.set_option("ascii_slices", slices)
     best = None
     for it in range(6):
         t0 = time.perf_counter()

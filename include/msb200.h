@@ -14,9 +14,12 @@
  *   - every function returns MSB_OK (0) or a negative MSB_E* code; msb_last_error() returns a
  *     thread-local message for the last failure on the calling thread.  Nothing calls exit()
  *     (the reference does on hit-allocation failure, cscore.c:360-363).
- *   - the library keeps no global mutable state: all state hangs off an msb_ctx (one device,
- *     one stream).  Different contexts may be used from different host threads concurrently
- *     (the reference's file-scope globals, cscore.c:26-34, make it single-caller).
+ *   - the library keeps no global mutable state: all state, including every tuning option, hangs
+ *     off an msb_ctx (one device, one stream).  Different contexts may be used from different
+ *     host threads concurrently -- that is how one process drives several GPUs -- while calls on
+ *     ONE context must be serialised by the caller (the reference's file-scope globals,
+ *     cscore.c:26-34, make it single-caller).  The handle-less mirrors msb_c_scan_motif /
+ *     msb_c_score keep one context per (calling thread, device) in thread-local storage.
  *   - PWMs are passed flat: motif m is the row-major 4 x lens[m] block at mats + mat_off[m]
  *     (rows A, C, G, T -- the reference's `double *matrix[4]`, cscore.c:6-11).
  *   - sequences are passed flat: sequence i is the ASCII bytes seq_bytes[seq_off[i] ..
@@ -65,8 +68,13 @@ enum { MSB_C_CANDIDATES = 0, MSB_C_DIRTY, MSB_C_HITS, MSB_C_LAUNCHES, MSB_C_RETR
        MSB_C_PREFILTER_LAUNCHES, MSB_C_COUNT };
 int msb_ctx_counters(const msb_ctx *ctx, int64_t *v, int n);
 
-/* Tuning knob for experiments: "prefilter_w" = windows per thread of the prefilter (4 or 8). */
-int msb_set_option(const char *name, int value);
+/* Tuning / test knobs of ONE context (nothing is process-wide): "prefilter_tc" 1 = tensor-core prefilter
+ * (default), 0 = shared-memory table prefilter; "prefilter_w" windows per thread of the table prefilter
+ * (4 or 8); "ascii_slices" upload slices of msb_scan_ascii (1..7); "tc_first_lane_cap" records per lane
+ * buffer on the first attempt (tests of the overflow retry; 0 = sized from the input); "poison_pool" 1 =
+ * recycled device buffers are filled with 0xFF (tests: nothing may rely on stale contents); "tc_prof" 1
+ * = per-role cycle counters of the tensor-core prefilter on stderr. */
+int msb_ctx_set_option(msb_ctx *ctx, const char *name, int value);
 
 /* Pinned host memory for callers that want full-speed H2D (cudaHostAlloc / cudaFreeHost). */
 int msb_pinned_alloc(int64_t bytes, void **ptr);
@@ -86,6 +94,21 @@ int msb_motifs_destroy(msb_motifs *motifs);
 /* Copies the bytes to the device and encodes + packs them there. */
 int msb_seqs_from_ascii(msb_ctx *ctx, int64_t n_seqs, const char *seq_bytes,
                         const int64_t *seq_off, msb_seqs **out);
+/* The same from sequences that are ALREADY packed the way the library keeps them (a packed genome cache
+ * on disk, another context's msb_seqs_to_packed): 0.375 B/bp cross PCIe instead of 1 B/bp, and nothing is
+ * encoded.  Layout: sequence i occupies the 32-base blocks [poff_i / 32, poff_{i+1} / 32) with poff_0 = 0 and
+ * poff_{i+1} = poff_i + lens[i] rounded up to 32; block b is codes[2 b], codes[2 b + 1] (2 bits per base,
+ * base k of the block at bits 2 (k % 16) of word k / 16; A C G T = 0 1 2 3, cscore.c:91-108) and nmask[b]
+ * (bit k set <=> base k is not A/C/G/T, cscore.c:109-110).  Bits behind a sequence's last base and codes
+ * of masked bases are ignored (cleared on the device). */
+#define MSB_SEQS_ASYNC 1   /* return at once: the copies run on the context's copy stream and overlap a scan in
+                            * progress; `codes` / `nmask` must stay valid (and should be pinned) until the first
+                            * scan of the set has returned, or msb_seqs_wait */
+int msb_seqs_from_packed(msb_ctx *ctx, int64_t n_seqs, const int64_t *lens, const uint32_t *codes,
+                         const uint32_t *nmask, int flags, msb_seqs **out);
+int msb_seqs_wait(const msb_seqs *seqs);
+/* The packed planes of a sequence set, in the layout above: 2 * B and B words, B = sum_i ceil(len_i / 32). */
+int msb_seqs_to_packed(msb_ctx *ctx, const msb_seqs *seqs, uint32_t *codes, uint32_t *nmask);
 /* Resident genome: instead of one host fetch per region (Scanner._extract_seq,
  * scanner.py:71-87 -> Genome.fetch_sequence -> pysam FastaFile.fetch, genome/__init__.py:135) the
  * chromosomes are encoded once into a resident msb_seqs and every later sequence set is cut out of
@@ -125,6 +148,14 @@ int msb_scan(msb_ctx *ctx, const msb_motifs *motifs, const msb_seqs *seqs, int s
  * sequence) and per strand, a site closer than the motif length to the previous survivor
  * replaces it only if it scores strictly higher. */
 #define MSB_SCAN_DEDUP 1
+/* MSB_SCAN_COUNTS: only per-motif site counts are wanted (genome-wide counting): the sites are neither
+ * ordered nor kept; valid with the *_device entry points (msb_scan_device_counts reads the counts), an error
+ * with the ones that return a msb_result.  Ignored together with MSB_SCAN_DEDUP (which needs the order). */
+#define MSB_SCAN_COUNTS 2
+/* MSB_SCAN_ASYNC: the call returns as soon as the device-to-host copy of the sites is enqueued on the
+ * context's copy stream; the next scan on the same context overlaps it.  msb_result_total is valid at
+ * once; msb_result_wait (or msb_result_counts / msb_result_arrays, which wait) makes the arrays valid. */
+#define MSB_SCAN_ASYNC 4
 int msb_scan_ex(msb_ctx *ctx, const msb_motifs *motifs, const msb_seqs *seqs, int strand,
                 int flags, msb_result **out);
 /* c_scan_motif in one call with persistent motifs (cscore.c:399-476: strings in, sites out):
@@ -156,12 +187,23 @@ int msb_scan_device_counts(msb_ctx *ctx, int64_t *counts, int32_t n_motifs);
  * msb_scan_ranges_device on this context: the only thing motif_enrichment needs from a scan
  * (stats.py:29-31 counts the regions whose site list is non-empty), reduced on the device. */
 int msb_scan_device_region_counts(msb_ctx *ctx, int64_t *counts, int32_t n_motifs);
+int msb_result_wait(msb_result *res);
 int msb_result_total(const msb_result *res, int64_t *n_sites);
 int msb_result_counts(const msb_result *res, int64_t *counts /* n_motifs */);
 /* Borrowed pointers into the result (valid until msb_result_destroy): n_sites entries each. */
 int msb_result_arrays(const msb_result *res, const int32_t **seq_idx, const int32_t **start,
                       const double **score, const int8_t **strand /* 1 or 2 */);
 int msb_result_destroy(msb_result *res);
+
+/* ---- host-side gather of several results (replaces the reference's per-motif result lists filled by
+ * its thread pool, cscore.c:323-328, 425-436) ----------------------------------------------------- */
+/* n_parts motif-major arrays (one per GPU or per batch, each over its own sequences, parts in ascending
+ * sequence order) -> one motif-major array: for every motif, part 0's entries, then part 1's, ...
+ * counts[p * n_motifs + m] = entries of motif m in part p; src[p] = part p's array of elem_size-byte entries;
+ * add_i32 (optional, 4-byte entries only): per-part addend, e.g. the part's first global sequence index.
+ * Pure host code (memcpy on up to n_threads threads); no device, no context. */
+int msb_merge_motif_major(int32_t n_parts, int32_t n_motifs, const int64_t *counts, const void *const *src,
+                          void *dst, int32_t elem_size, const int64_t *add_i32, int32_t n_threads);
 
 /* ---- score (replaces motif_score_thread + motif_score, cscore.c:174-302) -------------------- */
 /* out is n_motifs x n_seqs row-major: the offset-0 window score of every sequence. */

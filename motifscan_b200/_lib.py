@@ -14,6 +14,9 @@ LIB_PATH = os.environ.get("MSB200_LIB") or os.path.join(_HERE, "libmsb200.so")
 
 MSB_OK, MSB_EINVAL, MSB_ENOMEM, MSB_ECUDA, MSB_ESHORT = 0, -1, -2, -3, -4
 MSB_SCAN_DEDUP = 1
+MSB_SCAN_COUNTS = 2
+MSB_SCAN_ASYNC = 4
+MSB_SEQS_ASYNC = 1
 T_NAMES = ("h2d", "encode", "prefilter", "exact", "order", "d2h", "score", "select")
 C_NAMES = ("candidates", "dirty", "hits", "launches", "retries", "prefilter_launches")
 
@@ -33,7 +36,7 @@ SIGNATURES = {
     "msb_ctx_sync": (ctypes.c_int, [c_vp]),
     "msb_ctx_timings": (ctypes.c_int, [c_vp, c_f64p, ctypes.c_int]),
     "msb_ctx_counters": (ctypes.c_int, [c_vp, c_i64p, ctypes.c_int]),
-    "msb_set_option": (ctypes.c_int, [ctypes.c_char_p, ctypes.c_int]),
+    "msb_ctx_set_option": (ctypes.c_int, [c_vp, ctypes.c_char_p, ctypes.c_int]),
     "msb_pinned_alloc": (ctypes.c_int, [ctypes.c_int64, ctypes.POINTER(c_vp)]),
     "msb_pinned_free": (ctypes.c_int, [c_vp]),
     "msb_motifs_create": (ctypes.c_int, [c_vp, ctypes.c_int32, c_i32p, c_f64p, c_i64p, c_f64p,
@@ -43,6 +46,9 @@ SIGNATURES = {
     "msb_motifs_max_raw": (ctypes.c_int, [c_vp, c_f64p]),
     "msb_motifs_destroy": (ctypes.c_int, [c_vp]),
     "msb_seqs_from_ascii": (ctypes.c_int, [c_vp, ctypes.c_int64, c_vp, c_i64p, ctypes.POINTER(c_vp)]),
+    "msb_seqs_from_packed": (ctypes.c_int, [c_vp, ctypes.c_int64, c_i64p, c_vp, c_vp, ctypes.c_int, ctypes.POINTER(c_vp)]),
+    "msb_seqs_wait": (ctypes.c_int, [c_vp]),
+    "msb_seqs_to_packed": (ctypes.c_int, [c_vp, c_vp, c_vp, c_vp]),
     "msb_seqs_extract": (ctypes.c_int, [c_vp, c_vp, ctypes.c_int64, c_i32p, c_i64p, c_i64p, ctypes.POINTER(c_vp)]),
     "msb_seqs_lengths": (ctypes.c_int, [c_vp, c_i64p]),
     "msb_seqs_window_ncount": (ctypes.c_int, [c_vp, c_vp, ctypes.c_int64, c_i32p, c_i64p, ctypes.c_int32, c_i32p]),
@@ -61,6 +67,9 @@ SIGNATURES = {
     "msb_scan_device": (ctypes.c_int, [c_vp, c_vp, c_vp, ctypes.c_int, ctypes.c_int, c_i64p]),
     "msb_scan_device_counts": (ctypes.c_int, [c_vp, c_i64p, ctypes.c_int32]),
     "msb_scan_device_region_counts": (ctypes.c_int, [c_vp, c_i64p, ctypes.c_int32]),
+    "msb_result_wait": (ctypes.c_int, [c_vp]),
+    "msb_merge_motif_major": (ctypes.c_int, [ctypes.c_int32, ctypes.c_int32, c_i64p, ctypes.POINTER(c_vp), c_vp,
+                                             ctypes.c_int32, c_i64p, ctypes.c_int32]),
     "msb_result_total": (ctypes.c_int, [c_vp, c_i64p]),
     "msb_result_counts": (ctypes.c_int, [c_vp, c_i64p]),
     "msb_result_arrays": (ctypes.c_int, [c_vp, ctypes.POINTER(c_i32p), ctypes.POINTER(c_i32p),

@@ -6,7 +6,11 @@ Same flags as the reference's subcommands (cli/main.py:407-430, 504-579) and the
     reference's registry format, config.py:15-117) or taken as a directory path when one exists;
   * `--loc`, `--plot` and the install / list / search subcommands (gene annotation, matplotlib,
     remote databases) are out of scope (SURVEY.md section 2 rows 7-9, 13) and exit with a message;
-  * `-t` is accepted and ignored: the device has no thread count.
+  * `-t` is accepted and ignored: the device has no thread count; `--gpus N` scans on the first N
+    GPUs of the box (one host thread and one context per GPU, results gathered in region order);
+  * control regions are always whole-background random (`generate_control_regions` without genes):
+    the gene-distance-matched branch of cli/scan.py needs the annotation layer, which is out of
+    scope -- when the genome directory holds an annotation file a warning says so;
 
     python -m motifscan_b200 scan -i peaks.bed -m <motif set> -g <genome> -o out_dir
     python -m motifscan_b200 motif --build <motif set> -g <genome>
@@ -70,8 +74,9 @@ def run_scan(args):
     pwms = load_built_pwms(args.motif, genome.name)
     regions = load_motifscan_regions(args.input_file, args.input_format)
     logger.info("===== Scanning motifs =====")
+    devices = _devices(args.n_gpus)
     common = dict(genome=genome, window_size=args.window_size, strand=args.strand, p_value=args.p_value,
-                  remove_dup=True, n_threads=args.n_threads)
+                  remove_dup=True, n_threads=args.n_threads, devices=devices)
     sites = Scanner(regions=regions, **common).scan_motifs(pwms)
     logger.info("Saving the result tables")
     msio.write_sites_table(args.output_dir, pwms, regions, sites)
@@ -82,6 +87,9 @@ def run_scan(args):
         if args.control_file:
             controls = load_motifscan_regions(args.control_file, args.control_format)
         else:
+            if genome.path and any(f.endswith(("_gene_annotation.txt", "refGene.txt")) for f in os.listdir(genome.path)):
+                logger.warning("gene annotation found but unused: control regions are drawn from the whole "
+                               "background, not matched by gene distance as the reference does (out of scope)")
             controls = generate_control_regions(args.n_random, regions, genome.chrom_sizes, random_seed=args.seed)
         control_sites = Scanner(regions=controls, **common).scan_motifs(pwms)
         msio.write_enrich_table(args.output_dir, motif_enrichment(pwms, sites, control_sites))
@@ -108,6 +116,16 @@ def run_motif(args):
     pwms.write_motifscan_pwms(pwms_path(motif_dir, short, genome.name))
     logger.info("Successfully built!")
     return 0
+
+
+def _devices(n_gpus):
+    """`--gpus N`: the first N CUDA devices of this process (the reference's `-t` pool, cli/main.py:427-430,
+    565-568, becomes one host thread per GPU); more than there are is an error, not a silent clamp."""
+    from . import _lib
+    have = _lib.device_count()
+    if n_gpus > have:
+        raise SystemExit(f"motifscan: error: --gpus {n_gpus} but only {have} CUDA device(s) are visible")
+    return list(range(n_gpus))
 
 
 def _non_negative(text):
@@ -145,6 +163,8 @@ def make_parser():
     scan.add_argument("-c", dest="control_file", metavar="FILE")
     scan.add_argument("--cf", dest="control_format", choices=sorted(REGION_FORMATS), default="bed")
     scan.add_argument("-t", "--threads", dest="n_threads", type=int, default=1)
+    scan.add_argument("--gpus", dest="n_gpus", type=_positive, default=1, metavar="N",
+                      help="GPUs of this box to scan on (regions are dealt to them in contiguous blocks)")
     scan.add_argument("-o", "--output-dir", dest="output_dir", required=True, metavar="DIR")
     scan.add_argument("--site", dest="report_site", action="store_true")
     scan.add_argument("--plot", dest="plot_dist", action="store_true")

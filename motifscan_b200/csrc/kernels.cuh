@@ -110,6 +110,34 @@ extract_pack_kernel(SeqView src, const int32_t *__restrict__ src_idx, const int6
     blk_seq[b] = (int32_t) s;
 }
 
+// Sequences uploaded in the packed representation (msb_seqs_from_packed) -> canonical form: bits behind a
+// sequence's last base cleared in both planes, codes of non-ACGT bases cleared (N -> 0), block owners filled in.
+__device__ __forceinline__ uint32_t spread_bits16(uint32_t x) {   // bit i of the low half -> bit 2 i
+    x = (x | (x << 8)) & 0x00FF00FFu;
+    x = (x | (x << 4)) & 0x0F0F0F0Fu;
+    x = (x | (x << 2)) & 0x33333333u;
+    x = (x | (x << 1)) & 0x55555555u;
+    return x;
+}
+__global__ void __launch_bounds__(256)
+packed_fixup_kernel(const int64_t *__restrict__ poff, const int32_t *__restrict__ len, int64_t n_seqs,
+                    int64_t n_blocks, uint32_t *__restrict__ codes, uint32_t *__restrict__ nmask,
+                    int32_t *__restrict__ blk_seq) {
+    const int64_t b = (int64_t) blockIdx.x * blockDim.x + threadIdx.x;
+    if (b >= n_blocks) return;
+    const int64_t p = b * kPadBases;
+    const int64_t s = find_seq(poff, n_seqs, p);
+    const int64_t left = (int64_t) __ldg(len + s) - (p - __ldg(poff + s));
+    const int n = left >= kPadBases ? kPadBases : (left > 0 ? (int) left : 0);
+    const uint32_t valid = n >= 32 ? 0xffffffffu : ((1u << n) - 1u);
+    const uint32_t mask = nmask[b] & valid;
+    const uint32_t acgt = valid & ~mask;   // bases whose code counts
+    codes[2 * b] &= 3u * spread_bits16(acgt & 0xffffu);
+    codes[2 * b + 1] &= 3u * spread_bits16(acgt >> 16);
+    nmask[b] = mask;
+    blk_seq[b] = (int32_t) s;
+}
+
 // Number of non-ACGT bases in each of n windows [start, start + length) of a resident set (the
 // acceptance test of the background sampler, genome/__init__.py:172-175, counts the N of a sample).
 // One thread per window; the window is clipped at its sequence's end.
@@ -599,6 +627,27 @@ motif_offsets_kernel(const uint64_t *__restrict__ key, int64_t n, int32_t n_moti
         if ((int64_t) site_motif(__ldg(key + mid), key_shift) < (int64_t) m) lo = mid + 1; else hi = mid;
     }
     offsets[m] = lo;
+}
+
+// MSB_SCAN_COUNTS: per-motif site counts straight from the unsorted hit keys (a block-private histogram in
+// shared memory when the motif set fits, flushed with one global atomic per non-empty bin).
+__global__ void __launch_bounds__(256)
+count_hits_kernel(const uint64_t *__restrict__ key, int64_t n, int key_shift, int32_t n_motifs, int in_smem,
+                  unsigned long long *__restrict__ counts) {
+    extern __shared__ unsigned int s_hist[];
+    if (in_smem) {
+        for (int32_t m = threadIdx.x; m < n_motifs; m += blockDim.x) s_hist[m] = 0;
+        __syncthreads();
+    }
+    for (int64_t i = (int64_t) blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t) gridDim.x * blockDim.x) {
+        const uint32_t m = site_motif(__ldg(key + i), key_shift);
+        if (in_smem) atomicAdd(s_hist + m, 1u); else atomicAdd(counts + m, 1ull);
+    }
+    if (in_smem) {
+        __syncthreads();
+        for (int32_t m = threadIdx.x; m < n_motifs; m += blockDim.x)
+            if (s_hist[m]) atomicAdd(counts + m, (unsigned long long) s_hist[m]);
+    }
 }
 
 // Per motif, the number of sequences with at least one site (what motif_enrichment counts,

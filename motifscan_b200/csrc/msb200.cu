@@ -18,6 +18,7 @@
 #include <mutex>
 #include <new>
 #include <numeric>
+#include <thread>
 
 #include "kernels.cuh"
 #include "prefilter_tc.cuh"
@@ -74,10 +75,20 @@ struct msb_ctx {
     int64_t c[MSB_C_COUNT] = {};
     // scratch (grow-only, reused across calls)
     DevBuf ascii, seq_off, cand, dirty, hit_key, hit_score, key_alt, score_alt, sort_tmp, counters;
-    DevBuf out_seq, out_start, out_strand, out_counts, scores, scores_sorted, seg_off, ranks, sel;
-    DevBuf keep, keep_pos, out2_seq, out2_start, out2_strand;
+    DevBuf out_seq, out_start, out_strand, scores, scores_sorted, seg_off, ranks, sel;
+    DevBuf keep, keep_pos, motif_counts;
     DevBuf lane_count;   // tensor-core prefilter: records per epilogue lane
-    // final site arrays of the last scan (point into the buffers above)
+    // Final site arrays of a scan.  Two sets, used alternately: the device-to-host copy of scan k's
+    // sites (on d2h_stream, MSB_SCAN_ASYNC) reads one set while scan k + 1 fills the other.
+    struct FinSet {
+        DevBuf key, score, seq, start, strand, offsets;   // offsets: CSR over motifs, n_motifs + 1 entries
+        cudaEvent_t read_done = nullptr;                  // recorded on d2h_stream behind the copies that read this set
+        bool pending = false;
+    } fin[2];
+    int fin_cur = 0;
+    bool last_counts_only = false;
+    cudaStream_t d2h_stream = nullptr;
+    // final site arrays of the last scan (point into fin[fin_cur])
     uint64_t *fin_key = nullptr;
     double *fin_score = nullptr;
     int32_t *fin_seq = nullptr, *fin_start = nullptr;
@@ -91,6 +102,14 @@ struct msb_ctx {
     int64_t last_sites = 0;
     int32_t last_n_motifs = 0;
     int last_key_shift = 0;
+    // tuning / test knobs (msb_ctx_set_option): per context, so that contexts driven from different host
+    // threads never see each other's settings
+    int opt_prefilter_tc = 1;        // 1: tensor-core prefilter (prefilter_tc.cuh), 0: shared-memory table prefilter
+    int opt_prefilter_w = 4;         // windows per thread of the table prefilter (4 or 8)
+    int opt_tc_prof = 0;             // 1: print per-role cycle counters of the tensor-core prefilter to stderr
+    int opt_ascii_slices = 4;        // msb_scan_ascii: upload slices (1..7)
+    int opt_tc_first_lane_cap = 0;   // tests: records per lane buffer on the first attempt (0 = sized from the input)
+    int opt_poison_pool = 0;         // tests: fill device buffers with 0xFF when they go back to the pool
 };
 
 struct TableSet {
@@ -151,6 +170,11 @@ struct msb_seqs {
     std::vector<int64_t> seq_off, poff;
     DevBuf d_codes, d_nmask, d_poff, d_len, d_seq_off, d_blk_seq, d_limit;
     bool has_limit = false;
+    std::vector<int32_t> lens32;          // host copy of d_len (source of an asynchronous upload)
+    // MSB_SEQS_ASYNC: the upload runs on the context's copy stream; the first call that reads the set makes
+    // the main stream wait for `ready`
+    mutable cudaEvent_t ready = nullptr;
+    mutable bool ready_pending = false;
     SeqView view() const {
         SeqView v;
         v.codes = d_codes.as<uint32_t>();
@@ -167,14 +191,18 @@ struct msb_seqs {
 
 struct msb_result {
     msb_ctx *ctx = nullptr;
+    int device = 0;
     int64_t n_sites = 0;
     int32_t n_motifs = 0;
-    PinnedBlock block;
+    PinnedBlock block;       // score (8n) | seq_idx (4n) | start (4n) | strand (n) | pad | motif offsets (8 (n_motifs + 1))
     int32_t *seq_idx = nullptr;
     int32_t *start = nullptr;
     double *score = nullptr;
     int8_t *strand = nullptr;
+    int64_t *offsets = nullptr;
     std::vector<int64_t> counts;
+    cudaEvent_t t0 = nullptr, done = nullptr;   // on the context's d2h stream around the copies
+    bool pending = false;                       // MSB_SCAN_ASYNC: the copies may still be in flight
 };
 
 // ------------------------------------------------------------------------------------------------
@@ -227,6 +255,7 @@ static int dev_take(msb_ctx *ctx, DevBuf &b, size_t bytes) {
 }
 static void dev_give(msb_ctx *ctx, DevBuf &b) {
     if (!b.p) return;
+    if (ctx->opt_poison_pool) cudaMemsetAsync(b.p, 0xFF, b.cap, ctx->stream);
     std::lock_guard<std::mutex> g(ctx->dev_mu);
     if (ctx->dev_free.size() < 24) {
         ctx->dev_free.push_back(b);
@@ -235,6 +264,20 @@ static void dev_give(msb_ctx *ctx, DevBuf &b) {
     } else {
         b.release();
     }
+}
+
+static int ensure_copy_stream(msb_ctx *ctx) {
+    if (!ctx->copy_stream) MSB_CUDA(cudaStreamCreateWithFlags(&ctx->copy_stream, cudaStreamNonBlocking));
+    return MSB_OK;
+}
+
+// An asynchronously uploaded sequence set becomes readable on the main stream behind its `ready` event.
+static int seqs_ready(const msb_seqs *S) {
+    if (S && S->ready_pending) {
+        MSB_CUDA(cudaStreamWaitEvent(S->ctx->stream, S->ready, 0));
+        S->ready_pending = false;
+    }
+    return MSB_OK;
 }
 
 static inline float ev_ms(cudaEvent_t a, cudaEvent_t b) {
@@ -305,6 +348,7 @@ int msb_ctx_create(int device, void *stream, msb_ctx **out) {
         msb_ctx_destroy(ctx);
         return MSB_ENOMEM;
     }
+    ctx->opt_tc_prof = std::getenv("MSB_TC_PROF") ? 1 : 0;
     cudaFuncSetAttribute(prefilter_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) ctx->smem_optin);
     cudaFuncSetAttribute(prefilter_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) ctx->smem_optin);
     cudaFuncSetAttribute(prefilter_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kTcSmemBytes);
@@ -319,10 +363,16 @@ int msb_ctx_destroy(msb_ctx *ctx) {
     cudaStreamSynchronize(ctx->stream);
     for (DevBuf *b : {&ctx->ascii, &ctx->seq_off, &ctx->cand, &ctx->dirty, &ctx->hit_key, &ctx->hit_score,
                       &ctx->key_alt, &ctx->score_alt, &ctx->sort_tmp, &ctx->counters, &ctx->out_seq,
-                      &ctx->out_start, &ctx->out_strand, &ctx->out_counts, &ctx->scores,
+                      &ctx->out_start, &ctx->out_strand, &ctx->scores,
                       &ctx->scores_sorted, &ctx->seg_off, &ctx->ranks, &ctx->sel, &ctx->keep, &ctx->keep_pos,
-                      &ctx->out2_seq, &ctx->out2_start, &ctx->out2_strand, &ctx->lane_count})
+                      &ctx->motif_counts, &ctx->lane_count})
         b->release();
+    if (ctx->d2h_stream) cudaStreamSynchronize(ctx->d2h_stream);
+    for (auto &f : ctx->fin) {
+        for (DevBuf *b : {&f.key, &f.score, &f.seq, &f.start, &f.strand, &f.offsets}) b->release();
+        if (f.read_done) cudaEventDestroy(f.read_done);
+    }
+    if (ctx->d2h_stream) cudaStreamDestroy(ctx->d2h_stream);
     for (auto &b : ctx->pinned_free) cudaFreeHost(b.p);
     for (auto &b : ctx->dev_free) b.release();
     if (ctx->h_counters) cudaFreeHost(ctx->h_counters);
@@ -503,7 +553,7 @@ int msb_motifs_destroy(msb_motifs *M) {
 // the per-sequence tables and clear the code / mask planes (the kernels that read windows rely on
 // zero padding behind the last block).  `seq_off` holds the n_seqs + 1 cumulative lengths.
 static int seqs_prepare(msb_ctx *ctx, int64_t n_seqs, const int64_t *seq_off, msb_seqs **out,
-                        std::vector<int32_t> &lens) {
+                        std::vector<int32_t> &lens, cudaStream_t on_stream = nullptr) {
     msb_seqs *S = new (std::nothrow) msb_seqs();
     if (!S) { set_error("out of host memory"); return MSB_ENOMEM; }
     S->ctx = ctx;
@@ -539,11 +589,14 @@ static int seqs_prepare(msb_ctx *ctx, int64_t n_seqs, const int64_t *seq_off, ms
         msb_seqs_destroy(S);
         return rc;
     }
-    cudaStream_t st = ctx->stream;
+    cudaStream_t st = on_stream ? on_stream : ctx->stream;
     cudaError_t e = cudaSuccess;
     auto step = [&](cudaError_t x) { if (e == cudaSuccess) e = x; };
     step(cudaMemsetAsync(S->d_codes.p, 0, (size_t) (2 * n_blocks + 8) * 4, st));
     step(cudaMemsetAsync(S->d_nmask.p, 0, (size_t) (n_blocks + 4) * 4, st));
+    // the owner table comes out of the recycled pool too: msb_scan_ascii scans slice k before slice k + 1 is
+    // encoded, and a position tile may reach into the next slice's blocks
+    step(cudaMemsetAsync(S->d_blk_seq.p, 0, (size_t) std::max<int64_t>(n_blocks, 1) * 4, st));
     step(cudaMemcpyAsync(S->d_poff.p, S->poff.data(), (size_t) (n_seqs + 1) * 8, cudaMemcpyHostToDevice, st));
     step(cudaMemcpyAsync(S->d_seq_off.p, S->seq_off.data(), (size_t) (n_seqs + 1) * 8, cudaMemcpyHostToDevice, st));
     if (n_seqs) step(cudaMemcpyAsync(S->d_len.p, lens.data(), (size_t) n_seqs * 4, cudaMemcpyHostToDevice, st));
@@ -602,6 +655,77 @@ int msb_seqs_from_ascii(msb_ctx *ctx, int64_t n_seqs, const char *bytes, const i
     return MSB_OK;
 }
 
+int msb_seqs_from_packed(msb_ctx *ctx, int64_t n_seqs, const int64_t *lens, const uint32_t *codes,
+                         const uint32_t *nmask, int flags, msb_seqs **out) {
+    if (!ctx || !out || n_seqs < 0 || (n_seqs > 0 && !lens)) { set_error("msb_seqs_from_packed: bad argument"); return MSB_EINVAL; }
+    *out = nullptr;
+    std::vector<int64_t> seq_off((size_t) n_seqs + 1, 0);
+    for (int64_t i = 0; i < n_seqs; i++) {
+        if (lens[i] < 0 || lens[i] > (int64_t) 0x7fffffff - 64) { set_error("msb_seqs_from_packed: sequence length out of range"); return MSB_EINVAL; }
+        seq_off[i + 1] = seq_off[i] + lens[i];
+    }
+    if (seq_off[n_seqs] > 0 && (!codes || !nmask)) { set_error("msb_seqs_from_packed: null planes"); return MSB_EINVAL; }
+    MSB_CUDA(cudaSetDevice(ctx->device));
+    const bool async = (flags & MSB_SEQS_ASYNC) != 0;
+    if (async) MSB_TRY(ensure_copy_stream(ctx));
+    cudaStream_t st = async ? ctx->copy_stream : ctx->stream;
+    if (!async) MSB_CUDA(cudaEventRecord(ctx->ev[0], st));
+    msb_seqs *S = nullptr;
+    {
+        std::vector<int32_t> l32;
+        MSB_TRY(seqs_prepare(ctx, n_seqs, seq_off.data(), &S, l32, st));
+        S->lens32.swap(l32);   // seqs_prepare's copy of the lengths reads this vector: it lives as long as the set
+    }
+    const int64_t n_blocks = S->total_packed / kPadBases;
+    cudaError_t e = cudaSuccess;
+    auto step = [&](cudaError_t x) { if (e == cudaSuccess) e = x; };
+    if (n_blocks) {
+        step(cudaMemcpyAsync(S->d_codes.p, codes, (size_t) n_blocks * 8, cudaMemcpyHostToDevice, st));
+        step(cudaMemcpyAsync(S->d_nmask.p, nmask, (size_t) n_blocks * 4, cudaMemcpyHostToDevice, st));
+    }
+    if (!async) step(cudaEventRecord(ctx->ev[1], st));
+    if (e == cudaSuccess && n_blocks > 0) {
+        packed_fixup_kernel<<<(unsigned) ((n_blocks + 255) / 256), 256, 0, st>>>(
+            S->d_poff.as<int64_t>(), S->d_len.as<int32_t>(), n_seqs, n_blocks, S->d_codes.as<uint32_t>(),
+            S->d_nmask.as<uint32_t>(), S->d_blk_seq.as<int32_t>());
+        step(cudaGetLastError());
+    }
+    if (async) {
+        if (e == cudaSuccess) e = cudaEventCreateWithFlags(&S->ready, cudaEventDisableTiming);
+        step(cudaEventRecord(S->ready, st));
+        if (e == cudaSuccess) S->ready_pending = true;
+    } else {
+        step(cudaEventRecord(ctx->ev[2], st));
+        step(cudaStreamSynchronize(st));   // the caller's planes may go away after return
+    }
+    if (e != cudaSuccess) { msb_seqs_destroy(S); return cuda_fail(e, "msb_seqs_from_packed", __FILE__, __LINE__); }
+    if (!async) {
+        ctx->t[MSB_T_H2D] = ev_ms(ctx->ev[0], ctx->ev[1]);
+        ctx->t[MSB_T_ENCODE] = ev_ms(ctx->ev[1], ctx->ev[2]);
+    }
+    *out = S;
+    return MSB_OK;
+}
+
+int msb_seqs_wait(const msb_seqs *S) {
+    if (!S) { set_error("null seqs"); return MSB_EINVAL; }
+    if (S->ready) { MSB_CUDA(cudaSetDevice(S->ctx->device)); MSB_CUDA(cudaEventSynchronize(S->ready)); }
+    return MSB_OK;
+}
+
+int msb_seqs_to_packed(msb_ctx *ctx, const msb_seqs *S, uint32_t *codes, uint32_t *nmask) {
+    if (!ctx || !S) { set_error("msb_seqs_to_packed: null"); return MSB_EINVAL; }
+    const int64_t n_blocks = S->total_packed / kPadBases;
+    if (n_blocks == 0) return MSB_OK;
+    if (!codes || !nmask) { set_error("msb_seqs_to_packed: null planes"); return MSB_EINVAL; }
+    MSB_CUDA(cudaSetDevice(ctx->device));
+    MSB_TRY(seqs_ready(S));
+    MSB_CUDA(cudaMemcpyAsync(codes, S->d_codes.p, (size_t) n_blocks * 8, cudaMemcpyDeviceToHost, ctx->stream));
+    MSB_CUDA(cudaMemcpyAsync(nmask, S->d_nmask.p, (size_t) n_blocks * 4, cudaMemcpyDeviceToHost, ctx->stream));
+    MSB_CUDA(cudaStreamSynchronize(ctx->stream));
+    return MSB_OK;
+}
+
 int msb_seqs_extract(msb_ctx *ctx, const msb_seqs *src, int64_t n, const int32_t *src_idx,
                      const int64_t *start, const int64_t *end, msb_seqs **out) {
     if (!ctx || !src || !out || n < 0 || (n > 0 && (!src_idx || !start || !end))) {
@@ -610,6 +734,7 @@ int msb_seqs_extract(msb_ctx *ctx, const msb_seqs *src, int64_t n, const int32_t
     }
     *out = nullptr;
     if (src->ctx != ctx) { set_error("msb_seqs_extract: source belongs to another context"); return MSB_EINVAL; }
+    MSB_TRY(seqs_ready(src));
     // pysam's fetch (genome/__init__.py:135) clips `end` at the sequence length; an interval that
     // starts behind it, or is reversed, is empty.
     std::vector<int64_t> seq_off((size_t) n + 1, 0), clipped_start((size_t) std::max<int64_t>(n, 1), 0);
@@ -666,6 +791,7 @@ int msb_seqs_window_ncount(msb_ctx *ctx, const msb_seqs *src, int64_t n, const i
         return MSB_EINVAL;
     }
     if (src->ctx != ctx) { set_error("msb_seqs_window_ncount: source belongs to another context"); return MSB_EINVAL; }
+    MSB_TRY(seqs_ready(src));
     for (int64_t i = 0; i < n; i++)
         if (src_idx[i] < 0 || src_idx[i] >= src->n || start[i] < 0) { set_error("msb_seqs_window_ncount: window out of range"); return MSB_EINVAL; }
     if (n == 0) return MSB_OK;
@@ -715,6 +841,7 @@ int msb_seqs_codes(msb_ctx *ctx, const msb_seqs *S, int8_t *codes) {
     if (!ctx || !S || (!codes && S->total_bp)) { set_error("msb_seqs_codes: null"); return MSB_EINVAL; }
     if (S->total_bp == 0) return MSB_OK;
     MSB_CUDA(cudaSetDevice(ctx->device));
+    MSB_TRY(seqs_ready(S));
     DevBuf tmp;
     MSB_TRY(tmp.ensure((size_t) S->total_bp));
     const int64_t grid = (S->total_packed + 255) / 256;
@@ -730,6 +857,7 @@ int msb_seqs_codes(msb_ctx *ctx, const msb_seqs *S, int8_t *codes) {
 int msb_seqs_destroy(msb_seqs *S) {
     if (!S) return MSB_OK;
     cudaSetDevice(S->ctx->device);
+    if (S->ready) { cudaEventSynchronize(S->ready); cudaEventDestroy(S->ready); }
     cudaStreamSynchronize(S->ctx->stream);
     for (DevBuf *b : {&S->d_codes, &S->d_nmask, &S->d_poff, &S->d_len, &S->d_seq_off, &S->d_blk_seq, &S->d_limit}) dev_give(S->ctx, *b);
     delete S;
@@ -1097,12 +1225,6 @@ static int launch_positions(msb_ctx *ctx, const ExactParams &E, const int64_t *p
     return MSB_OK;
 }
 
-static int g_prefilter_w = 4;   // windows per thread of the table prefilter (4 or 8)
-static int g_tc_prof = std::getenv("MSB_TC_PROF") ? 1 : 0;   // 1: print per-role cycle counters of the tensor-core prefilter to stderr
-static int g_ascii_slices = 4;       // msb_scan_ascii: upload slices (1..7)
-static int g_tc_first_lane_cap = 0;  // tests: records per lane buffer on the first attempt (0 = sized from the input)
-static int g_prefilter_tc = 1;  // 1: tensor-core prefilter (prefilter_tc.cuh), 0: shared-memory table prefilter
-
 // Packed-position ranges [lo, hi) of a range scan; nullptr = the whole sequence set.
 typedef std::vector<std::pair<int64_t, int64_t>> RangeList;
 
@@ -1133,7 +1255,8 @@ static int scan_device(msb_ctx *ctx, msb_motifs *M, const msb_seqs *S, int stran
     if (strand < 1 || strand > 3) { set_error("msb_scan: strand must be 1, 2 or 3"); return MSB_EINVAL; }
     if (M->ctx != ctx || S->ctx != ctx) { set_error("msb_scan: motifs/seqs belong to another context"); return MSB_EINVAL; }
     MSB_CUDA(cudaSetDevice(ctx->device));
-    const bool use_tc = g_prefilter_tc != 0;
+    MSB_TRY(seqs_ready(S));
+    const bool use_tc = ctx->opt_prefilter_tc != 0;
     if (ranges && !use_tc) { set_error("msb_scan_ranges needs the tensor-core prefilter (prefilter_tc = 1)"); return MSB_EINVAL; }
     RangeList whole;
     if (!ranges) {
@@ -1156,10 +1279,19 @@ static int scan_device(msb_ctx *ctx, msb_motifs *M, const msb_seqs *S, int stran
     std::fill(ctx->c, ctx->c + MSB_C_COUNT, 0);
     ctx->last_sites = 0;
     ctx->last_n_motifs = M->n;
-    MSB_TRY(ctx->out_counts.ensure((size_t) (M->n + 1) * 8));  // CSR offsets over motifs
-    MSB_CUDA(cudaMemsetAsync(ctx->out_counts.p, 0, (size_t) (M->n + 1) * 8, st));
+    // this scan's final arrays go to the set the previous scan did not use; a copy that still reads it
+    // (an asynchronous result two scans back) is waited for on the device, not on the host
+    const int fin_set = ctx->fin_cur ^ 1;
+    msb_ctx::FinSet &F = ctx->fin[fin_set];
+    if (F.pending) { MSB_CUDA(cudaStreamWaitEvent(st, F.read_done, 0)); F.pending = false; }
+    const bool counts_only = (flags & MSB_SCAN_COUNTS) && !(flags & MSB_SCAN_DEDUP);
+    MSB_TRY(F.offsets.ensure((size_t) (M->n + 1) * 8));  // CSR offsets over motifs
+    MSB_CUDA(cudaMemsetAsync(F.offsets.p, 0, (size_t) (M->n + 1) * 8, st));
+    ctx->fin_key = nullptr;
     if (M->n == 0 || span == 0) {
         MSB_CUDA(cudaStreamSynchronize(st));
+        ctx->fin_cur = fin_set;
+        ctx->last_counts_only = counts_only;
         return MSB_OK;
     }
     const SeqView sv = S->view();
@@ -1196,7 +1328,7 @@ static int scan_device(msb_ctx *ctx, msb_motifs *M, const msb_seqs *S, int stran
             P.lmax_all = std::max(lmax_fast, 1);
             P.any_zero_hit = any_zero_hit;
             lane_cap = std::max<int64_t>(cand_cap / 2 / n_lanes, 1);   // 16-byte records per lane buffer
-            if (attempt == 0 && g_tc_first_lane_cap > 0) lane_cap = std::min<int64_t>(lane_cap, g_tc_first_lane_cap);
+            if (attempt == 0 && ctx->opt_tc_first_lane_cap > 0) lane_cap = std::min<int64_t>(lane_cap, ctx->opt_tc_first_lane_cap);
             MSB_TRY(ctx->lane_count.ensure((size_t) n_lanes * 4));
             MSB_CUDA(cudaMemsetAsync(ctx->lane_count.p, 0, (size_t) n_lanes * 4, st));
             P.cand = ctx->cand.as<uint4>();
@@ -1207,7 +1339,7 @@ static int scan_device(msb_ctx *ctx, msb_motifs *M, const msb_seqs *S, int stran
             P.counters = ctx->counters.as<unsigned long long>();
             P.prof = nullptr;
             DevBuf prof;
-            if (g_tc_prof) {
+            if (ctx->opt_tc_prof) {
                 MSB_TRY(prof.ensure((size_t) (ctx->sm_count + 16) * 16 * 8));
                 MSB_CUDA(cudaMemsetAsync(prof.p, 0, (size_t) (ctx->sm_count + 16) * 16 * 8, st));
                 P.prof = prof.as<long long>();
@@ -1224,7 +1356,7 @@ static int scan_device(msb_ctx *ctx, msb_motifs *M, const msb_seqs *S, int stran
                 for (size_t b = 0; b < TT->batches.size(); b++) {
                     P.batch = TT->batches[b];
                     P.emit_dirty = (b == 0);
-                    if (g_tc_prof) prefilter_tc_kernel<true><<<grid, kTcThreads, smem, st>>>(P);
+                    if (ctx->opt_tc_prof) prefilter_tc_kernel<true><<<grid, kTcThreads, smem, st>>>(P);
                     else prefilter_tc_kernel<false><<<grid, kTcThreads, smem, st>>>(P);
                     MSB_CUDA(cudaGetLastError());
                     ctx->c[MSB_C_LAUNCHES]++;
@@ -1235,7 +1367,7 @@ static int scan_device(msb_ctx *ctx, msb_motifs *M, const msb_seqs *S, int stran
                                                    ctx->counters.as<unsigned long long>());
             MSB_CUDA(cudaGetLastError());
             ctx->c[MSB_C_LAUNCHES]++;
-            if (g_tc_prof) {
+            if (ctx->opt_tc_prof) {
                 std::vector<long long> h((size_t) (ctx->sm_count + 16) * 16);
                 MSB_CUDA(cudaMemcpyAsync(h.data(), prof.p, h.size() * 8, cudaMemcpyDeviceToHost, st));
                 MSB_CUDA(cudaStreamSynchronize(st));
@@ -1271,7 +1403,7 @@ static int scan_device(msb_ctx *ctx, msb_motifs *M, const msb_seqs *S, int stran
             P.batch = T->batches[b];
             P.emit_dirty = (b == 0);
             const size_t smem = (size_t) P.batch.tab_words * 4;
-            if (g_prefilter_w == 8)
+            if (ctx->opt_prefilter_w == 8)
                 prefilter_kernel<8><<<ctx->sm_count, PF<8>::kThreads, smem, st>>>(P);
             else
                 prefilter_kernel<4><<<ctx->sm_count, PF<4>::kThreads, smem, st>>>(P);
@@ -1357,51 +1489,69 @@ static int scan_device(msb_ctx *ctx, msb_motifs *M, const msb_seqs *S, int stran
     ctx->c[MSB_C_HITS] = n_hits;
 
     // ---- stage 3: order (motif, sequence, start, fwd < rev), decode, optional de-duplication ----
-    ctx->fin_key = nullptr;
     int64_t n_final = n_hits;
-    if (n_hits) {
-        MSB_TRY(ctx->key_alt.ensure((size_t) n_hits * 8));
-        MSB_TRY(ctx->score_alt.ensure((size_t) n_hits * 8));
-        MSB_TRY(ctx->out_seq.ensure((size_t) n_hits * 4));
-        MSB_TRY(ctx->out_start.ensure((size_t) n_hits * 4));
-        MSB_TRY(ctx->out_strand.ensure((size_t) n_hits));
+    if (counts_only) {
+        // MSB_SCAN_COUNTS: nobody will look at the sites -- a histogram of the keys' motif field replaces
+        // the sort, the decode and the site arrays
+        MSB_TRY(ctx->motif_counts.ensure((size_t) (M->n + 1) * 8));
+        MSB_CUDA(cudaMemsetAsync(ctx->motif_counts.p, 0, (size_t) (M->n + 1) * 8, st));
+        if (n_hits) {
+            const bool in_smem = (size_t) M->n * 4 <= 40 * 1024;
+            const unsigned grid = (unsigned) std::min<int64_t>((n_hits + 2047) / 2048, (int64_t) ctx->sm_count * 8);
+            count_hits_kernel<<<grid, 256, in_smem ? (size_t) M->n * 4 : 0, st>>>(
+                ctx->hit_key.as<uint64_t>(), n_hits, key_shift, M->n, in_smem ? 1 : 0, ctx->motif_counts.as<unsigned long long>());
+            MSB_CUDA(cudaGetLastError());
+            ctx->c[MSB_C_LAUNCHES]++;
+        }
+        size_t scan_bytes = 0;
+        MSB_CUDA(cub::DeviceScan::ExclusiveSum(nullptr, scan_bytes, ctx->motif_counts.as<int64_t>(), F.offsets.as<int64_t>(), M->n + 1, st));
+        MSB_TRY(ctx->sort_tmp.ensure(std::max<size_t>(scan_bytes, 16)));
+        MSB_CUDA(cub::DeviceScan::ExclusiveSum(ctx->sort_tmp.p, scan_bytes, ctx->motif_counts.as<int64_t>(), F.offsets.as<int64_t>(), M->n + 1, st));
+    } else if (n_hits) {
+        const bool dedup = (flags & MSB_SCAN_DEDUP) != 0;
+        // without de-duplication the sorted arrays ARE the final ones; with it they are scratch and the
+        // survivors are scattered into the final set
+        DevBuf &s_key = dedup ? ctx->key_alt : F.key, &s_score = dedup ? ctx->score_alt : F.score;
+        DevBuf &s_seq = dedup ? ctx->out_seq : F.seq, &s_start = dedup ? ctx->out_start : F.start;
+        DevBuf &s_strand = dedup ? ctx->out_strand : F.strand;
+        MSB_TRY(s_key.ensure((size_t) n_hits * 8));
+        MSB_TRY(s_score.ensure((size_t) n_hits * 8));
+        MSB_TRY(s_seq.ensure((size_t) n_hits * 4));
+        MSB_TRY(s_start.ensure((size_t) n_hits * 4));
+        MSB_TRY(s_strand.ensure((size_t) n_hits));
         const int end_bit = key_shift + motif_bits;
         size_t tmp_bytes = 0;
-        MSB_CUDA(cub::DeviceRadixSort::SortPairs(nullptr, tmp_bytes, ctx->hit_key.as<uint64_t>(), ctx->key_alt.as<uint64_t>(),
-                                                 ctx->hit_score.as<double>(), ctx->score_alt.as<double>(), n_hits, 0, end_bit, st));
+        MSB_CUDA(cub::DeviceRadixSort::SortPairs(nullptr, tmp_bytes, ctx->hit_key.as<uint64_t>(), s_key.as<uint64_t>(),
+                                                 ctx->hit_score.as<double>(), s_score.as<double>(), n_hits, 0, end_bit, st));
         MSB_TRY(ctx->sort_tmp.ensure(std::max<size_t>(tmp_bytes, 16)));
-        MSB_CUDA(cub::DeviceRadixSort::SortPairs(ctx->sort_tmp.p, tmp_bytes, ctx->hit_key.as<uint64_t>(), ctx->key_alt.as<uint64_t>(),
-                                                 ctx->hit_score.as<double>(), ctx->score_alt.as<double>(), n_hits, 0, end_bit, st));
+        MSB_CUDA(cub::DeviceRadixSort::SortPairs(ctx->sort_tmp.p, tmp_bytes, ctx->hit_key.as<uint64_t>(), s_key.as<uint64_t>(),
+                                                 ctx->hit_score.as<double>(), s_score.as<double>(), n_hits, 0, end_bit, st));
         const unsigned grid = (unsigned) ((n_hits + 255) / 256);
-        decode_sites_kernel<<<grid, 256, 0, st>>>(sv, ctx->key_alt.as<uint64_t>(), n_hits, key_shift, ctx->out_seq.as<int32_t>(),
-                                                  ctx->out_start.as<int32_t>(), ctx->out_strand.as<int8_t>());
+        decode_sites_kernel<<<grid, 256, 0, st>>>(sv, s_key.as<uint64_t>(), n_hits, key_shift, s_seq.as<int32_t>(),
+                                                  s_start.as<int32_t>(), s_strand.as<int8_t>());
         MSB_CUDA(cudaGetLastError());
         ctx->c[MSB_C_LAUNCHES] += 2;  // sort (several CUB kernels, counted once) + decode
-        ctx->fin_key = ctx->key_alt.as<uint64_t>();
-        ctx->fin_score = ctx->score_alt.as<double>();
-        ctx->fin_seq = ctx->out_seq.as<int32_t>();
-        ctx->fin_start = ctx->out_start.as<int32_t>();
-        ctx->fin_strand = ctx->out_strand.as<int8_t>();
-        if (flags & MSB_SCAN_DEDUP) {
+        if (dedup) {
             // scanner.py:171-193 on the device: keep flags, exclusive scan, scatter.
             MSB_TRY(ctx->keep.ensure((size_t) n_hits * 4));
             MSB_TRY(ctx->keep_pos.ensure((size_t) n_hits * 8));
-            MSB_TRY(ctx->out2_seq.ensure((size_t) n_hits * 4));
-            MSB_TRY(ctx->out2_start.ensure((size_t) n_hits * 4));
-            MSB_TRY(ctx->out2_strand.ensure((size_t) n_hits));
-            dedup_flags_kernel<<<grid, 256, 0, st>>>(ctx->fin_key, ctx->fin_seq, ctx->fin_start, ctx->fin_strand, ctx->fin_score,
+            MSB_TRY(F.key.ensure((size_t) n_hits * 8));
+            MSB_TRY(F.score.ensure((size_t) n_hits * 8));
+            MSB_TRY(F.seq.ensure((size_t) n_hits * 4));
+            MSB_TRY(F.start.ensure((size_t) n_hits * 4));
+            MSB_TRY(F.strand.ensure((size_t) n_hits));
+            dedup_flags_kernel<<<grid, 256, 0, st>>>(s_key.as<uint64_t>(), s_seq.as<int32_t>(), s_start.as<int32_t>(),
+                                                     s_strand.as<int8_t>(), s_score.as<double>(),
                                                      n_hits, mv.len, key_shift, ctx->keep.as<int32_t>());
             MSB_CUDA(cudaGetLastError());
             size_t scan_bytes = 0;
             MSB_CUDA(cub::DeviceScan::ExclusiveSum(nullptr, scan_bytes, ctx->keep.as<int32_t>(), ctx->keep_pos.as<int64_t>(), n_hits, st));
             MSB_TRY(ctx->sort_tmp.ensure(std::max<size_t>(scan_bytes, 16)));
             MSB_CUDA(cub::DeviceScan::ExclusiveSum(ctx->sort_tmp.p, scan_bytes, ctx->keep.as<int32_t>(), ctx->keep_pos.as<int64_t>(), n_hits, st));
-            // hit_key / hit_score are free again after the sort: reuse them as the compacted output
-            scatter_kept_kernel<<<grid, 256, 0, st>>>(ctx->keep.as<int32_t>(), ctx->keep_pos.as<int64_t>(), n_hits, ctx->fin_key,
-                                                      ctx->fin_score, ctx->fin_seq, ctx->fin_start, ctx->fin_strand,
-                                                      ctx->hit_key.as<uint64_t>(), ctx->hit_score.as<double>(),
-                                                      ctx->out2_seq.as<int32_t>(), ctx->out2_start.as<int32_t>(),
-                                                      ctx->out2_strand.as<int8_t>());
+            scatter_kept_kernel<<<grid, 256, 0, st>>>(ctx->keep.as<int32_t>(), ctx->keep_pos.as<int64_t>(), n_hits, s_key.as<uint64_t>(),
+                                                      s_score.as<double>(), s_seq.as<int32_t>(), s_start.as<int32_t>(),
+                                                      s_strand.as<int8_t>(), F.key.as<uint64_t>(), F.score.as<double>(),
+                                                      F.seq.as<int32_t>(), F.start.as<int32_t>(), F.strand.as<int8_t>());
             MSB_CUDA(cudaGetLastError());
             ctx->c[MSB_C_LAUNCHES] += 3;
             int32_t last_keep = 0;
@@ -1410,14 +1560,14 @@ static int scan_device(msb_ctx *ctx, msb_motifs *M, const msb_seqs *S, int stran
             MSB_CUDA(cudaMemcpyAsync(&last_pos, ctx->keep_pos.as<int64_t>() + (n_hits - 1), 8, cudaMemcpyDeviceToHost, st));
             MSB_CUDA(cudaStreamSynchronize(st));
             n_final = last_pos + last_keep;
-            ctx->fin_key = ctx->hit_key.as<uint64_t>();
-            ctx->fin_score = ctx->hit_score.as<double>();
-            ctx->fin_seq = ctx->out2_seq.as<int32_t>();
-            ctx->fin_start = ctx->out2_start.as<int32_t>();
-            ctx->fin_strand = ctx->out2_strand.as<int8_t>();
         }
+        ctx->fin_key = F.key.as<uint64_t>();
+        ctx->fin_score = F.score.as<double>();
+        ctx->fin_seq = F.seq.as<int32_t>();
+        ctx->fin_start = F.start.as<int32_t>();
+        ctx->fin_strand = F.strand.as<int8_t>();
         motif_offsets_kernel<<<(unsigned) ((M->n + 1 + 255) / 256), 256, 0, st>>>(ctx->fin_key, n_final, M->n, key_shift,
-                                                                                  ctx->out_counts.as<int64_t>());
+                                                                                  F.offsets.as<int64_t>());
         MSB_CUDA(cudaGetLastError());
         ctx->c[MSB_C_LAUNCHES] += 1;
     }
@@ -1428,6 +1578,8 @@ static int scan_device(msb_ctx *ctx, msb_motifs *M, const msb_seqs *S, int stran
     ctx->t[MSB_T_ORDER] = ev_ms(ctx->ev[2], ctx->ev[3]);
     ctx->t[MSB_T_D2H] = 0;
     ctx->last_sites = n_final;
+    ctx->fin_cur = fin_set;
+    ctx->last_counts_only = counts_only;
     return MSB_OK;
 }
 
@@ -1435,13 +1587,15 @@ static int scan_device(msb_ctx *ctx, msb_motifs *M, const msb_seqs *S, int stran
 
 extern "C" {
 
-int msb_set_option(const char *name, int value) {
-    if (name && !std::strcmp(name, "prefilter_w") && (value == 4 || value == 8)) { g_prefilter_w = value; return MSB_OK; }
-    if (name && !std::strcmp(name, "prefilter_tc") && (value == 0 || value == 1)) { g_prefilter_tc = value; return MSB_OK; }
-    if (name && !std::strcmp(name, "tc_prof") && (value == 0 || value == 1)) { g_tc_prof = value; return MSB_OK; }
-    if (name && !std::strcmp(name, "tc_first_lane_cap") && value >= 0) { g_tc_first_lane_cap = value; return MSB_OK; }
-    if (name && !std::strcmp(name, "ascii_slices") && value >= 1 && value <= 7) { g_ascii_slices = value; return MSB_OK; }
-    set_error("msb_set_option: unknown option or value");
+int msb_ctx_set_option(msb_ctx *ctx, const char *name, int value) {
+    if (!ctx) { set_error("msb_ctx_set_option: null ctx"); return MSB_EINVAL; }
+    if (name && !std::strcmp(name, "prefilter_w") && (value == 4 || value == 8)) { ctx->opt_prefilter_w = value; return MSB_OK; }
+    if (name && !std::strcmp(name, "prefilter_tc") && (value == 0 || value == 1)) { ctx->opt_prefilter_tc = value; return MSB_OK; }
+    if (name && !std::strcmp(name, "tc_prof") && (value == 0 || value == 1)) { ctx->opt_tc_prof = value; return MSB_OK; }
+    if (name && !std::strcmp(name, "tc_first_lane_cap") && value >= 0) { ctx->opt_tc_first_lane_cap = value; return MSB_OK; }
+    if (name && !std::strcmp(name, "ascii_slices") && value >= 1 && value <= 7) { ctx->opt_ascii_slices = value; return MSB_OK; }
+    if (name && !std::strcmp(name, "poison_pool") && (value == 0 || value == 1)) { ctx->opt_poison_pool = value; return MSB_OK; }
+    set_error("msb_ctx_set_option: unknown option or value");
     return MSB_EINVAL;
 }
 
@@ -1458,7 +1612,7 @@ int msb_scan_device_counts(msb_ctx *ctx, int64_t *counts, int32_t n_motifs) {
     MSB_CUDA(cudaSetDevice(ctx->device));
     std::vector<int64_t> offsets((size_t) n_motifs + 1, 0);
     if (ctx->last_sites)
-        MSB_CUDA(cudaMemcpyAsync(offsets.data(), ctx->out_counts.p, offsets.size() * 8, cudaMemcpyDeviceToHost, ctx->stream));
+        MSB_CUDA(cudaMemcpyAsync(offsets.data(), ctx->fin[ctx->fin_cur].offsets.p, offsets.size() * 8, cudaMemcpyDeviceToHost, ctx->stream));
     MSB_CUDA(cudaStreamSynchronize(ctx->stream));
     for (int32_t m = 0; m < n_motifs; m++) counts[m] = offsets[m + 1] - offsets[m];
     return MSB_OK;
@@ -1470,6 +1624,7 @@ int msb_scan_device_region_counts(msb_ctx *ctx, int64_t *counts, int32_t n_motif
     if (n_motifs == 0) return MSB_OK;
     MSB_CUDA(cudaSetDevice(ctx->device));
     std::fill(counts, counts + n_motifs, (int64_t) 0);
+    if (ctx->last_counts_only) { set_error("msb_scan_device_region_counts: the last scan kept per-motif counts only (MSB_SCAN_COUNTS)"); return MSB_EINVAL; }
     if (ctx->last_sites == 0) return MSB_OK;
     cudaStream_t st = ctx->stream;
     MSB_TRY(ctx->sel.ensure((size_t) n_motifs * 8));
@@ -1493,7 +1648,7 @@ int msb_scan_ranges_device(msb_ctx *ctx, const msb_motifs *M, const msb_seqs *S,
     return MSB_OK;
 }
 
-static int collect_result(msb_ctx *ctx, const msb_motifs *M, msb_result **out);
+static int collect_result(msb_ctx *ctx, const msb_motifs *M, int flags, msb_result **out);
 
 int msb_scan_ranges(msb_ctx *ctx, const msb_motifs *M, const msb_seqs *S, int strand, int flags,
                     int64_t n_ranges, const int64_t *seq_idx, const int64_t *start, const int64_t *end,
@@ -1501,7 +1656,7 @@ int msb_scan_ranges(msb_ctx *ctx, const msb_motifs *M, const msb_seqs *S, int st
     if (!out) { set_error("msb_scan_ranges: null out"); return MSB_EINVAL; }
     *out = nullptr;
     MSB_TRY(msb_scan_ranges_device(ctx, M, S, strand, flags, n_ranges, seq_idx, start, end, nullptr));
-    return collect_result(ctx, M, out);
+    return collect_result(ctx, M, flags, out);
 }
 
 int msb_scan_ascii(msb_ctx *ctx, const msb_motifs *M, int64_t n_seqs, const char *bytes, const int64_t *seq_off,
@@ -1523,10 +1678,10 @@ int msb_scan_ascii(msb_ctx *ctx, const msb_motifs *M, int64_t n_seqs, const char
     MSB_CUDA(cudaSetDevice(ctx->device));
     const int64_t total_bp = seq_off[n_seqs];
     // Small inputs, the table prefilter (no range launches) and an unusable copy stream take the plain path.
-    const int kSlices = g_ascii_slices;
-    bool sliced = g_prefilter_tc != 0 && total_bp >= (8 << 20) && n_seqs >= kSlices;
-    if (sliced && !ctx->copy_stream) {
-        if (cudaStreamCreateWithFlags(&ctx->copy_stream, cudaStreamNonBlocking) != cudaSuccess) { cudaGetLastError(); sliced = false; }
+    const int kSlices = ctx->opt_ascii_slices;
+    bool sliced = ctx->opt_prefilter_tc != 0 && total_bp >= (8 << 20) && n_seqs >= kSlices;
+    if (sliced && ensure_copy_stream(ctx) != MSB_OK) sliced = false;
+    if (sliced && !ctx->slice_ev[0]) {
         for (auto &evt : ctx->slice_ev)
             if (sliced && cudaEventCreateWithFlags(&evt, cudaEventDisableTiming) != cudaSuccess) { cudaGetLastError(); sliced = false; }
     }
@@ -1577,7 +1732,7 @@ int msb_scan_ascii(msb_ctx *ctx, const msb_motifs *M, int64_t n_seqs, const char
             return MSB_OK;
         };
         if (rc == MSB_OK) rc = scan_device(ctx, const_cast<msb_motifs *>(M), S, strand, flags, &ranges, &hook);
-        if (rc == MSB_OK) rc = collect_result(ctx, M, out);
+        if (rc == MSB_OK) rc = collect_result(ctx, M, flags, out);
         cudaStreamSynchronize(ctx->copy_stream);   // `bytes` may go away after return, also on failure
         cudaStreamSynchronize(st);
         ctx->t[MSB_T_H2D] = 0;                      // hidden behind the scan; not separable
@@ -1596,44 +1751,75 @@ int msb_scan_ex(msb_ctx *ctx, const msb_motifs *M, const msb_seqs *S, int strand
     if (!out) { set_error("msb_scan: null out"); return MSB_EINVAL; }
     *out = nullptr;
     MSB_TRY(scan_device(ctx, const_cast<msb_motifs *>(M), S, strand, flags));
-    return collect_result(ctx, M, out);
+    return collect_result(ctx, M, flags, out);
 }
 
-// Sites of the last scan_device on this context -> pinned host memory.
-static int collect_result(msb_ctx *ctx, const msb_motifs *M, msb_result **out) {
+// Sites of the last scan_device on this context -> pinned host memory.  The copies run on the context's
+// d2h stream behind an event of the main stream, so with MSB_SCAN_ASYNC the caller's next scan overlaps them
+// (it fills the other FinSet); without the flag the call waits for them.
+static int result_finish(msb_result *R) {
+    if (!R->pending) return MSB_OK;
+    cudaError_t e = cudaEventSynchronize(R->done);
+    if (e != cudaSuccess) return cuda_fail(e, "msb_result_wait", __FILE__, __LINE__);
+    R->pending = false;
+    for (int32_t m = 0; m < R->n_motifs; m++) R->counts[m] = R->offsets[m + 1] - R->offsets[m];
+    float ms = 0;
+    if (cudaEventElapsedTime(&ms, R->t0, R->done) == cudaSuccess && R->ctx) R->ctx->t[MSB_T_D2H] = ms; else cudaGetLastError();
+    return MSB_OK;
+}
+
+static int collect_result(msb_ctx *ctx, const msb_motifs *M, int flags, msb_result **out) {
+    if (ctx->last_counts_only) { set_error("msb_scan: MSB_SCAN_COUNTS keeps no sites; use msb_scan_device / msb_scan_ranges_device + msb_scan_device_counts"); return MSB_EINVAL; }
+    if (!ctx->d2h_stream) MSB_CUDA(cudaStreamCreateWithFlags(&ctx->d2h_stream, cudaStreamNonBlocking));
+    msb_ctx::FinSet &F = ctx->fin[ctx->fin_cur];
+    if (!F.read_done) MSB_CUDA(cudaEventCreateWithFlags(&F.read_done, cudaEventDisableTiming));
     msb_result *R = new (std::nothrow) msb_result();
     if (!R) { set_error("out of host memory"); return MSB_ENOMEM; }
     R->ctx = ctx;
+    R->device = ctx->device;
     R->n_sites = ctx->last_sites;
     R->n_motifs = M->n;
     R->counts.assign((size_t) M->n, 0);
-    std::vector<int64_t> offsets((size_t) M->n + 1, 0);
     const int64_t n = R->n_sites;
-    // one pinned block: score (8n) | seq_idx (4n) | start (4n) | strand (n)
-    int rc = pinned_get(ctx, (size_t) std::max<int64_t>(17 * n, 64), &R->block);
+    const size_t off_at = ((size_t) 17 * (size_t) n + 7) & ~(size_t) 7;
+    int rc = pinned_get(ctx, off_at + (size_t) (M->n + 1) * 8, &R->block);
     if (rc != MSB_OK) { delete R; return rc; }
     char *base = (char *) R->block.p;
     R->score = (double *) base;
     R->seq_idx = (int32_t *) (base + 8 * n);
     R->start = (int32_t *) (base + 12 * n);
     R->strand = (int8_t *) (base + 16 * n);
-    cudaStream_t st = ctx->stream;
-    cudaError_t e = cudaEventRecord(ctx->ev[4], st);
+    R->offsets = (int64_t *) (base + off_at);
+    cudaStream_t st = ctx->stream, cs = ctx->d2h_stream;
+    cudaError_t e = cudaEventCreate(&R->t0);
     auto step = [&](cudaError_t x) { if (e == cudaSuccess) e = x; };
+    step(cudaEventCreate(&R->done));
+    step(cudaEventRecord(ctx->ev[4], st));                 // everything the scan enqueued
+    step(cudaStreamWaitEvent(cs, ctx->ev[4], 0));
+    step(cudaEventRecord(R->t0, cs));
     if (n) {
-        step(cudaMemcpyAsync(R->score, ctx->fin_score, (size_t) n * 8, cudaMemcpyDeviceToHost, st));
-        step(cudaMemcpyAsync(R->seq_idx, ctx->fin_seq, (size_t) n * 4, cudaMemcpyDeviceToHost, st));
-        step(cudaMemcpyAsync(R->start, ctx->fin_start, (size_t) n * 4, cudaMemcpyDeviceToHost, st));
-        step(cudaMemcpyAsync(R->strand, ctx->fin_strand, (size_t) n, cudaMemcpyDeviceToHost, st));
-        step(cudaMemcpyAsync(offsets.data(), ctx->out_counts.p, (size_t) (M->n + 1) * 8, cudaMemcpyDeviceToHost, st));
+        step(cudaMemcpyAsync(R->score, ctx->fin_score, (size_t) n * 8, cudaMemcpyDeviceToHost, cs));
+        step(cudaMemcpyAsync(R->seq_idx, ctx->fin_seq, (size_t) n * 4, cudaMemcpyDeviceToHost, cs));
+        step(cudaMemcpyAsync(R->start, ctx->fin_start, (size_t) n * 4, cudaMemcpyDeviceToHost, cs));
+        step(cudaMemcpyAsync(R->strand, ctx->fin_strand, (size_t) n, cudaMemcpyDeviceToHost, cs));
     }
-    step(cudaEventRecord(ctx->ev[5], st));
-    step(cudaStreamSynchronize(st));
+    step(cudaMemcpyAsync(R->offsets, F.offsets.p, (size_t) (M->n + 1) * 8, cudaMemcpyDeviceToHost, cs));
+    step(cudaEventRecord(R->done, cs));
+    step(cudaEventRecord(F.read_done, cs));
     if (e != cudaSuccess) { msb_result_destroy(R); return cuda_fail(e, "msb_scan D2H", __FILE__, __LINE__); }
-    for (int32_t m = 0; m < M->n; m++) R->counts[m] = offsets[m + 1] - offsets[m];
-    ctx->t[MSB_T_D2H] = ev_ms(ctx->ev[4], ctx->ev[5]);
+    F.pending = true;
+    R->pending = true;
+    if (!(flags & MSB_SCAN_ASYNC)) {
+        rc = result_finish(R);
+        if (rc != MSB_OK) { msb_result_destroy(R); return rc; }
+    }
     *out = R;
     return MSB_OK;
+}
+
+int msb_result_wait(msb_result *R) {
+    if (!R) { set_error("null result"); return MSB_EINVAL; }
+    return result_finish(R);
 }
 
 int msb_scan(msb_ctx *ctx, const msb_motifs *M, const msb_seqs *S, int strand, msb_result **out) {
@@ -1642,17 +1828,19 @@ int msb_scan(msb_ctx *ctx, const msb_motifs *M, const msb_seqs *S, int strand, m
 
 int msb_result_total(const msb_result *R, int64_t *n) {
     if (!R || !n) { set_error("null"); return MSB_EINVAL; }
-    *n = R->n_sites;
+    *n = R->n_sites;   // known when the scan returns, also for an asynchronous result
     return MSB_OK;
 }
 int msb_result_counts(const msb_result *R, int64_t *counts) {
     if (!R || (!counts && R->n_motifs)) { set_error("null"); return MSB_EINVAL; }
+    MSB_TRY(result_finish(const_cast<msb_result *>(R)));
     std::copy(R->counts.begin(), R->counts.end(), counts);
     return MSB_OK;
 }
 int msb_result_arrays(const msb_result *R, const int32_t **seq_idx, const int32_t **start,
                       const double **score, const int8_t **strand) {
     if (!R) { set_error("null result"); return MSB_EINVAL; }
+    MSB_TRY(result_finish(const_cast<msb_result *>(R)));
     if (seq_idx) *seq_idx = R->seq_idx;
     if (start) *start = R->start;
     if (score) *score = R->score;
@@ -1661,9 +1849,76 @@ int msb_result_arrays(const msb_result *R, const int32_t **seq_idx, const int32_
 }
 int msb_result_destroy(msb_result *R) {
     if (!R) return MSB_OK;
+    cudaSetDevice(R->device);
+    if (R->pending && R->done) cudaEventSynchronize(R->done);   // the copies write into the block
+    if (R->t0) cudaEventDestroy(R->t0);
+    if (R->done) cudaEventDestroy(R->done);
     if (R->ctx) pinned_put(R->ctx, R->block);
     else if (R->block.p) cudaFreeHost(R->block.p);
     delete R;
+    return MSB_OK;
+}
+
+// ---- host-side gather ----------------------------------------------------------------------------
+// The reference's pool hands out whole motifs and its results are per-motif lists (cscore.c:323-328,
+// 425-436); here several GPUs (or several batches of one) each return a motif-major array over THEIR
+// sequences, in ascending sequence order across parts, so the gathered list of motif m is part 0's slice,
+// then part 1's, ...: a copy, no sort, no pickling.  Host threads split the motifs by bytes.
+int msb_merge_motif_major(int32_t n_parts, int32_t n_motifs, const int64_t *counts, const void *const *src,
+                          void *dst, int32_t elem_size, const int64_t *add_i32, int32_t n_threads) {
+    if (n_parts < 0 || n_motifs < 0 || elem_size < 1 || (n_parts > 0 && n_motifs > 0 && (!counts || !src))) {
+        set_error("msb_merge_motif_major: bad argument");
+        return MSB_EINVAL;
+    }
+    if (add_i32 && elem_size != 4) { set_error("msb_merge_motif_major: an addend needs 4-byte elements"); return MSB_EINVAL; }
+    if (n_parts == 0 || n_motifs == 0) return MSB_OK;
+    // source offset of (part, motif) and destination offset of motif
+    std::vector<int64_t> src_off((size_t) n_parts * n_motifs), dst_off((size_t) n_motifs + 1, 0);
+    for (int32_t p = 0; p < n_parts; p++) {
+        int64_t at = 0;
+        for (int32_t m = 0; m < n_motifs; m++) {
+            const int64_t c = counts[(size_t) p * n_motifs + m];
+            if (c < 0) { set_error("msb_merge_motif_major: negative count"); return MSB_EINVAL; }
+            src_off[(size_t) p * n_motifs + m] = at;
+            at += c;
+            dst_off[m + 1] += c;
+        }
+    }
+    for (int32_t m = 0; m < n_motifs; m++) dst_off[m + 1] += dst_off[m];
+    const int64_t total = dst_off[n_motifs];
+    if (total == 0) return MSB_OK;
+    if (!dst) { set_error("msb_merge_motif_major: null destination"); return MSB_EINVAL; }
+    int nt = std::max(1, std::min<int>(n_threads, 64));
+    if ((int64_t) total * elem_size < (4 << 20)) nt = 1;
+    auto work = [&](int t) {
+        // motifs [m0, m1): boundaries at equal shares of the output
+        const int64_t lo = total * t / nt, hi = total * (t + 1) / nt;
+        const int32_t m0 = (int32_t) (std::lower_bound(dst_off.begin(), dst_off.end() - 1, lo) - dst_off.begin());
+        const int32_t m1 = t + 1 == nt ? n_motifs : (int32_t) (std::lower_bound(dst_off.begin(), dst_off.end() - 1, hi) - dst_off.begin());
+        for (int32_t m = m0; m < m1; m++) {
+            int64_t at = dst_off[m];
+            for (int32_t p = 0; p < n_parts; p++) {
+                const int64_t c = counts[(size_t) p * n_motifs + m];
+                if (!c) continue;
+                const char *from = (const char *) src[p] + src_off[(size_t) p * n_motifs + m] * elem_size;
+                char *to = (char *) dst + at * elem_size;
+                if (add_i32 && add_i32[p]) {
+                    const int32_t add = (int32_t) add_i32[p];
+                    const int32_t *f = (const int32_t *) from;
+                    int32_t *o = (int32_t *) to;
+                    for (int64_t i = 0; i < c; i++) o[i] = f[i] + add;
+                } else {
+                    std::memcpy(to, from, (size_t) c * elem_size);
+                }
+                at += c;
+            }
+        }
+    };
+    if (nt == 1) { work(0); return MSB_OK; }
+    std::vector<std::thread> pool;
+    for (int t = 1; t < nt; t++) pool.emplace_back(work, t);
+    work(0);
+    for (auto &th : pool) th.join();
     return MSB_OK;
 }
 
@@ -1672,6 +1927,8 @@ static int check_score_args(msb_ctx *ctx, const msb_motifs *M, const msb_seqs *S
     if (!ctx || !M || !S) { set_error("msb_score: null argument"); return MSB_EINVAL; }
     if (strand < 1 || strand > 3) { set_error("msb_score: strand must be 1, 2 or 3"); return MSB_EINVAL; }
     if (M->ctx != ctx || S->ctx != ctx) { set_error("msb_score: motifs/seqs belong to another context"); return MSB_EINVAL; }
+    MSB_CUDA(cudaSetDevice(ctx->device));
+    MSB_TRY(seqs_ready(S));
     if (S->n > 0 && M->n > 0 && S->min_len < M->lmax) {
         // the reference reads lens[m] bases without a length check (cscore.c:195): undefined there
         set_error("msb_score: a sequence is shorter than the longest motif");
@@ -1762,34 +2019,40 @@ int msb_score_select(msb_ctx *ctx, const msb_motifs *M, const msb_seqs *S, int s
 }
 
 // ---- one-shot mirrors --------------------------------------------------------------------------
-static std::mutex g_default_mu;
-static msb_ctx *g_default_ctx[64] = {};
+// The reference's two methods take no handle (cscore.c:399, :231), so these need a context from
+// somewhere: one per (calling host thread, device), created on first use and destroyed when the
+// thread ends.  No process-wide table, no lock: concurrent callers never share a context.
+struct ThreadContexts {
+    std::vector<msb_ctx *> by_device;
+    ~ThreadContexts() { for (msb_ctx *c : by_device) if (c) msb_ctx_destroy(c); }
+};
 
 static int default_ctx(int device, msb_ctx **out) {
-    if (device < 0 || device >= 64) { set_error("device out of range"); return MSB_EINVAL; }
-    if (!g_default_ctx[device]) MSB_TRY(msb_ctx_create(device, nullptr, &g_default_ctx[device]));
-    *out = g_default_ctx[device];
+    static thread_local ThreadContexts tls;
+    if (device < 0 || device >= 1024) { set_error("device out of range"); return MSB_EINVAL; }
+    if ((size_t) device >= tls.by_device.size()) tls.by_device.resize((size_t) device + 1, nullptr);
+    if (!tls.by_device[device]) MSB_TRY(msb_ctx_create(device, nullptr, &tls.by_device[device]));
+    *out = tls.by_device[device];
     return MSB_OK;
 }
 
 int msb_c_scan_motif(int device, int32_t n_motifs, const int32_t *lens, const double *mats,
                      const int64_t *mat_off, const double *cutoffs, int64_t n_seqs, const char *seq_bytes,
                      const int64_t *seq_off, int strand, msb_result **out) {
-    std::lock_guard<std::mutex> g(g_default_mu);
     msb_ctx *ctx = nullptr;
     MSB_TRY(default_ctx(device, &ctx));
     msb_motifs *M = nullptr;
-    msb_seqs *S = nullptr;
     int rc = msb_motifs_create(ctx, n_motifs, lens, mats, mat_off, cutoffs, &M);
     if (rc == MSB_OK) rc = msb_scan_ascii(ctx, M, n_seqs, seq_bytes, seq_off, strand, 0, nullptr, out);
-    msb_seqs_destroy(S);
+    // the result may outlive the calling thread (and with it the thread's context): it owns its pinned
+    // block outright instead of handing it back to the context's pool
+    if (rc == MSB_OK && out && *out) (*out)->ctx = nullptr;
     msb_motifs_destroy(M);
     return rc;
 }
 
 int msb_c_score(int device, int32_t n_motifs, const int32_t *lens, const double *mats, const int64_t *mat_off,
                 int64_t n_seqs, const char *seq_bytes, const int64_t *seq_off, int strand, double *out) {
-    std::lock_guard<std::mutex> g(g_default_mu);
     msb_ctx *ctx = nullptr;
     MSB_TRY(default_ctx(device, &ctx));
     msb_motifs *M = nullptr;

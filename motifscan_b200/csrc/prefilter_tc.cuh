@@ -80,7 +80,7 @@ struct TcParams {
     int64_t *dirty;
     int64_t dirty_cap;
     unsigned long long *counters;   // [1] dirty positions (the record totals are reduced from lane_count by lane_totals_kernel)
-    long long *prof;           // optional [grid][16] cycle counters (msb_set_option("tc_prof", 1)); nullptr = off
+    long long *prof;           // optional [grid][16] cycle counters (msb_ctx_set_option(ctx, "tc_prof", 1)); nullptr = off
 };
 
 namespace tc {
@@ -396,7 +396,9 @@ prefilter_tc_kernel(const __grid_constant__ TcParams P) {
                 uint32_t ign = 0xffffffffu;
                 if (lane < 16) {
                     const int64_t q0 = tile_start + lane * 32;
-                    if (q0 < S.total_packed) {
+                    // blocks wholly outside the scanned range are never looked up: behind pos_hi the owner
+                    // table may not be written yet (msb_scan_ascii encodes slice k + 1 after this launch)
+                    if (q0 < S.total_packed && q0 < P.pos_hi && q0 + 32 > P.pos_lo) {
                         const int64_t blk = q0 >> 5;
                         const int64_t s = __ldg(S.blk_seq + blk);
                         const int64_t j0 = q0 - __ldg(S.poff + s);

@@ -41,6 +41,11 @@ class Context:
     def sync(self):
         check(self._lib.msb_ctx_sync(self._h))
 
+    def set_option(self, name, value):
+        """Tuning / test knob of this context only (msb_ctx_set_option; names in include/msb200.h)."""
+        with self._lock:
+            check(self._lib.msb_ctx_set_option(self._h, name.encode(), int(value)))
+
     def timings(self):
         """Device milliseconds per phase of the last call (CUDA events on the context's stream)."""
         a = np.zeros(len(_lib.T_NAMES), dtype=np.float64)
@@ -147,6 +152,38 @@ class SequenceSet:
             check(self._lib.msb_seqs_from_ascii(ctx._h, self.n, ctypes.c_void_p(data), ptr(seq_off, ctypes.c_int64),
                                                 ctypes.byref(self._h)))
 
+    @classmethod
+    def from_packed(cls, ctx, lens, codes, nmask, async_=False):
+        """Sequences that are already packed in the library's layout (msb_seqs_from_packed): `codes`
+        uint32[2 B], `nmask` uint32[B] with B = sum ceil(len / 32); 0.375 B/bp cross PCIe and nothing is
+        encoded.  The arrays may be views into a larger (pinned) buffer, e.g. a `genome.PackedGenome`.
+        `async_`: the copy runs on the context's copy stream and overlaps a scan in progress."""
+        lens = np.ascontiguousarray(np.asarray(lens, dtype=np.int64))
+        n_blocks = int(((lens + 31) // 32).sum())
+        codes = np.ascontiguousarray(codes, dtype=np.uint32)
+        nmask = np.ascontiguousarray(nmask, dtype=np.uint32)
+        if codes.size < 2 * n_blocks or nmask.size < n_blocks:
+            raise ValueError("packed planes are shorter than the sequence lengths require")
+        h = ctypes.c_void_p()
+        with ctx._lock:
+            check(ctx._lib.msb_seqs_from_packed(ctx._h, len(lens), ptr(lens, ctypes.c_int64),
+                                                ctypes.c_void_p(codes.ctypes.data if n_blocks else 0),
+                                                ctypes.c_void_p(nmask.ctypes.data if n_blocks else 0),
+                                                _lib.MSB_SEQS_ASYNC if async_ else 0, ctypes.byref(h)))
+        out = cls(ctx, _handle=h)
+        out._planes = (codes, nmask) if async_ else None   # an asynchronous upload still reads them
+        return out
+
+    def to_packed(self):
+        """(codes uint32[2 B], nmask uint32[B]): the packed planes as the device holds them."""
+        n_blocks = int(((np.diff(self.seq_off) + 31) // 32).sum())
+        codes = np.zeros(max(2 * n_blocks, 1), dtype=np.uint32)
+        nmask = np.zeros(max(n_blocks, 1), dtype=np.uint32)
+        with self.ctx._lock:
+            check(self._lib.msb_seqs_to_packed(self.ctx._h, self._h, ctypes.c_void_p(codes.ctypes.data),
+                                               ctypes.c_void_p(nmask.ctypes.data)))
+        return codes[:2 * n_blocks], nmask[:n_blocks]
+
     def extract(self, src_idx, start, end):
         """A new sequence set cut out of this (resident) one on the device: sequence i = bases
         [start[i], end[i]) of sequence src_idx[i], `end` clipped at the source length like
@@ -206,18 +243,27 @@ class SequenceSet:
 
 class ScanResult:
     """Sites of one scan in the reference's order (motif-major; sequence, start ascending;
-    forward before reverse).  Arrays are views into pinned memory owned by the result."""
+    forward before reverse).  Arrays are views into pinned memory owned by the result.  A result of
+    an asynchronous scan (`async_=True`) knows `n_sites` at once; everything else waits for the
+    device-to-host copy on first use (`wait()`)."""
 
     def __init__(self, ctx, handle, n_motifs):
         self.ctx = ctx
         self._lib = ctx._lib
         self._h = handle
+        self.n_motifs = n_motifs
         n = ctypes.c_int64(0)
         check(self._lib.msb_result_total(self._h, ctypes.byref(n)))
         self.n_sites = n.value
-        self.counts = np.zeros(max(n_motifs, 1), dtype=np.int64)
-        check(self._lib.msb_result_counts(self._h, ptr(self.counts, ctypes.c_int64)))
-        self.counts = self.counts[:n_motifs]
+        self._loaded = False
+
+    def wait(self):
+        if self._loaded:
+            return self
+        n_motifs = self.n_motifs
+        counts = np.zeros(max(n_motifs, 1), dtype=np.int64)
+        check(self._lib.msb_result_counts(self._h, ptr(counts, ctypes.c_int64)))   # waits for the copies
+        self.counts = counts[:n_motifs]
         self.offsets = np.zeros(n_motifs + 1, dtype=np.int64)
         np.cumsum(self.counts, out=self.offsets[1:])
         p_seq, p_start = _lib.c_i32p(), _lib.c_i32p()
@@ -235,9 +281,19 @@ class ScanResult:
             self.start = np.zeros(0, dtype=np.int32)
             self.score = np.zeros(0, dtype=np.float64)
             self.strand = np.zeros(0, dtype=np.int8)
+        self._loaded = True
+        return self
+
+    def __getattr__(self, name):
+        # counts / offsets / seq_idx / start / score / strand exist once the copies have landed
+        if name in ("counts", "offsets", "seq_idx", "start", "score", "strand") and not self.__dict__.get("_loaded", True):
+            self.wait()
+            return self.__dict__[name]
+        raise AttributeError(name)
 
     def detach(self):
         """Copy the arrays out of the pinned block and release it."""
+        self.wait()
         self.seq_idx = self.seq_idx.copy()
         self.start = self.start.copy()
         self.score = self.score.copy()
@@ -257,24 +313,52 @@ class ScanResult:
             pass
 
 
-def scan(ctx, motifs, seqs, strand, remove_dup=False):
+def _flags(remove_dup=False, counts_only=False, async_=False):
+    return ((_lib.MSB_SCAN_DEDUP if remove_dup else 0) | (_lib.MSB_SCAN_COUNTS if counts_only else 0)
+            | (_lib.MSB_SCAN_ASYNC if async_ else 0))
+
+
+def merge_motif_major(counts, arrays, add=None, n_threads=None):
+    """Gather motif-major arrays of several scans (one per GPU or batch, parts in ascending sequence
+    order) into one motif-major array (msb_merge_motif_major: host memcpy on several threads, no
+    sort, no pickling).  `counts` int64[n_parts, n_motifs]; `arrays` one array per part; `add`
+    optional per-part addend for int32 arrays (the part's first global sequence index)."""
+    import os
+    counts = np.ascontiguousarray(np.asarray(counts, dtype=np.int64))
+    n_parts, n_motifs = counts.shape
+    if n_parts == 0:
+        return np.zeros(0, dtype=np.int32)
+    dtype = arrays[0].dtype
+    keep = [np.ascontiguousarray(a) for a in arrays]
+    src = (ctypes.c_void_p * n_parts)(*[ctypes.c_void_p(a.ctypes.data if a.size else 0) for a in keep])
+    out = np.empty(int(counts.sum()), dtype=dtype)
+    add_arr = None if add is None else np.ascontiguousarray(np.asarray(add, dtype=np.int64))
+    check(_lib.load().msb_merge_motif_major(n_parts, n_motifs, ptr(counts, ctypes.c_int64), src,
+                                            ctypes.c_void_p(out.ctypes.data if out.size else 0), dtype.itemsize,
+                                            ptr(add_arr, ctypes.c_int64) if add_arr is not None else None,
+                                            int(n_threads or min(os.cpu_count() or 1, 16))))
+    return out
+
+
+def scan(ctx, motifs, seqs, strand, remove_dup=False, async_=False):
     """Scan; with remove_dup the reference's adjacent-site de-duplication (scanner.py:156-193)
-    runs on the device before the sites are copied back."""
+    runs on the device before the sites are copied back.  `async_`: return while the copy of the
+    sites is still in flight (the next scan on `ctx` overlaps it; `ScanResult.wait`)."""
     h = ctypes.c_void_p()
-    flags = _lib.MSB_SCAN_DEDUP if remove_dup else 0
+    flags = _flags(remove_dup, async_=async_)
     with ctx._lock:
         check(ctx._lib.msb_scan_ex(ctx._h, motifs._h, seqs._h, int(strand), flags, ctypes.byref(h)))
     return ScanResult(ctx, h, motifs.n)
 
 
-def scan_ascii(ctx, motifs, blob, seq_off, strand, remove_dup=False):
+def scan_ascii(ctx, motifs, blob, seq_off, strand, remove_dup=False, async_=False):
     """Host ASCII in, host sites out in one call (msb_scan_ascii): the upload of the sequence bytes
     is cut into slices that overlap with the scan.  `blob` should live in pinned memory
     (`pinned_array`) for the overlap to happen; any uint8 array works."""
     blob = np.ascontiguousarray(blob, dtype=np.uint8) if not isinstance(blob, np.ndarray) else blob
     seq_off = np.ascontiguousarray(seq_off, dtype=np.int64)
     h = ctypes.c_void_p()
-    flags = _lib.MSB_SCAN_DEDUP if remove_dup else 0
+    flags = _flags(remove_dup, async_=async_)
     data = blob.ctypes.data if blob.size else None
     with ctx._lock:
         check(ctx._lib.msb_scan_ascii(ctx._h, motifs._h, len(seq_off) - 1, ctypes.c_void_p(data), ptr(seq_off, ctypes.c_int64),
@@ -303,10 +387,11 @@ class PinnedArray:
             pass
 
 
-def scan_device(ctx, motifs, seqs, strand, remove_dup=False):
-    """Kernels only (results stay on the device); returns the number of sites."""
+def scan_device(ctx, motifs, seqs, strand, remove_dup=False, counts_only=False):
+    """Kernels only (results stay on the device); returns the number of sites.  `counts_only`: the
+    sites are not even ordered -- `ctx.site_counts` is all that can be read afterwards."""
     n = ctypes.c_int64(0)
-    flags = _lib.MSB_SCAN_DEDUP if remove_dup else 0
+    flags = _flags(remove_dup, counts_only)
     with ctx._lock:
         check(ctx._lib.msb_scan_device(ctx._h, motifs._h, seqs._h, int(strand), flags, ctypes.byref(n)))
     return n.value
@@ -317,23 +402,23 @@ def _ranges(ranges):
     return (len(r), np.ascontiguousarray(r[:, 0]), np.ascontiguousarray(r[:, 1]), np.ascontiguousarray(r[:, 2]))
 
 
-def scan_ranges(ctx, motifs, seqs, strand, ranges, remove_dup=False):
+def scan_ranges(ctx, motifs, seqs, strand, ranges, remove_dup=False, async_=False):
     """Scan only the windows that start in the given (sequence index, start, end) ranges of a
     resident sequence set; sites refer to the sequences of `seqs` (msb_scan_ranges)."""
     n, a, b, c = _ranges(ranges)
     h = ctypes.c_void_p()
-    flags = _lib.MSB_SCAN_DEDUP if remove_dup else 0
+    flags = _flags(remove_dup, async_=async_)
     with ctx._lock:
         check(ctx._lib.msb_scan_ranges(ctx._h, motifs._h, seqs._h, int(strand), flags, n, ptr(a, ctypes.c_int64),
                                        ptr(b, ctypes.c_int64), ptr(c, ctypes.c_int64), ctypes.byref(h)))
     return ScanResult(ctx, h, motifs.n)
 
 
-def scan_ranges_device(ctx, motifs, seqs, strand, ranges, remove_dup=False):
+def scan_ranges_device(ctx, motifs, seqs, strand, ranges, remove_dup=False, counts_only=False):
     """The same, results left on the device (`ctx.site_counts`); returns the number of sites."""
     n, a, b, c = _ranges(ranges)
     total = ctypes.c_int64(0)
-    flags = _lib.MSB_SCAN_DEDUP if remove_dup else 0
+    flags = _flags(remove_dup, counts_only)
     with ctx._lock:
         check(ctx._lib.msb_scan_ranges_device(ctx._h, motifs._h, seqs._h, int(strand), flags, n, ptr(a, ctypes.c_int64),
                                               ptr(b, ctypes.c_int64), ptr(c, ctypes.c_int64), ctypes.byref(total)))

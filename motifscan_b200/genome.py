@@ -132,6 +132,139 @@ class Genome:
             attempt += 1
 
 
+class PackedGenome:
+    """A genome in the library's packed representation on the HOST: 2-bit codes + N mask of every
+    chromosome (0.375 B/bp; hg19 = 1.16 GB), each chromosome padded to 32 bases, planes concatenated in
+    `chroms` order, in page-locked memory when a CUDA device is there.
+
+    This is the host-side source of every device copy: `DeviceGenome(PackedGenome)` uploads the planes
+    as they are (`msb_seqs_from_packed`), and a multi-GPU genome scan gives each GPU one contiguous
+    block range of them (`genome_scan.plan_shares`).  Built once per genome from the FASTA (encoded on a
+    GPU, chromosome by chromosome) and cached next to it with `save` / `load`, the way the reference
+    keeps a `.fai` next to its FASTA (genome/__init__.py:61-95).  Soft-masking (lower case) is not kept:
+    scoring never sees it (cscore.c:91-108 folds case)."""
+
+    def __init__(self, chroms, chrom_sizes, codes, nmask, name="packed", genome=None, _pin=None):
+        self.name = name
+        self.chroms = list(chroms)
+        self.chrom_sizes = {c: int(chrom_sizes[c]) for c in self.chroms}
+        self.chrom_index = {c: i for i, c in enumerate(self.chroms)}
+        blocks = np.array([(self.chrom_sizes[c] + 31) // 32 for c in self.chroms], dtype=np.int64)
+        self.block_off = np.zeros(len(self.chroms) + 1, dtype=np.int64)
+        np.cumsum(blocks, out=self.block_off[1:])
+        self.n_blocks = int(self.block_off[-1])
+        if codes.size != 2 * self.n_blocks or nmask.size != self.n_blocks:
+            raise ValueError("packed planes do not match the chromosome sizes")
+        self.codes, self.nmask = codes, nmask
+        self.genome = genome          # optional host genome the planes came from (bg_freq, strings with case)
+        self._pin = _pin              # keeps the pinned allocations alive
+
+    @staticmethod
+    def _alloc(n_blocks, pinned=True):
+        """(codes, nmask, keepalive): page-locked when the CUDA library can allocate it."""
+        if pinned:
+            try:
+                from . import engine
+                a, b = engine.PinnedArray(max(8 * n_blocks, 8)), engine.PinnedArray(max(4 * n_blocks, 4))
+                return a.array[:8 * n_blocks].view(np.uint32), b.array[:4 * n_blocks].view(np.uint32), (a, b)
+            except Exception:
+                pass
+        return np.zeros(2 * n_blocks, dtype=np.uint32), np.zeros(n_blocks, dtype=np.uint32), None
+
+    @classmethod
+    def from_genome(cls, genome, ctx=None, pinned=True):
+        """Encode a host genome (anything with chroms / chrom_sizes / fetch_bytes or fetch_sequence) on the
+        device, one chromosome at a time, and keep the packed planes on the host."""
+        from . import engine
+        ctx = ctx or engine.default_context(0)
+        chroms = list(genome.chroms)
+        sizes = {c: int(genome.chrom_sizes[c]) for c in chroms}
+        n_blocks = sum((sizes[c] + 31) // 32 for c in chroms)
+        codes, nmask, pin = cls._alloc(n_blocks, pinned)
+        fetch = getattr(genome, "fetch_bytes", None)
+        at = 0
+        for c in chroms:
+            raw = fetch(c, 0, sizes[c]) if fetch else genome.fetch_sequence(c, 0, sizes[c]).encode()
+            if len(raw) != sizes[c]:
+                raise ValueError(f"chromosome {c}: fetched {len(raw)} bases, index says {sizes[c]}")
+            sset = engine.SequenceSet(ctx, blob=np.frombuffer(raw, dtype=np.uint8), seq_off=np.array([0, sizes[c]], dtype=np.int64))
+            try:
+                cw, mw = sset.to_packed()
+            finally:
+                sset.close()
+            nb = (sizes[c] + 31) // 32
+            codes[2 * at:2 * (at + nb)] = cw
+            nmask[at:at + nb] = mw
+            at += nb
+        return cls(chroms, sizes, codes, nmask, name=getattr(genome, "name", "packed"), genome=genome, _pin=pin)
+
+    def save(self, prefix):
+        """`<prefix>.codes.npy`, `<prefix>.nmask.npy`, `<prefix>.chroms.tsv`: the packed-genome cache."""
+        np.save(prefix + ".codes.npy", np.asarray(self.codes))
+        np.save(prefix + ".nmask.npy", np.asarray(self.nmask))
+        with open(prefix + ".chroms.tsv", "w") as out:
+            for c in self.chroms:
+                out.write(f"{c}\t{self.chrom_sizes[c]}\n")
+
+    @classmethod
+    def load(cls, prefix, genome=None, pinned=True):
+        chroms, sizes = [], {}
+        with open(prefix + ".chroms.tsv") as fh:
+            for line in fh:
+                c, n = line.rstrip("\n").split("\t")
+                chroms.append(c)
+                sizes[c] = int(n)
+        n_blocks = sum((sizes[c] + 31) // 32 for c in chroms)
+        codes, nmask, pin = cls._alloc(n_blocks, pinned)
+        codes[:] = np.load(prefix + ".codes.npy", mmap_mode="r")
+        nmask[:] = np.load(prefix + ".nmask.npy", mmap_mode="r")
+        return cls(chroms, sizes, codes, nmask, name=os.path.basename(prefix), genome=genome, _pin=pin)
+
+    def __getattr__(self, name):
+        g = self.__dict__.get("genome")
+        if g is None:
+            raise AttributeError(name)
+        return getattr(g, name)
+
+    def planes(self, block0, block1):
+        """Views of the planes of blocks [block0, block1) (no copy: they go to the device as they are)."""
+        return self.codes[2 * block0:2 * block1], self.nmask[block0:block1]
+
+    def fetch_bytes(self, chrom, start, end):
+        """Bases [start, end): the source genome's own bytes when there is one (case and IUPAC codes as in
+        the FASTA, which the background sampler's N count looks at, genome/__init__.py:172-175), else
+        decoded from the planes."""
+        g = self.__dict__.get("genome")
+        if g is not None:
+            fetch = getattr(g, "fetch_bytes", None)
+            return fetch(chrom, start, end) if fetch else g.fetch_sequence(chrom, start, end).encode()
+        return self.decode_bytes(chrom, start, end)
+
+    def decode_bytes(self, chrom, start, end):
+        """Bases [start, end) of a chromosome decoded from the planes to upper-case ASCII, non-ACGT as `N`
+        (`end` clipped at the chromosome size, like pysam's fetch)."""
+        size = self.chrom_sizes[chrom]      # KeyError for unknown chromosomes
+        start, end = max(int(start), 0), min(int(end), size)
+        if end <= start:
+            return b""
+        b0 = int(self.block_off[self.chrom_index[chrom]])
+        w0, w1 = start // 16, (end + 15) // 16
+        cw = np.asarray(self.codes[2 * b0 + w0:2 * b0 + w1])
+        two = ((cw[:, None] >> (2 * np.arange(16, dtype=np.uint32))[None, :]) & 3).astype(np.uint8).ravel()
+        m0, m1 = start // 32, (end + 31) // 32
+        mw = np.asarray(self.nmask[b0 + m0:b0 + m1])
+        isn = ((mw[:, None] >> np.arange(32, dtype=np.uint32)[None, :]) & 1).astype(bool).ravel()
+        out = np.frombuffer(b"ACGT", dtype=np.uint8)[two[start - 16 * w0:end - 16 * w0]]
+        out[isn[start - 32 * m0:end - 32 * m0]] = ord("N")
+        return out.tobytes()
+
+    def fetch_sequence(self, chrom, start, end):
+        return self.fetch_bytes(chrom, start, end).decode("ascii")
+
+    def close(self):
+        self._pin = None
+
+
 class DeviceGenome:
     """The chromosomes of a genome encoded once (2-bit codes + N mask, 0.375 B/bp) and kept resident
     in one GPU's HBM.
@@ -151,6 +284,10 @@ class DeviceGenome:
         self.chroms = list(genome.chroms)
         self.chrom_sizes = {c: int(genome.chrom_sizes[c]) for c in self.chroms}
         self.chrom_index = {c: i for i, c in enumerate(self.chroms)}
+        if isinstance(genome, PackedGenome):    # already packed on the host: the planes go up as they are
+            self.seqs = engine.SequenceSet.from_packed(self.ctx, [self.chrom_sizes[c] for c in self.chroms],
+                                                       genome.codes, genome.nmask)
+            return
         off = np.zeros(len(self.chroms) + 1, dtype=np.int64)
         np.cumsum([self.chrom_sizes[c] for c in self.chroms], out=off[1:])
         blob = np.empty(int(off[-1]), dtype=np.uint8)

@@ -151,6 +151,209 @@ def scan_genome_resident(dgenome, pwms, p_value="1e-4", strand="both", chunk_bp=
     return out
 
 
+# ------------------------------------------------------------------------------------------------
+# Sharded genome scan: several GPUs of one process (one host thread + one context per GPU) and / or
+# several processes (world, rank), over a host `genome.PackedGenome`.
+# ------------------------------------------------------------------------------------------------
+class Unit:
+    """A contiguous run of 32-base blocks [block0, block1) of the packed genome, uploaded with `halo`
+    extra blocks behind it, as the sequences `pieces` = (chromosome index, start, owned end, fetched end):
+    windows that START in [start, owned end) belong to the unit and may read on to `fetched end`."""
+    __slots__ = ("block0", "block1", "upload1", "pieces")
+
+    def __init__(self, block0, block1, upload1, pieces):
+        self.block0, self.block1, self.upload1, self.pieces = block0, block1, upload1, pieces
+
+    @property
+    def owned_bp(self):
+        return sum(b - a for _, a, b, _ in self.pieces)
+
+
+def plan_units(block_off, chrom_sizes, n_shares, unit_blocks, halo_bases):
+    """Cut the packed block space [0, B) into `n_shares` contiguous shares of (almost) equal size and every
+    share into units of at most `unit_blocks` blocks.  Returns a list (per share) of lists of `Unit`.
+    Every base of every chromosome is owned by exactly one unit; share and unit boundaries are multiples
+    of 32 bases inside a chromosome, so a unit's planes are a plain slice of the genome's."""
+    n_blocks = int(block_off[-1])
+    halo = (max(int(halo_bases), 0) + 31) // 32
+    shares = []
+    for k in range(n_shares):
+        s0, s1 = n_blocks * k // n_shares, n_blocks * (k + 1) // n_shares
+        n_units = max(1, -(-(s1 - s0) // max(int(unit_blocks), 1)))
+        units = []
+        for u in range(n_units):
+            u0, u1 = s0 + (s1 - s0) * u // n_units, s0 + (s1 - s0) * (u + 1) // n_units
+            if u1 <= u0:
+                continue
+            pieces = []
+            c = int(np.searchsorted(block_off, u0, side="right")) - 1
+            upload1 = u1
+            while c < len(chrom_sizes) and block_off[c] < u1:
+                cb0, size = int(block_off[c]), int(chrom_sizes[c])
+                a = (max(u0, cb0) - cb0) * 32
+                b = min((min(u1, int(block_off[c + 1])) - cb0) * 32, size)
+                f = min(b + halo * 32, size)
+                if b > a:
+                    pieces.append((c, a, b, f))
+                    upload1 = max(upload1, cb0 + (f + 31) // 32)
+                c += 1
+            units.append(Unit(u0, u1, upload1, pieces))
+        shares.append(units)
+    return shares
+
+
+class ShardedSites(GenomeSites):
+    """GenomeSites over the per-unit results of a sharded scan: the per-motif counts are there at once,
+    the site arrays are gathered on first use (`msb_merge_motif_major`: per motif, unit after unit in
+    genome order -- a copy, no sort) and unit-local (piece, offset) coordinates become (chromosome, start)."""
+
+    def __init__(self, chroms, n_motifs, counts, parts):
+        # parts: list of (ScanResult, piece chromosome index array, piece start array), in genome order
+        GenomeSites.__init__(self, chroms, n_motifs, counts, None, None, None, None, None)
+        self._parts = parts
+        self._merged = False
+
+    def _merge(self):
+        if self._merged:
+            return
+        parts = [p for p in self._parts if p[0].n_sites]
+        if not parts:
+            self.chrom_idx, self.start = np.zeros(0, np.int32), np.zeros(0, np.int32)
+            self.score, self.strand = np.zeros(0, np.float64), np.zeros(0, np.int8)
+        else:
+            cnt = np.stack([p[0].counts for p in parts])
+            first_piece = np.zeros(len(parts), dtype=np.int64)        # global piece number of a part's piece 0
+            np.cumsum([len(p[1]) for p in parts[:-1]], out=first_piece[1:])
+            piece = engine.merge_motif_major(cnt, [p[0].seq_idx for p in parts], add=first_piece)
+            start = engine.merge_motif_major(cnt, [p[0].start for p in parts])
+            self.score = engine.merge_motif_major(cnt, [p[0].score for p in parts])
+            self.strand = engine.merge_motif_major(cnt, [p[0].strand for p in parts])
+            piece_chrom = np.concatenate([p[1] for p in parts]).astype(np.int32)
+            piece_start = np.concatenate([p[2] for p in parts]).astype(np.int32)
+            self.chrom_idx = piece_chrom[piece]
+            if piece_start.any():
+                start += piece_start[piece]
+            self.start = start
+        for p in self._parts:
+            p[0].close()
+        self._parts = []
+        self._merged = True
+
+    def __getattr__(self, name):
+        if name in ("chrom_idx", "start", "score", "strand") and not self.__dict__.get("_merged", True):
+            self._merge()
+            return self.__dict__[name]
+        raise AttributeError(name)
+
+    def close(self):
+        for p in self._parts:
+            p[0].close()
+        self._parts = []
+
+
+class GenomeScanner:
+    """Genome-wide scan of a host `PackedGenome` on several GPUs: `devices` of THIS process (one host thread
+    and one context per device; the C calls drop the GIL) times `world` processes (`rank` = this one).  The
+    packed genome is cut into world x len(devices) contiguous shares; a share is processed in units that
+    are uploaded (0.375 B/bp, asynchronously, on the copy stream), scanned, and whose sites are copied back
+    (asynchronously, on the d2h stream) while the next unit is being scanned.  No device ever talks to
+    another one: the only gather is the host-side sum of the per-motif counts and the per-motif
+    concatenation of the site arrays (the reference's analogue is its in-process
+    thread pool over motifs, cscore.c:323-328, 425-436)."""
+
+    def __init__(self, pg, pwms, cutoffs=None, p_value="1e-4", strand="both", devices=None, world=1, rank=0,
+                 unit_bp=1 << 26, resident=False, contexts=None):
+        self.pg = pg
+        self.matrices = [getattr(pwm, "matrix", pwm) for pwm in pwms]
+        if cutoffs is None:
+            cutoffs = [pwm.cutoffs[p_value] for pwm in pwms]
+        self.cutoffs = np.ascontiguousarray(np.asarray(cutoffs, dtype=np.float64))
+        self.strand = _STRAND_ARG[strand]
+        if contexts is not None:                  # the caller's contexts (e.g. on its own streams), one per device
+            devices = [c.device for c in contexts]
+        self.devices = list(devices) if devices is not None else [0]
+        self.world, self.rank = int(world), int(rank)
+        lmax = max([np.asarray(m).shape[1] for m in self.matrices] + [1])
+        sizes = [pg.chrom_sizes[c] for c in pg.chroms]
+        shares = plan_units(pg.block_off, sizes, self.world * len(self.devices), max(int(unit_bp) // 32, 1), lmax - 1)
+        self.shares = shares[self.rank * len(self.devices):(self.rank + 1) * len(self.devices)]
+        self.ctxs = list(contexts) if contexts is not None else [engine.default_context(d) for d in self.devices]
+        self.motifs = [engine.MotifSet(ctx, self.matrices, self.cutoffs) for ctx in self.ctxs]
+        self.resident = [None] * len(self.devices)     # per device: the uploaded units, kept between scans
+        self.keep_resident = bool(resident)
+        self.last_stats = None
+
+    def _upload(self, ctx, unit, async_):
+        codes, nmask = self.pg.planes(unit.block0, unit.upload1)
+        return engine.SequenceSet.from_packed(ctx, [f - a for _, a, _, f in unit.pieces], codes, nmask, async_=async_)
+
+    def _scan_share(self, k, collect_sites, order_sites=False):
+        ctx, motifs, units = self.ctxs[k], self.motifs[k], self.shares[k]
+        n_motifs = len(self.matrices)
+        counts = np.zeros(n_motifs, dtype=np.int64)
+        parts, stats = [], {}
+        kept = self.resident[k]
+        nxt = None
+        try:
+            for i, unit in enumerate(units):
+                if kept is not None:
+                    sset = kept[i]
+                else:
+                    sset = nxt if nxt is not None else self._upload(ctx, unit, True)
+                    nxt = None
+                    if i + 1 < len(units):        # the next unit's planes travel while this one is scanned
+                        nxt = self._upload(ctx, units[i + 1], True)
+                ranges = [(j, 0, b - a) for j, (_, a, b, _) in enumerate(unit.pieces)]
+                if collect_sites:
+                    res = engine.scan_ranges(ctx, motifs, sset, self.strand, ranges, async_=True)
+                    parts.append((res, np.array([p[0] for p in unit.pieces]), np.array([p[1] for p in unit.pieces])))
+                else:
+                    engine.scan_ranges_device(ctx, motifs, sset, self.strand, ranges, counts_only=not order_sites)
+                    counts += ctx.site_counts(n_motifs)
+                t = ctx.timings()
+                for name in ("prefilter", "exact", "order"):
+                    stats[name] = stats.get(name, 0.0) + t[name]
+                c = ctx.counters()
+                for name in ("launches", "prefilter_launches", "candidates", "hits"):
+                    stats[name] = stats.get(name, 0) + c[name]
+                if self.keep_resident and kept is None:
+                    self.resident[k] = (self.resident[k] or []) + [sset]
+                elif kept is None:
+                    sset.close()
+            for res, _, _ in parts:
+                counts += res.counts            # waits for that unit's copy
+        finally:
+            if nxt is not None:
+                nxt.close()
+        stats["units"] = len(units)
+        return counts, parts, stats
+
+    def scan(self, collect_sites=True, order_sites=False):
+        """One pass over this process's shares.  Returns a `ShardedSites` (`collect_sites=False`: per-motif
+        counts only -- MSB_SCAN_COUNTS, nothing but 8 bytes per motif and unit leaves a device;
+        `order_sites=True` then still orders the sites on the device, as a measurement of that stage)."""
+        n = len(self.devices)
+        if n == 1:
+            outs = [self._scan_share(0, collect_sites, order_sites)]
+        else:
+            import concurrent.futures
+            with concurrent.futures.ThreadPoolExecutor(max_workers=n) as pool:
+                outs = list(pool.map(lambda k: self._scan_share(k, collect_sites, order_sites), range(n)))
+        counts = np.sum([o[0] for o in outs], axis=0)
+        parts = [p for o in outs for p in o[1]]
+        self.last_stats = [o[2] for o in outs]
+        return ShardedSites(self.pg.chroms, len(self.matrices), counts, parts)
+
+    def close(self):
+        for kept in self.resident:
+            for sset in kept or []:
+                sset.close()
+        self.resident = [None] * len(self.devices)
+        for m in self.motifs:
+            m.close()
+        self.motifs = []
+
+
 def plan_chunks(chrom_sizes, chunk_bp, halo, world=1, rank=0):
     """This rank's chunks as (chrom, start, end, fetch_end), in (chromosome, start) order."""
     chunks = shard.genome_chunks(chrom_sizes, chunk_bp, halo)
@@ -161,13 +364,26 @@ def plan_chunks(chrom_sizes, chunk_bp, halo, world=1, rank=0):
 
 
 def scan_genome(genome, pwms, p_value="1e-4", strand="both", chunk_bp=1 << 22, batch_bp=1 << 28,
-                ctx=None, world=1, rank=0, collect_sites=True, cutoffs=None, resident=True):
+                ctx=None, world=1, rank=0, collect_sites=True, cutoffs=None, resident=True, devices=None):
     """Scan all chromosomes of `genome` (anything with `.chroms`, `.chrom_sizes`, `.fetch_bytes`).
+
+    `devices=[...]`: use these GPUs of this process together (`GenomeScanner`; the genome is packed on
+    the host first unless it already is a `genome.PackedGenome`); sites come back gathered in the
+    reference's order, identical to the one-GPU result.
 
     Returns a GenomeSites for this rank's chunks (`collect_sites=False`: counts only, the site
     arrays stay empty and nothing but the counts leaves the device).  A `genome.DeviceGenome` is
     scanned in place; a host genome is first made resident (`resident=True`, the default) or
     streamed chunk by chunk with overlaps (`resident=False`)."""
+    from .genome import PackedGenome
+    if devices is not None or isinstance(genome, PackedGenome):
+        devices = list(devices) if devices is not None else [ctx.device if ctx is not None else 0]
+        pg = genome if isinstance(genome, PackedGenome) else PackedGenome.from_genome(genome, engine.default_context(devices[0]))
+        gs = GenomeScanner(pg, pwms, cutoffs=cutoffs, p_value=p_value, strand=strand, devices=devices, world=world, rank=rank)
+        try:
+            return gs.scan(collect_sites=collect_sites)
+        finally:
+            gs.close()
     if hasattr(genome, "chrom_index") and hasattr(genome, "seqs"):
         return scan_genome_resident(genome, pwms, p_value, strand, chunk_bp, batch_bp, world, rank,
                                     collect_sites, cutoffs)

@@ -21,9 +21,28 @@ MotifSite = namedtuple("MotifSite", ["start", "score", "strand"])  # scanner.py:
 _STRAND_ARG = {"+": 1, "-": 2, "both": 3}  # scanner.py:118-123
 
 
+class _MergedResult:
+    """The gathered arrays of several devices' ScanResults, shaped like one (what MotifSites reads)."""
+
+    def __init__(self, results, block_starts, n_motifs):
+        counts = np.stack([r.counts for r in results]) if results else np.zeros((0, n_motifs), dtype=np.int64)
+        self.counts = counts.sum(axis=0) if len(results) else np.zeros(n_motifs, dtype=np.int64)
+        self.offsets = np.zeros(n_motifs + 1, dtype=np.int64)
+        np.cumsum(self.counts, out=self.offsets[1:])
+        self.n_sites = int(self.counts.sum())
+        # per motif: device 0's sites, then device 1's, ... -- the devices hold ascending blocks of regions,
+        # so this is the reference's (motif, region, start) order; region indices become global on the way
+        self.seq_idx = engine.merge_motif_major(counts, [r.seq_idx for r in results], add=block_starts)
+        self.start = engine.merge_motif_major(counts, [r.start for r in results])
+        self.score = engine.merge_motif_major(counts, [r.score for r in results])
+        self.strand = engine.merge_motif_major(counts, [r.strand for r in results])
+        for r in results:
+            r.close()
+
+
 class Scanner:
     def __init__(self, genome, regions, window_size=0, strand="both", p_value="1e-4",
-                 remove_dup=True, n_threads=1, device=None):
+                 remove_dup=True, n_threads=1, device=None, devices=None):
         self.window_size = window_size if window_size > 0 else 0
         self.extend = window_size // 2
         if strand not in _STRAND_ARG:
@@ -34,13 +53,18 @@ class Scanner:
         # kept for signature compatibility (scanner.py:56-66); the GPU path has no thread count
         self.n_threads = max(1, min(int(n_threads), os.cpu_count() or 1))
         self.device = device
+        # several GPUs of this process: the regions are dealt to them in contiguous blocks, one host thread
+        # and one context per GPU (the reference's n_threads pool over motifs, cscore.c:323-328, 425-436)
+        self.devices = list(devices) if devices is not None else None
         self.seq_starts = []
         self.seq_ends = []
         self._chunks = []
         self._chroms = []
         self._sequences = None
-        # a genome.DeviceGenome keeps the packed chromosomes in HBM: windows are cut out on the device
+        # a genome.DeviceGenome keeps the packed chromosomes in HBM: windows are cut out on the device;
+        # a genome.PackedGenome (host planes) is made resident on every device that scans
         self._resident = genome if hasattr(genome, "extract") and hasattr(genome, "chrom_index") else None
+        self._packed = genome if self._resident is None and hasattr(genome, "planes") else None
         self._genome = genome
         self._extract_seq(genome, regions)
 
@@ -57,8 +81,8 @@ class Scanner:
                 end = min(region.summit + self.extend, sizes[region.chrom])
             self.seq_starts.append(start)
             self.seq_ends.append(end)
-            if self._resident is not None:
-                self._resident.chrom_index[region.chrom]   # KeyError for unknown chromosomes, as fetch raises
+            if self._resident is not None or self._packed is not None:
+                genome.chrom_index[region.chrom]   # KeyError for unknown chromosomes, as fetch raises
                 self._chroms.append(region.chrom)
             elif fetch is not None:
                 self._chunks.append(fetch(region.chrom, start, end))
@@ -68,7 +92,7 @@ class Scanner:
     @property
     def sequences(self):
         if self._sequences is None:
-            if self._resident is not None:   # only materialised when somebody asks for the strings
+            if self._resident is not None or self._packed is not None:   # only materialised when somebody asks for the strings
                 self._sequences = [self._genome.fetch_sequence(c, a, b)
                                    for c, a, b in zip(self._chroms, self.seq_starts, self.seq_ends)]
             else:
@@ -90,31 +114,63 @@ class Scanner:
                 cutoffs.append(pwm.cutoffs[self.p_value])
             except (TypeError, KeyError):
                 raise ValueError(f"PWM has no motif score cutoff set for P-value {self.p_value!r}")
-        if self._resident is not None:
-            ctx = self._resident.ctx       # the windows live where the genome lives
-        if ctx is None:
-            dev = self.device
-            if dev is None:
-                dev = int(os.environ.get("MOTIFSCAN_B200_DEVICE", os.environ.get("LOCAL_RANK", "0")))
-            ctx = engine.default_context(dev)
         matrices = [pwm.matrix for pwm in pwms]
         lengths = [pwm.length for pwm in pwms]
         if not matrices:
             return MotifSites(None, 0, self.seq_starts, lengths)
-        motifs = engine.MotifSet(ctx, matrices, cutoffs)
-        try:
-            if self._resident is not None:
-                sset = self._resident.extract(self._chroms, self.seq_starts, self.seq_ends)
-                try:
-                    res = engine.scan(ctx, motifs, sset, _STRAND_ARG[self.strand], remove_dup=self.remove_dup)
-                finally:
-                    sset.close()
-            else:
-                blob, off = self._flat()
-                res = engine.scan_ascii(ctx, motifs, blob, off, _STRAND_ARG[self.strand], remove_dup=self.remove_dup)
-        finally:
-            motifs.close()
-        return MotifSites(res.detach(), len(matrices), self.seq_starts, lengths)
+        if self._resident is not None:
+            ctxs = [self._resident.ctx]       # the windows live where the genome lives
+        elif ctx is not None:
+            ctxs = [ctx]
+        elif self.devices:
+            ctxs = [engine.default_context(d) for d in self.devices]
+        else:
+            dev = self.device
+            if dev is None:
+                dev = int(os.environ.get("MOTIFSCAN_B200_DEVICE", os.environ.get("LOCAL_RANK", "0")))
+            ctxs = [engine.default_context(dev)]
+        n = len(self.seq_starts)
+        ctxs = ctxs[:max(1, min(len(ctxs), n))]
+        bounds = [n * k // len(ctxs) for k in range(len(ctxs) + 1)]    # contiguous blocks of regions
+        strand = _STRAND_ARG[self.strand]
+
+        def scan_block(k):
+            c, a, b = ctxs[k], bounds[k], bounds[k + 1]
+            motifs = engine.MotifSet(c, matrices, cutoffs)
+            try:
+                if self._resident is not None or self._packed is not None:
+                    dg = self._resident if self._resident is not None else self._packed_on(c)
+                    sset = dg.extract(self._chroms[a:b], self.seq_starts[a:b], self.seq_ends[a:b])
+                    try:
+                        return engine.scan(c, motifs, sset, strand, remove_dup=self.remove_dup)
+                    finally:
+                        sset.close()
+                chunks = self._chunks[a:b]
+                off = np.zeros(len(chunks) + 1, dtype=np.int64)
+                if chunks:
+                    np.cumsum([len(x) for x in chunks], out=off[1:])
+                blob = np.frombuffer(b"".join(chunks), dtype=np.uint8)
+                return engine.scan_ascii(c, motifs, blob, off, strand, remove_dup=self.remove_dup)
+            finally:
+                motifs.close()
+
+        if len(ctxs) == 1:
+            res = scan_block(0).detach()
+        else:
+            import concurrent.futures
+            with concurrent.futures.ThreadPoolExecutor(max_workers=len(ctxs)) as pool:
+                results = list(pool.map(scan_block, range(len(ctxs))))
+            res = _MergedResult(results, bounds[:-1], len(matrices))
+        return MotifSites(res, len(matrices), self.seq_starts, lengths)
+
+    def _packed_on(self, ctx):
+        """The device-resident copy of a host PackedGenome on `ctx`'s GPU (made on first use, kept on the
+        PackedGenome so that target and control scanners share it)."""
+        from .genome import DeviceGenome
+        cache = self._packed.__dict__.setdefault("_device_copies", {})
+        if ctx.device not in cache:
+            cache[ctx.device] = DeviceGenome(self._packed, ctx)
+        return cache[ctx.device]
 
 
 class _PerMotif:

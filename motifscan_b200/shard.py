@@ -43,41 +43,60 @@ def assign_lpt(costs, world):
     return owner, load
 
 
-def drop_halo_sites(seq_idx, start, motif_len_of_site, own_len):
-    """Mask of sites whose START lies in the chunk's own range [0, own_len[seq]) -- sites that
-    start inside the halo belong to the next chunk."""
-    return start < own_len[seq_idx]
+def gather_counts(counts, dist=None):
+    """The final gather of a sharded scan: per-motif site counts summed over the ranks (one all-reduce of
+    n_motifs int64 on the process group's host backend; NCCL is not on this path).  Every rank gets the sum."""
+    counts = np.ascontiguousarray(np.asarray(counts, dtype=np.int64))
+    if dist is None or not dist.is_initialized() or dist.get_world_size() == 1:
+        return counts.copy()
+    import torch
+    t = torch.from_numpy(counts.copy())
+    dist.all_reduce(t)
+    return t.numpy()
 
 
 def gather_sites(local, n_motifs, dist=None, dst=0):
-    """Gather per-rank site arrays on rank `dst` and restore the reference's order.
+    """Gather per-rank site arrays on rank `dst` in the reference's order (cscore.c:336-389: motif, sequence,
+    start, forward before reverse).
 
-    `local` = dict(counts int64[n_motifs], motif int32[T], seq int64[T] (GLOBAL sequence ids),
-    start int64[T], score float64[T], strand int8[T]).  Sequence ids must be global and each
-    sequence must live on exactly one rank, so sorting the concatenation by (motif, seq, start,
-    strand) reproduces the unsharded list order (cscore.c:336-389).  Returns the merged dict on
-    `dst`, None elsewhere.  With dist=None (single process) it only re-sorts."""
+    `local` = dict(counts int64[n_motifs], seq int64[T] (GLOBAL sequence ids), start int64[T],
+    score float64[T], strand int8[T]), motif-major, each rank holding an ASCENDING block of the sequences
+    (`region_block`), so motif m's gathered list is rank 0's slice, then rank 1's, ...: the arrays travel as
+    plain tensors (`dist.gather`, padded to the largest rank) and are interleaved by
+    `engine.merge_motif_major` -- no pickling, no sort.  Returns the merged dict (with `motif`) on `dst`,
+    None elsewhere; with dist=None (single process) it returns the input's arrays."""
+    from . import engine
+    names = ("seq", "start", "score", "strand")
+    counts = np.ascontiguousarray(np.asarray(local["counts"], dtype=np.int64))
     if dist is None or not dist.is_initialized() or dist.get_world_size() == 1:
-        parts = [local]
+        parts_counts = counts[None, :]
+        parts = {k: [np.ascontiguousarray(local[k])] for k in names}
     else:
-        parts = [None] * dist.get_world_size() if dist.get_rank() == dst else None
-        dist.gather_object(local, parts, dst=dst)
-        if dist.get_rank() != dst:
+        import torch
+        world, rank = dist.get_world_size(), dist.get_rank()
+        all_counts = [torch.zeros(n_motifs, dtype=torch.int64) for _ in range(world)]
+        dist.all_gather(all_counts, torch.from_numpy(counts.copy()))
+        parts_counts = np.stack([c.numpy() for c in all_counts])
+        totals = parts_counts.sum(axis=1)
+        width = int(totals.max())
+        parts = {}
+        for k in names:
+            arr = np.ascontiguousarray(local[k])
+            padded = np.zeros(width, dtype=arr.dtype)
+            padded[:arr.size] = arr
+            recv = [torch.zeros(width, dtype=torch.from_numpy(padded).dtype) for _ in range(world)] if rank == dst else None
+            dist.gather(torch.from_numpy(padded), recv, dst=dst)
+            if rank == dst:
+                parts[k] = [recv[r].numpy()[:int(totals[r])] for r in range(world)]
+        if rank != dst:
             return None
-    motif = np.concatenate([p["motif"] for p in parts])
-    seq = np.concatenate([p["seq"] for p in parts])
-    start = np.concatenate([p["start"] for p in parts])
-    score = np.concatenate([p["score"] for p in parts])
-    strand = np.concatenate([p["strand"] for p in parts])
-    order = np.lexsort((strand, start, seq, motif))
-    counts = np.sum([p["counts"] for p in parts], axis=0)
-    return dict(counts=counts, motif=motif[order], seq=seq[order], start=start[order],
-                score=score[order], strand=strand[order])
+    out = {k: engine.merge_motif_major(parts_counts, parts[k]) for k in names}
+    out["counts"] = parts_counts.sum(axis=0)
+    out["motif"] = np.repeat(np.arange(n_motifs, dtype=np.int32), out["counts"])
+    return out
 
 
 def result_to_local(res, n_motifs, seq_global_ids):
     """engine.ScanResult -> the dict gather_sites expects (sequence ids mapped to global ids)."""
-    motif = np.repeat(np.arange(n_motifs, dtype=np.int32), res.counts)
-    return dict(counts=res.counts.copy(), motif=motif,
-                seq=np.asarray(seq_global_ids, dtype=np.int64)[res.seq_idx],
+    return dict(counts=res.counts.copy(), seq=np.asarray(seq_global_ids, dtype=np.int64)[res.seq_idx],
                 start=res.start.astype(np.int64), score=res.score.copy(), strand=res.strand.copy())

@@ -89,3 +89,60 @@ def genome_chunk(n_bases, seed, n_block=None):
         a, ln = n_block
         s[a:a + ln] = ord("N")
     return s
+
+
+def pack_ascii(blob):
+    """numpy restatement of the library's packed layout for ONE sequence (include/msb200.h,
+    msb_seqs_from_packed): (codes uint32[2 B], nmask uint32[B]), B = ceil(len / 32).  Test / bench
+    infrastructure: the product encodes on the device (encode_pack_kernel)."""
+    blob = np.asarray(blob, dtype=np.uint8)
+    n = blob.size
+    n_blocks = (n + 31) // 32
+    lut = np.full(256, 4, dtype=np.uint8)
+    for k, ch in enumerate(b"ACGT"):
+        lut[ch] = k
+        lut[ch | 0x20] = k
+    c = np.zeros(n_blocks * 32, dtype=np.uint8)
+    c[:n] = lut[blob]
+    isn = c == 4
+    isn[n:] = False
+    c[c == 4] = 0
+    c[n:] = 0
+    sh2 = (2 * np.arange(16, dtype=np.uint64))[None, :]
+    codes = (c.reshape(-1, 16).astype(np.uint64) << sh2).sum(axis=1).astype(np.uint32)
+    sh1 = np.arange(32, dtype=np.uint64)[None, :]
+    nmask = (isn.reshape(-1, 32).astype(np.uint64) << sh1).sum(axis=1).astype(np.uint32)
+    return codes, nmask
+
+
+def packed_genome(sizes, names=None, seed=19, n_frac=0.07, pinned=False):
+    """A small synthetic `genome.PackedGenome` for tests: iid bases of the synthetic composition, 10 kb-scaled
+    N runs at both chromosome ends and one interior N block per chromosome (about `n_frac` of it)."""
+    from .genome import PackedGenome
+    rng = np.random.default_rng(seed)
+    names = names or [f"chr{i + 1:02d}" for i in range(len(sizes))]
+    order = sorted(range(len(sizes)), key=lambda i: names[i])
+    chroms = [names[i] for i in order]
+    cs, ms = [], []
+    for i in order:
+        n = int(sizes[i])
+        s = random_bases(rng, n)
+        if n_frac > 0 and n >= 200:
+            edge = max(1, min(10000, n // 50))
+            s[:edge] = ord("N")
+            s[n - edge:] = ord("N")
+            ln = int(n * n_frac)
+            a = int(rng.integers(edge, max(n - edge - ln, edge + 1)))
+            s[a:a + ln] = ord("N")
+        c, m = pack_ascii(s)
+        cs.append(c)
+        ms.append(m)
+    codes = np.concatenate(cs) if cs else np.zeros(0, np.uint32)
+    nmask = np.concatenate(ms) if ms else np.zeros(0, np.uint32)
+    if pinned:
+        pc, pm, pin = PackedGenome._alloc(nmask.size, True)
+        pc[:], pm[:] = codes, nmask
+        codes, nmask = pc, pm
+    else:
+        pin = None
+    return PackedGenome(chroms, {names[i]: int(sizes[i]) for i in order}, codes, nmask, name="synthetic", _pin=pin)

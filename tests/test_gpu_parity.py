@@ -241,13 +241,13 @@ def test_lane_record_buffer_overflow_retry(eng):
     sset = eng.SequenceSet(ctx, seqs)
     expect = oracle.scan_arrays(pwms, cutoffs, seqs, 3, n_threads=8)
     try:
-        _lib.check(_lib.load().msb_set_option(b"tc_first_lane_cap", 2))
+        ctx.set_option("tc_first_lane_cap", 2)
         res = eng.scan(ctx, motifs, sset, 3)
         assert ctx.counters()["retries"] >= 1
         assert_scan_equal(res, expect)
         res.close()
     finally:
-        _lib.check(_lib.load().msb_set_option(b"tc_first_lane_cap", 0))
+        ctx.set_option("tc_first_lane_cap", 0)
     res = eng.scan(ctx, motifs, sset, 3)
     assert ctx.counters()["retries"] == 0
     assert_scan_equal(res, expect)
@@ -281,14 +281,14 @@ def test_prefilter_w8_same_sites(eng):
     sset = eng.SequenceSet(ctx, seqs)
     expect = oracle.scan_arrays(pwms, cutoffs, seqs, 3, n_threads=8)
     try:
-        _lib.check(_lib.load().msb_set_option(b"prefilter_tc", 0))
-        _lib.check(_lib.load().msb_set_option(b"prefilter_w", 8))
+        ctx.set_option("prefilter_tc", 0)
+        ctx.set_option("prefilter_w", 8)
         res = eng.scan(ctx, motifs, sset, 3)
         assert_scan_equal(res, expect)
         res.close()
     finally:
-        _lib.check(_lib.load().msb_set_option(b"prefilter_w", 4))
-        _lib.check(_lib.load().msb_set_option(b"prefilter_tc", 1))
+        ctx.set_option("prefilter_w", 4)
+        ctx.set_option("prefilter_tc", 1)
     sset.close(), motifs.close()
 
 
@@ -309,13 +309,13 @@ def test_table_and_tensor_prefilters_same_sites(eng, strand):
     cand = {}
     try:
         for tc in (0, 1):
-            _lib.check(_lib.load().msb_set_option(b"prefilter_tc", tc))
+            ctx.set_option("prefilter_tc", tc)
             res = eng.scan(ctx, motifs, sset, strand)
             assert_scan_equal(res, expect)
             cand[tc] = ctx.counters()["candidates"]
             res.close()
     finally:
-        _lib.check(_lib.load().msb_set_option(b"prefilter_tc", 1))
+        ctx.set_option("prefilter_tc", 1)
     assert cand[1] <= 3 * cand[0] + 1000, cand
     sset.close(), motifs.close()
 
@@ -386,6 +386,38 @@ def test_scan_ascii_sliced_upload_equals_two_step_scan(eng):
     ref = oracle.scan_arrays(pwms, cutoffs, seqs[:40], 3, n_threads=4)
     assert_scan_equal(small, ref)
     small.close(), pinned.close(), sset.close(), motifs.close()
+
+
+def test_sliced_scan_after_a_differently_sized_scan_with_a_poisoned_pool(eng):
+    """The device buffers of a sequence set come from a recycling pool.  msb_scan_ascii scans slice k
+    before slice k + 1 is encoded, and the last position tile of a slice reaches into the next slice's
+    blocks: nothing there (codes, mask, block-owner table) may be read as if it were valid.  The pool
+    is poisoned (0xFF) between two sliced scans of different shapes; results must still be the
+    two-step scan's, which is checked against the oracle on a prefix."""
+    from motifscan_b200 import _lib
+    rng = np.random.default_rng(177)
+    pwms = synth_pwms(rng, 16)
+    ctx = eng.Context(0)
+    ctx.set_option("poison_pool", 1)
+    try:
+        for n, lo, hi in ((5000, 1500, 2500), (9000, 800, 1200), (2500, 3300, 3500)):
+            seqs = synth_seqs(rng, n, lo, hi, p_n=0.0005, n_blocks=True)
+            cutoffs = cutoffs_for(pwms, seqs[:200], 5e-4)
+            blob, off = _lib.flatten_seqs(seqs)
+            assert blob.size >= (8 << 20)
+            motifs = eng.MotifSet(ctx, pwms, cutoffs)
+            got = eng.scan_ascii(ctx, motifs, blob, off, 3)
+            sset = eng.SequenceSet(ctx, blob=blob, seq_off=off)
+            want = eng.scan(ctx, motifs, sset, 3)
+            assert got.n_sites == want.n_sites > 1000
+            assert np.array_equal(got.counts, want.counts) and np.array_equal(got.seq_idx, want.seq_idx)
+            assert np.array_equal(got.start, want.start) and np.array_equal(got.strand, want.strand)
+            assert np.array_equal(got.score.view(np.uint64), want.score.view(np.uint64))
+            head = eng.scan_ascii(ctx, motifs, blob[:off[300]], off[:301], 3)
+            assert_scan_equal(head, oracle.scan_arrays(pwms, cutoffs, seqs[:300], 3, n_threads=8))
+            head.close(), got.close(), want.close(), sset.close(), motifs.close()
+    finally:
+        ctx.close()
 
 
 def test_threads_sharing_a_context_are_serialised(eng):

@@ -1,0 +1,139 @@
+"""CPU tests of the host logic added for the multi-GPU paths: share / unit planning over the packed genome,
+the packed layout's numpy restatement, the host-side gather (msb_merge_motif_major is plain host code in the
+library: it loads and runs without a GPU), and the world-size-2 count gather over gloo."""
+import os
+import socket
+import sys
+
+import numpy as np
+import pytest
+
+from conftest import ROOT
+
+
+def test_merge_motif_major_equals_a_stable_sort():
+    from motifscan_b200 import engine
+    rng = np.random.default_rng(1)
+    for n_parts, n_motifs, scale in ((1, 5, 10), (4, 750, 40), (8, 13, 200000), (3, 1, 7), (5, 40, 0)):
+        counts = rng.integers(0, scale + 1, size=(n_parts, n_motifs)).astype(np.int64)
+        parts_motif = [np.repeat(np.arange(n_motifs), counts[p]) for p in range(n_parts)]
+        for dtype in (np.int32, np.float64, np.int8):
+            arrays = [rng.integers(-100, 100, size=int(counts[p].sum())).astype(dtype) for p in range(n_parts)]
+            got = engine.merge_motif_major(counts, arrays)
+            motif = np.concatenate(parts_motif)
+            order = np.argsort(motif, kind="stable")          # part order is kept within a motif
+            assert np.array_equal(got, np.concatenate(arrays)[order])
+        seq = [rng.integers(0, 1000, size=int(counts[p].sum())).astype(np.int32) for p in range(n_parts)]
+        add = np.arange(n_parts, dtype=np.int64) * 1000
+        got = engine.merge_motif_major(counts, seq, add=add)
+        want = np.concatenate([s + int(a) for s, a in zip(seq, add)])[np.argsort(np.concatenate(parts_motif), kind="stable")]
+        assert np.array_equal(got, want)
+    assert engine.merge_motif_major(np.zeros((0, 4), dtype=np.int64), []).size == 0
+
+
+def test_plan_units_partitions_hg19():
+    from motifscan_b200.genome_scan import plan_units
+    from motifscan_b200.synth import HG19_NAMES, HG19_SIZES
+    order = sorted(range(len(HG19_NAMES)), key=lambda i: HG19_NAMES[i])
+    sizes = [HG19_SIZES[i] for i in order]
+    block_off = np.zeros(len(sizes) + 1, dtype=np.int64)
+    np.cumsum([(s + 31) // 32 for s in sizes], out=block_off[1:])
+    for n_shares in (1, 2, 4, 8):
+        shares = plan_units(block_off, sizes, n_shares, (1 << 26) // 32, 29)
+        assert len(shares) == n_shares
+        per_share = [sum(u.owned_bp for u in units) for units in shares]
+        assert sum(per_share) == sum(sizes)
+        assert max(per_share) / (sum(per_share) / n_shares) < 1.001           # shares balance to 0.1 %
+        owned = {c: [] for c in range(len(sizes))}
+        for units in shares:
+            for u in units:
+                assert u.block1 - u.block0 <= (1 << 26) // 32 and u.upload1 - u.block1 <= 1
+                at = u.block0
+                for c, a, b, f in u.pieces:
+                    assert a % 32 == 0 and a < b <= f <= sizes[c] and f - b == min(32, sizes[c] - b)
+                    assert block_off[c] + a // 32 == at       # the pieces tile the uploaded planes
+                    at += (f - a + 31) // 32
+                    owned[c].append((a, b))
+                assert at == u.upload1
+        for c, spans in owned.items():                         # every base owned exactly once
+            spans.sort()
+            assert spans[0][0] == 0 and spans[-1][1] == sizes[c]
+            assert all(spans[i][1] == spans[i + 1][0] for i in range(len(spans) - 1))
+
+
+def test_packed_layout_restatement_and_decode():
+    from motifscan_b200 import synth
+    import oracle
+    rng = np.random.default_rng(2)
+    alphabet = np.frombuffer(b"ACGTacgtNnRy-", dtype=np.uint8)
+    for n in (1, 15, 16, 17, 31, 32, 33, 1000):
+        s = alphabet[rng.integers(0, len(alphabet), size=n)]
+        codes, nmask = synth.pack_ascii(s)
+        assert nmask.size == (n + 31) // 32 and codes.size == 2 * nmask.size
+        want = oracle.encode(bytes(s).decode())               # the reference's int8 codes (cscore.c:81-114)
+        two = ((codes[:, None] >> (2 * np.arange(16, dtype=np.uint32))[None, :]) & 3).ravel()[:n].astype(np.int8)
+        isn = ((nmask[:, None] >> np.arange(32, dtype=np.uint32)[None, :]) & 1).ravel()[:n].astype(bool)
+        assert np.array_equal(np.where(isn, -1, two), want)
+        assert not two[isn].any()                             # N -> code 0
+    pg = synth.packed_genome([5000, 333, 64, 10001, 31], seed=3)
+    for c in pg.chroms:
+        whole = pg.decode_bytes(c, 0, 1 << 40)
+        assert len(whole) == pg.chrom_sizes[c]
+        for a, b in ((0, 1), (5, 77), (31, 33), (100, 100), (pg.chrom_sizes[c] - 3, pg.chrom_sizes[c] + 9)):
+            assert pg.decode_bytes(c, a, b) == whole[max(a, 0):b]
+    with pytest.raises(KeyError):
+        pg.decode_bytes("chrNope", 0, 1)
+
+
+def _free_port():
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    port = s.getsockname()[1]
+    s.close()
+    return port
+
+
+def _worker(rank, world, port, q):
+    sys.path.insert(0, ROOT)
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
+    import torch.distributed as dist
+    import oracle
+    from motifscan_b200 import shard, synth
+    from motifscan_b200.genome_scan import plan_units
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        # a sharded genome scan with the oracle as the per-unit scanner: this rank's units -> counts -> gather
+        pg = synth.packed_genome([9000, 4001, 700], seed=8)
+        rng = np.random.default_rng(9)
+        pwms = [np.around(rng.normal(0, 2, size=(4, int(rng.integers(4, 20)))), 5).tolist() for _ in range(6)]
+        cutoffs = [0.4] * len(pwms)
+        sizes = [pg.chrom_sizes[c] for c in pg.chroms]
+        shares = plan_units(pg.block_off, sizes, world, 40, max(len(p[0]) for p in pwms) - 1)
+        counts = np.zeros(len(pwms), dtype=np.int64)
+        for unit in shares[rank]:
+            for c, a, b, f in unit.pieces:
+                seq = pg.decode_bytes(pg.chroms[c], a, f).decode()
+                cnt, _, start, _, _ = oracle.scan_arrays(pwms, cutoffs, [seq], 3)
+                motif = np.repeat(np.arange(len(pwms)), cnt)
+                counts += np.bincount(motif[start < b - a], minlength=len(pwms))    # starts in the halo belong to the next unit
+        total = shard.gather_counts(counts, dist)
+        whole = [pg.decode_bytes(c, 0, pg.chrom_sizes[c]).decode() for c in pg.chroms]
+        full = oracle.scan_arrays(pwms, cutoffs, whole, 3)[0]
+        q.put(bool(np.array_equal(total, full) and full.sum() > 100 and counts.sum() < full.sum()))
+    finally:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+def test_two_rank_sharded_count_gather():
+    import torch.multiprocessing as mp
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    for p in procs:
+        p.join(timeout=120)
+        assert p.exitcode == 0
+    assert q.get(timeout=5) is True and q.get(timeout=5) is True
