@@ -73,7 +73,8 @@ int msb_ctx_counters(const msb_ctx *ctx, int64_t *v, int n);
  * (4 or 8); "ascii_slices" upload slices of msb_scan_ascii (1..7); "tc_first_lane_cap" records per lane
  * buffer on the first attempt (tests of the overflow retry; 0 = sized from the input); "poison_pool" 1 =
  * recycled device buffers are filled with 0xFF (tests: nothing may rely on stale contents); "tc_prof" 1
- * = per-role cycle counters of the tensor-core prefilter on stderr. */
+ * = per-role cycle counters of the tensor-core prefilter on stderr; "select_pilot" 0 = msb_score_select scores
+ * every sample for every motif instead of the pilot + scan scheme (A/B tests). */
 int msb_ctx_set_option(msb_ctx *ctx, const char *name, int value);
 
 /* Pinned host memory for callers that want full-speed H2D (cudaHostAlloc / cudaFreeHost). */
@@ -209,10 +210,11 @@ int msb_merge_motif_major(int32_t n_parts, int32_t n_motifs, const int64_t *coun
 /* out is n_motifs x n_seqs row-major: the offset-0 window score of every sequence. */
 int msb_score(msb_ctx *ctx, const msb_motifs *motifs, const msb_seqs *seqs, int strand,
               double *out);
-/* Fused `motif --build` step (cli/motif.py:133-137 + motif/__init__.py:378-401): score as
- * above with strand 3, then for every motif return the n_ranks order statistics
- * sorted_descending(scores)[ranks[k]] without moving the score matrix to the host.
- * out is n_motifs x n_ranks row-major. */
+/* Fused `motif --build` step (cli/motif.py:133-137 + motif/__init__.py:378-401): for every motif the
+ * n_ranks (<= 8) order statistics sorted_descending(scores of all sequences)[ranks[k]], bit-identical to
+ * sorting msb_score's rows, without ever materialising the score matrix when the ranks sit in the top
+ * 1/32 of a large sample (a pilot picks per-motif thresholds, the scan path returns the samples above them
+ * with their exact scores, a radix select reads the ranks).  out is n_motifs x n_ranks row-major. */
 int msb_score_select(msb_ctx *ctx, const msb_motifs *motifs, const msb_seqs *seqs, int strand,
                      int32_t n_ranks, const int64_t *ranks, double *out);
 

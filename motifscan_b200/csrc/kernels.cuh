@@ -744,6 +744,161 @@ score0_kernel(SeqView S, MotifView M, int strand, int32_t m_begin, int32_t m_end
     }
 }
 
+// ---------------------------------------------------------------------------------------------
+// Order statistics of score distributions (get_score_cutoffs, motif/__init__.py:378-401: sort
+// descending, read a handful of indices) by radix SELECT instead of a sort.
+//
+// order_key: the bijection double -> uint64 whose unsigned order is the order a radix sort of doubles
+// uses (negative values below positive ones, -0.0 below +0.0, NaNs at the ends by bit pattern), so the
+// selected values are the ones msb_score_select's former cub::DeviceSegmentedRadixSort returned.
+// Key 0 (the bit pattern of a negative NaN with every payload bit set) marks a dead entry.
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint64_t order_key(double v) {
+    const uint64_t b = (uint64_t) __double_as_longlong(v);
+    return (b >> 63) ? ~b : (b | 0x8000000000000000ull);
+}
+__device__ __forceinline__ double order_key_inv(uint64_t k) {
+    const uint64_t b = (k >> 63) ? (k & 0x7fffffffffffffffull) : ~k;
+    return __longlong_as_double((long long) b);
+}
+
+constexpr int kSelMaxRanks = 8;
+constexpr int kSelThreads = 512;
+
+// One block per segment.  Segment s holds the keys (kFromDoubles: doubles, keyed on the fly) at
+// data[begin .. end) with begin = seg_off ? seg_off[s] : s * stride and end = seg_off ? seg_off[s + 1] :
+// begin + stride.  out[s * n_ranks + j] = the ranks[j]-th largest value (0-based), found digit by digit
+// from the top: per 8-bit digit one pass over the segment builds, for every group of ranks that still share
+// a prefix, the histogram of the next digit among the keys with that prefix; the bucket that holds the rank
+// extends the prefix.  Eight passes for all ranks together; the segment is staged in shared memory when
+// it fits (smem_keys), else re-read from L2.  Warp-level vote merges equal digits before the
+// shared-memory atomic: score keys share their top bytes.  ok[s] (optional) = 0 when some rank is not
+// below live[s] (the number of entries that are not dead).
+template <bool kFromDoubles>
+__global__ void __launch_bounds__(kSelThreads)
+select_ranks_kernel(const void *__restrict__ data, const int64_t *__restrict__ seg_off, int64_t stride,
+                    const int64_t *__restrict__ ranks, int n_ranks, int smem_keys, const int64_t *__restrict__ live,
+                    double *__restrict__ out, int32_t *__restrict__ ok) {
+    extern __shared__ __align__(16) uint64_t s_keys[];
+    __shared__ unsigned int s_hist[kSelMaxRanks][256];
+    __shared__ uint64_t s_prefix[kSelMaxRanks];
+    __shared__ long long s_rank[kSelMaxRanks];
+    __shared__ int s_group[kSelMaxRanks], s_ngroups;
+    const int seg = blockIdx.x;
+    const int64_t begin = seg_off ? seg_off[seg] : (int64_t) seg * stride;
+    const int64_t n = seg_off ? seg_off[seg + 1] - begin : stride;
+    const int64_t n_live = live ? live[seg] : n;
+    const uint64_t *keys = reinterpret_cast<const uint64_t *>(data) + begin;
+    const double *vals = reinterpret_cast<const double *>(data) + begin;
+    const bool staged = n <= (int64_t) smem_keys;
+    if (staged)
+        for (int64_t i = threadIdx.x; i < n; i += kSelThreads) s_keys[i] = kFromDoubles ? order_key(vals[i]) : keys[i];
+    if (threadIdx.x < n_ranks) {
+        s_prefix[threadIdx.x] = 0;
+        s_rank[threadIdx.x] = ranks[threadIdx.x];
+    }
+    if (threadIdx.x == 0) {
+        bool fine = true;
+        for (int j = 0; j < n_ranks; j++) fine = fine && ranks[j] >= 0 && ranks[j] < n_live;
+        if (ok) ok[seg] = fine ? 1 : 0;
+        s_ngroups = fine ? 1 : 0;
+        for (int j = 0; j < n_ranks; j++) s_group[j] = 0;
+    }
+    __syncthreads();
+    if (s_ngroups == 0) {   // not enough live entries: the caller takes another path for this segment
+        if (threadIdx.x < n_ranks) out[(int64_t) seg * n_ranks + threadIdx.x] = __longlong_as_double(0x7ff8000000000000ll);
+        return;
+    }
+    for (int shift = 56; shift >= 0; shift -= 8) {
+        const int ng = s_ngroups;
+        for (int i = threadIdx.x; i < ng * 256; i += kSelThreads) (&s_hist[0][0])[i] = 0;
+        __syncthreads();
+        const uint64_t mask = shift == 56 ? 0ull : (~0ull << (shift + 8));
+        // group g's prefix = the prefix of its first rank
+        uint64_t gp[kSelMaxRanks];
+        {
+            int g = 0;
+            for (int j = 0; j < n_ranks && g < ng; j++)
+                if (s_group[j] == g) gp[g++] = s_prefix[j];
+        }
+        const int64_t n_round = (n + 31) / 32 * 32;   // whole warps take part in the vote
+        for (int64_t i = threadIdx.x; i < n_round; i += kSelThreads) {
+            const bool have = i < n;
+            const uint64_t k = !have ? 0ull : (staged ? s_keys[i] : (kFromDoubles ? order_key(vals[i]) : keys[i]));
+            int g = -1;
+            if (have)
+                for (int t = 0; t < ng; t++)
+                    if ((k & mask) == gp[t]) g = t;
+            // lanes with the same (group, digit) elect one to add their number
+            const unsigned int tag = g < 0 ? 0xffffffffu : (unsigned int) (g * 256 + (int) ((k >> shift) & 255));
+            const unsigned int peers = __match_any_sync(0xffffffffu, tag);
+            if (g >= 0 && (threadIdx.x & 31) == __ffs(peers) - 1) atomicAdd(&s_hist[0][0] + tag, (unsigned int) __popc(peers));
+        }
+        __syncthreads();
+        if (threadIdx.x < n_ranks) {
+            const int j = threadIdx.x;
+            const unsigned int *h = s_hist[s_group[j]];
+            long long r = s_rank[j], above = 0;
+            int b = 255;
+            for (; b > 0; b--) {
+                if (above + (long long) h[b] > r) break;
+                above += h[b];
+            }
+            s_rank[j] = r - above;
+            s_prefix[j] |= (uint64_t) b << shift;
+        }
+        __syncthreads();
+        if (threadIdx.x == 0) {   // regroup: ranks with equal prefixes share a histogram in the next pass
+            int ngn = 0;
+            for (int j = 0; j < n_ranks; j++) {
+                int g = -1;
+                for (int t = 0; t < j; t++)
+                    if (s_prefix[t] == s_prefix[j]) { g = s_group[t]; break; }
+                s_group[j] = g >= 0 ? g : ngn++;
+            }
+            s_ngroups = ngn;
+        }
+        __syncthreads();
+    }
+    if (threadIdx.x < n_ranks) out[(int64_t) seg * n_ranks + threadIdx.x] = order_key_inv(s_prefix[threadIdx.x]);
+}
+
+// After a scan with a start limit of 1 (only the offset-0 window of every sample) the sorted site list holds,
+// per motif, one site per (sample, strand) that reached the pilot cutoff.  c_score's value for strand 3 is the
+// better strand (cscore.c:215-221): key[i] = order_key(max over the sample's sites); the second site of a
+// sample becomes a dead entry (key 0) and is counted in dead[motif].
+__global__ void __launch_bounds__(256)
+sample_keys_kernel(const uint64_t *__restrict__ site_key, const int32_t *__restrict__ seq_idx,
+                   const double *__restrict__ score, int64_t n, int key_shift, uint64_t *__restrict__ key,
+                   unsigned long long *__restrict__ dead) {
+    const int64_t i = (int64_t) blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const uint32_t m = site_motif(site_key[i], key_shift);
+    const int32_t s = seq_idx[i];
+    if (i > 0 && site_motif(site_key[i - 1], key_shift) == m && seq_idx[i - 1] == s) {
+        key[i] = 0;
+        atomicAdd(dead + m, 1ull);
+        return;
+    }
+    uint64_t k = order_key(score[i]);
+    if (i + 1 < n && site_motif(site_key[i + 1], key_shift) == m && seq_idx[i + 1] == s) k = max(k, order_key(score[i + 1]));
+    key[i] = k;
+}
+
+// live[m] = offsets[m + 1] - offsets[m] - dead[m]
+__global__ void __launch_bounds__(256)
+live_counts_kernel(const int64_t *__restrict__ offsets, const unsigned long long *__restrict__ dead, int32_t n_motifs,
+                   int64_t *__restrict__ live) {
+    const int32_t m = blockIdx.x * blockDim.x + threadIdx.x;
+    if (m < n_motifs) live[m] = offsets[m + 1] - offsets[m] - (int64_t) dead[m];
+}
+
+// fill an int32 array with one value (the start limit of the offset-0 scan)
+__global__ void __launch_bounds__(256) fill_i32_kernel(int32_t *__restrict__ p, int64_t n, int32_t v) {
+    const int64_t i = (int64_t) blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) p[i] = v;
+}
+
 __global__ void __launch_bounds__(256)
 gather_ranks_kernel(const double *__restrict__ sorted, int64_t n_seqs, int32_t n_motifs_chunk,
                     const int64_t *__restrict__ ranks, int32_t n_ranks, double *__restrict__ out) {

@@ -25,6 +25,8 @@
 
 namespace msb {
 
+static constexpr int kSelSmemKeys = 24576;   // select_ranks_kernel: 192 KB of staged keys per block
+
 static thread_local std::string g_err;
 void set_error(const std::string &msg) { g_err = msg; }
 int cuda_fail(cudaError_t e, const char *what, const char *file, int line) {
@@ -76,7 +78,7 @@ struct msb_ctx {
     // scratch (grow-only, reused across calls)
     DevBuf ascii, seq_off, cand, dirty, hit_key, hit_score, key_alt, score_alt, sort_tmp, counters;
     DevBuf out_seq, out_start, out_strand, scores, scores_sorted, seg_off, ranks, sel;
-    DevBuf keep, keep_pos, motif_counts;
+    DevBuf keep, keep_pos, motif_counts, sel_aux, limit1;
     DevBuf lane_count;   // tensor-core prefilter: records per epilogue lane
     // Final site arrays of a scan.  Two sets, used alternately: the device-to-host copy of scan k's
     // sites (on d2h_stream, MSB_SCAN_ASYNC) reads one set while scan k + 1 fills the other.
@@ -110,6 +112,7 @@ struct msb_ctx {
     int opt_ascii_slices = 4;        // msb_scan_ascii: upload slices (1..7)
     int opt_tc_first_lane_cap = 0;   // tests: records per lane buffer on the first attempt (0 = sized from the input)
     int opt_poison_pool = 0;         // tests: fill device buffers with 0xFF when they go back to the pool
+    int opt_select_pilot = 1;        // msb_score_select: 0 = always score every sample for every motif (the plain form)
 };
 
 struct TableSet {
@@ -220,7 +223,8 @@ static int pinned_get(msb_ctx *ctx, size_t bytes, PinnedBlock *out) {
             return MSB_OK;
         }
     }
-    size_t cap = std::max<size_t>(bytes, 4096);
+    // some headroom, whole MiB: the next scan's result of about the same size finds this block in the pool
+    size_t cap = bytes < (1 << 20) ? std::max<size_t>(bytes, 4096) : (((bytes + bytes / 8) >> 20) + 1) << 20;
     void *p = nullptr;
     MSB_CUDA(cudaHostAlloc(&p, cap, cudaHostAllocDefault));
     out->p = p;
@@ -230,7 +234,9 @@ static int pinned_get(msb_ctx *ctx, size_t bytes, PinnedBlock *out) {
 static void pinned_put(msb_ctx *ctx, PinnedBlock b) {
     if (!b.p) return;
     std::lock_guard<std::mutex> g(ctx->pinned_mu);
-    if (ctx->pinned_free.size() < 8) ctx->pinned_free.push_back(b);
+    // a genome-wide scan holds one block per unit (~50 for hg19) until its sites are gathered, step after step:
+    // page-locking is slow (~0.3 ms/MB), so the pool keeps them all
+    if (ctx->pinned_free.size() < 512) ctx->pinned_free.push_back(b);
     else cudaFreeHost(b.p);
 }
 
@@ -353,6 +359,8 @@ int msb_ctx_create(int device, void *stream, msb_ctx **out) {
     cudaFuncSetAttribute(prefilter_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) ctx->smem_optin);
     cudaFuncSetAttribute(prefilter_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kTcSmemBytes);
     cudaFuncSetAttribute(prefilter_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kTcSmemBytes);
+    cudaFuncSetAttribute(select_ranks_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSelSmemKeys * 8);
+    cudaFuncSetAttribute(select_ranks_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSelSmemKeys * 8);
     *out = ctx;
     return MSB_OK;
 }
@@ -365,7 +373,7 @@ int msb_ctx_destroy(msb_ctx *ctx) {
                       &ctx->key_alt, &ctx->score_alt, &ctx->sort_tmp, &ctx->counters, &ctx->out_seq,
                       &ctx->out_start, &ctx->out_strand, &ctx->scores,
                       &ctx->scores_sorted, &ctx->seg_off, &ctx->ranks, &ctx->sel, &ctx->keep, &ctx->keep_pos,
-                      &ctx->motif_counts, &ctx->lane_count})
+                      &ctx->motif_counts, &ctx->sel_aux, &ctx->limit1, &ctx->lane_count})
         b->release();
     if (ctx->d2h_stream) cudaStreamSynchronize(ctx->d2h_stream);
     for (auto &f : ctx->fin) {
@@ -1249,8 +1257,12 @@ static int make_ranges(const msb_seqs *S, int64_t n_ranges, const int64_t *r_seq
 // (msb_scan_ascii makes the stream wait for that slice's bytes and encodes them there).
 typedef std::function<int(size_t)> RangeHook;
 
+// `limit_override`: a device array of per-sequence start limits used instead of the set's own
+// (msb_score_select scans only the offset-0 window of every sample); `cand_scale`: the candidate buffers
+// are sized for that many times the usual candidate density.
 static int scan_device(msb_ctx *ctx, msb_motifs *M, const msb_seqs *S, int strand, int flags,
-                       const RangeList *ranges = nullptr, const RangeHook *before_range = nullptr) {
+                       const RangeList *ranges = nullptr, const RangeHook *before_range = nullptr,
+                       const int32_t *limit_override = nullptr, int cand_scale = 1) {
     if (!ctx || !M || !S) { set_error("msb_scan: null argument"); return MSB_EINVAL; }
     if (strand < 1 || strand > 3) { set_error("msb_scan: strand must be 1, 2 or 3"); return MSB_EINVAL; }
     if (M->ctx != ctx || S->ctx != ctx) { set_error("msb_scan: motifs/seqs belong to another context"); return MSB_EINVAL; }
@@ -1294,7 +1306,8 @@ static int scan_device(msb_ctx *ctx, msb_motifs *M, const msb_seqs *S, int stran
         ctx->last_counts_only = counts_only;
         return MSB_OK;
     }
-    const SeqView sv = S->view();
+    SeqView sv = S->view();
+    if (limit_override) sv.limit = limit_override;
     const MotifView mv = M->view();
     // site key = motif << key_shift | packed position << 1 | strand (make_site_key)
     int pos_bits = 1, motif_bits = 1;
@@ -1305,7 +1318,7 @@ static int scan_device(msb_ctx *ctx, msb_motifs *M, const msb_seqs *S, int stran
 
     // ---- stage 1: prefilter ------------------------------------------------------------------
     const double cells = (double) span * (double) std::max<int32_t>(n_fast, 1);
-    int64_t cand_cap = (int64_t) std::min<double>(std::max<double>(cells / 512.0, 1 << 22), (double) (1ll << 30));   // in 8-byte units
+    int64_t cand_cap = (int64_t) std::min<double>(std::max<double>(cells / 512.0 * cand_scale, 1 << 22), (double) (1ll << 30));   // in 8-byte units
     int64_t dirty_cap = std::max<int64_t>(1 << 16, span / 64);
     if (ctx->cand.cap / 8 > (size_t) cand_cap) cand_cap = (int64_t) (ctx->cand.cap / 8);
     if (ctx->dirty.cap / 8 > (size_t) dirty_cap) dirty_cap = (int64_t) (ctx->dirty.cap / 8);
@@ -1595,6 +1608,7 @@ int msb_ctx_set_option(msb_ctx *ctx, const char *name, int value) {
     if (name && !std::strcmp(name, "tc_first_lane_cap") && value >= 0) { ctx->opt_tc_first_lane_cap = value; return MSB_OK; }
     if (name && !std::strcmp(name, "ascii_slices") && value >= 1 && value <= 7) { ctx->opt_ascii_slices = value; return MSB_OK; }
     if (name && !std::strcmp(name, "poison_pool") && (value == 0 || value == 1)) { ctx->opt_poison_pool = value; return MSB_OK; }
+    if (name && !std::strcmp(name, "select_pilot") && (value == 0 || value == 1)) { ctx->opt_select_pilot = value; return MSB_OK; }
     set_error("msb_ctx_set_option: unknown option or value");
     return MSB_EINVAL;
 }
@@ -1969,50 +1983,161 @@ int msb_score(msb_ctx *ctx, const msb_motifs *M, const msb_seqs *S, int strand, 
     return MSB_OK;
 }
 
+// Radix select over `n_segs` segments (kernels.cuh, select_ranks_kernel): data = doubles or ready-made keys.
+static int launch_select(msb_ctx *ctx, bool from_doubles, const void *data, const int64_t *d_seg_off, int64_t stride,
+                         int32_t n_segs, const int64_t *d_ranks, int32_t n_ranks, const int64_t *d_live, int64_t max_seg_len,
+                         double *d_out, int32_t *d_ok) {
+    if (n_segs <= 0) return MSB_OK;
+    const int smem_keys = (int) std::min<int64_t>(std::max<int64_t>(max_seg_len, 1), kSelSmemKeys);
+    const size_t smem = (size_t) smem_keys * 8;
+    if (from_doubles)
+        select_ranks_kernel<true><<<(unsigned) n_segs, kSelThreads, smem, ctx->stream>>>(data, d_seg_off, stride, d_ranks, n_ranks, smem_keys, d_live, d_out, d_ok);
+    else
+        select_ranks_kernel<false><<<(unsigned) n_segs, kSelThreads, smem, ctx->stream>>>(data, d_seg_off, stride, d_ranks, n_ranks, smem_keys, d_live, d_out, d_ok);
+    MSB_CUDA(cudaGetLastError());
+    return MSB_OK;
+}
+
+// Every sample scored for motifs [m0, m1) and the order statistics selected from the score rows: the plain
+// form of the step, used for small inputs and for the motifs the pilot scheme below could not serve.
+static int score_select_direct(msb_ctx *ctx, const msb_motifs *M, const msb_seqs *S, int strand, int32_t m0, int32_t m1,
+                               int32_t n_ranks, double *out, double *score_ms, double *select_ms) {
+    cudaStream_t st = ctx->stream;
+    const int64_t max_elems = (int64_t) 1 << 28;  // 2 GiB of doubles per slice
+    const int32_t per = (int32_t) std::max<int64_t>(1, std::min<int64_t>(m1 - m0, max_elems / std::max<int64_t>(S->n, 1)));
+    MSB_TRY(ctx->scores.ensure((size_t) per * (size_t) S->n * 8));
+    MSB_TRY(ctx->sel.ensure((size_t) per * (size_t) n_ranks * 8));
+    for (int32_t a = m0; a < m1; a += per) {
+        const int32_t b = std::min(m1, a + per), cnt = b - a;
+        MSB_CUDA(cudaEventRecord(ctx->ev[0], st));
+        MSB_TRY(launch_score0(ctx, M, S, strand, a, b, ctx->scores.as<double>()));
+        MSB_CUDA(cudaEventRecord(ctx->ev[1], st));
+        MSB_TRY(launch_select(ctx, true, ctx->scores.p, nullptr, S->n, cnt, ctx->ranks.as<int64_t>(), n_ranks, nullptr, S->n,
+                              ctx->sel.as<double>(), nullptr));
+        MSB_CUDA(cudaEventRecord(ctx->ev[2], st));
+        MSB_CUDA(cudaMemcpyAsync(out + (size_t) a * n_ranks, ctx->sel.p, (size_t) cnt * n_ranks * 8, cudaMemcpyDeviceToHost, st));
+        MSB_CUDA(cudaStreamSynchronize(st));
+        *score_ms += ev_ms(ctx->ev[0], ctx->ev[1]);
+        *select_ms += ev_ms(ctx->ev[1], ctx->ev[2]);
+    }
+    return MSB_OK;
+}
+
+// The cutoff step of `motif --build` (cli/motif.py:133-137 + motif/__init__.py:378-401) without the score matrix.
+//
+// The reference scores every background sample for every motif (750 x 1e6 doubles = 6 GB), sorts each row and
+// reads five indices, all in the top 1 %.  Here:
+//   1. pilot: the first 32,768 samples are scored for all motifs (score0_kernel) and a radix select reads, per
+//      motif, the pilot score tau_m at 1.5 x the deepest wanted quantile;
+//   2. the scan path -- tensor-core prefilter + exact fp64 re-score -- runs over ALL samples with the tau_m as
+//      cutoffs and a start limit of 1 (only the offset-0 window of a sample is a window of the distribution,
+//      cscore.c:195-213): it returns exactly the samples whose score reaches tau_m, with the reference's doubles,
+//      i.e. the top ~1.5 % of every row (a set that is closed upwards, so ranks inside it are ranks in the row);
+//   3. per (motif, sample) the better strand (cscore.c:215-221), then a radix select per motif over those ~15,000
+//      keys reads the wanted order statistics.
+// A motif whose candidate set turns out smaller than the deepest rank (probability ~1e-9 per motif for iid
+// samples; certain for NaN scores) is redone the plain way.  What crosses HBM is the 12 B/sample of packed
+// sequence and ~16 B per candidate instead of 8 B per (motif, sample) twice.
 int msb_score_select(msb_ctx *ctx, const msb_motifs *M, const msb_seqs *S, int strand, int32_t n_ranks,
                      const int64_t *ranks, double *out) {
     MSB_TRY(check_score_args(ctx, M, S, strand));
     if (n_ranks < 0 || (n_ranks > 0 && (!ranks || !out))) { set_error("msb_score_select: bad ranks"); return MSB_EINVAL; }
-    for (int32_t k = 0; k < n_ranks; k++)
+    if (n_ranks > kSelMaxRanks) { set_error("msb_score_select: at most 8 ranks per call"); return MSB_EINVAL; }
+    int64_t deepest = 0;
+    for (int32_t k = 0; k < n_ranks; k++) {
         if (ranks[k] < 0 || ranks[k] >= S->n) { set_error("msb_score_select: rank out of range"); return MSB_EINVAL; }
+        deepest = std::max(deepest, ranks[k]);
+    }
     if (M->n == 0 || n_ranks == 0) return MSB_OK;
     MSB_CUDA(cudaSetDevice(ctx->device));
     cudaStream_t st = ctx->stream;
-    const int64_t max_elems = (int64_t) 1 << 28;  // 2 GiB of doubles per slice, twice (in + sorted)
-    const int32_t per = (int32_t) std::max<int64_t>(1, std::min<int64_t>(M->n, max_elems / std::max<int64_t>(S->n, 1)));
-    MSB_TRY(ctx->scores.ensure((size_t) per * (size_t) S->n * 8));
-    MSB_TRY(ctx->scores_sorted.ensure((size_t) per * (size_t) S->n * 8));
-    MSB_TRY(ctx->seg_off.ensure((size_t) (per + 1) * 8));
     MSB_TRY(ctx->ranks.ensure((size_t) n_ranks * 8));
-    MSB_TRY(ctx->sel.ensure((size_t) per * (size_t) n_ranks * 8));
-    std::vector<int64_t> seg((size_t) per + 1);
-    for (int32_t k = 0; k <= per; k++) seg[k] = (int64_t) k * S->n;
-    MSB_CUDA(cudaMemcpyAsync(ctx->seg_off.p, seg.data(), seg.size() * 8, cudaMemcpyHostToDevice, st));
     MSB_CUDA(cudaMemcpyAsync(ctx->ranks.p, ranks, (size_t) n_ranks * 8, cudaMemcpyHostToDevice, st));
     double score_ms = 0, select_ms = 0;
-    for (int32_t m0 = 0; m0 < M->n; m0 += per) {
-        const int32_t m1 = std::min(M->n, m0 + per), cnt = m1 - m0;
-        MSB_CUDA(cudaEventRecord(ctx->ev[0], st));
-        MSB_TRY(launch_score0(ctx, M, S, strand, m0, m1, ctx->scores.as<double>()));
-        MSB_CUDA(cudaEventRecord(ctx->ev[1], st));
-        size_t tmp_bytes = 0;
-        const int64_t total = (int64_t) cnt * S->n;
-        MSB_CUDA(cub::DeviceSegmentedRadixSort::SortKeysDescending(
-            nullptr, tmp_bytes, ctx->scores.as<double>(), ctx->scores_sorted.as<double>(), total, cnt,
-            ctx->seg_off.as<int64_t>(), ctx->seg_off.as<int64_t>() + 1, 0, 64, st));
-        MSB_TRY(ctx->sort_tmp.ensure(std::max<size_t>(tmp_bytes, 16)));
-        MSB_CUDA(cub::DeviceSegmentedRadixSort::SortKeysDescending(
-            ctx->sort_tmp.p, tmp_bytes, ctx->scores.as<double>(), ctx->scores_sorted.as<double>(), total, cnt,
-            ctx->seg_off.as<int64_t>(), ctx->seg_off.as<int64_t>() + 1, 0, 64, st));
-        gather_ranks_kernel<<<(cnt * n_ranks + 255) / 256, 256, 0, st>>>(
-            ctx->scores_sorted.as<double>(), S->n, cnt, ctx->ranks.as<int64_t>(), n_ranks, ctx->sel.as<double>());
-        MSB_CUDA(cudaGetLastError());
-        MSB_CUDA(cudaEventRecord(ctx->ev[2], st));
-        MSB_CUDA(cudaMemcpyAsync(out + (size_t) m0 * n_ranks, ctx->sel.p, (size_t) cnt * n_ranks * 8, cudaMemcpyDeviceToHost, st));
-        MSB_CUDA(cudaStreamSynchronize(st));
-        score_ms += ev_ms(ctx->ev[0], ctx->ev[1]);
-        select_ms += ev_ms(ctx->ev[1], ctx->ev[2]);
+    const int64_t kPilot = 32768;
+    const bool pilot = ctx->opt_select_pilot && ctx->opt_prefilter_tc && S->n >= 8 * kPilot && (deepest + 1) * 32 <= S->n;
+    ctx->c[MSB_C_RETRIES] = 0;
+    if (!pilot) {
+        MSB_TRY(score_select_direct(ctx, M, S, strand, 0, M->n, n_ranks, out, &score_ms, &select_ms));
+        ctx->t[MSB_T_SCORE] = score_ms;
+        ctx->t[MSB_T_SELECT] = select_ms;
+        return MSB_OK;
     }
+    // ---- 1. pilot thresholds -------------------------------------------------------------------------------
+    const int64_t q = (int64_t) (1.5 * (double) (deepest + 1) * (double) kPilot / (double) S->n) + 32;
+    MSB_TRY(ctx->scores.ensure((size_t) M->n * (size_t) kPilot * 8));
+    MSB_TRY(ctx->sel.ensure((size_t) M->n * (size_t) std::max(n_ranks, 1) * 8));
+    MSB_TRY(ctx->sel_aux.ensure((size_t) (M->n + 1) * 32 + 64));
+    int64_t *d_q = ctx->sel_aux.as<int64_t>();                                  // [1] pilot rank
+    unsigned long long *d_dead = (unsigned long long *) (d_q + 1);              // [n] second-strand sites per motif
+    int64_t *d_live = (int64_t *) (d_dead + M->n);                              // [n]
+    int32_t *d_ok = (int32_t *) (d_live + M->n);                                // [n]
+    MSB_CUDA(cudaMemcpyAsync(d_q, &q, 8, cudaMemcpyHostToDevice, st));
+    MSB_CUDA(cudaMemsetAsync(d_dead, 0, (size_t) M->n * 8, st));
+    MSB_CUDA(cudaEventRecord(ctx->ev[6], st));
+    {
+        SeqView head = S->view();
+        head.n_seqs = kPilot;
+        dim3 grid((unsigned) ((kPilot + 255) / 256), (unsigned) std::min<int32_t>(M->n, 1024));
+        score0_kernel<<<grid, 256, 0, st>>>(head, M->view(), strand, 0, M->n, kPilot, ctx->scores.as<double>());
+        MSB_CUDA(cudaGetLastError());
+    }
+    MSB_CUDA(cudaEventRecord(ctx->ev[7], st));
+    MSB_TRY(launch_select(ctx, true, ctx->scores.p, nullptr, kPilot, M->n, d_q, 1, nullptr, kPilot, ctx->sel.as<double>(), nullptr));
+    MSB_CUDA(cudaEventRecord(ctx->ev[5], st));
+    std::vector<double> tau((size_t) M->n);
+    MSB_CUDA(cudaMemcpyAsync(tau.data(), ctx->sel.p, (size_t) M->n * 8, cudaMemcpyDeviceToHost, st));
+    MSB_CUDA(cudaStreamSynchronize(st));
+    score_ms += ev_ms(ctx->ev[6], ctx->ev[7]);
+    select_ms += ev_ms(ctx->ev[7], ctx->ev[5]);
+    // ---- 2. the scan path over all samples, offset-0 windows only ---------------------------------------------
+    // the site predicate is score - cutoff >= -1e-10 (cscore.c:358): any cutoff keeps the candidate set closed
+    // upwards; tau is only a way to size it
+    msb_motifs *Mt = nullptr;
+    MSB_TRY(msb_motifs_create(ctx, M->n, M->lens.data(), M->mats.data(), M->mat_off.data(), tau.data(), &Mt));
+    int rc = ctx->limit1.ensure((size_t) std::max<int64_t>(S->n, 1) * 4);
+    if (rc == MSB_OK) {
+        fill_i32_kernel<<<(unsigned) ((S->n + 255) / 256), 256, 0, st>>>(ctx->limit1.as<int32_t>(), S->n, 1);
+        cudaError_t e = cudaGetLastError();
+        if (e != cudaSuccess) rc = cuda_fail(e, "fill_i32_kernel", __FILE__, __LINE__);
+    }
+    if (rc == MSB_OK) rc = scan_device(ctx, Mt, S, strand, 0, nullptr, nullptr, ctx->limit1.as<int32_t>(), 8);
+    msb_motifs_destroy(Mt);
+    MSB_TRY(rc);
+    score_ms += ctx->t[MSB_T_PREFILTER] + ctx->t[MSB_T_EXACT] + ctx->t[MSB_T_ORDER];
+    // ---- 3. better strand per sample, select per motif ---------------------------------------------------------
+    const int64_t n_sites = ctx->last_sites;
+    msb_ctx::FinSet &F = ctx->fin[ctx->fin_cur];
+    std::vector<int64_t> offsets((size_t) M->n + 1, 0);
+    MSB_CUDA(cudaEventRecord(ctx->ev[6], st));
+    if (n_sites) {
+        MSB_TRY(ctx->scores_sorted.ensure((size_t) n_sites * 8));
+        sample_keys_kernel<<<(unsigned) ((n_sites + 255) / 256), 256, 0, st>>>(ctx->fin_key, ctx->fin_seq, ctx->fin_score, n_sites,
+                                                                                ctx->last_key_shift, ctx->scores_sorted.as<uint64_t>(), d_dead);
+        MSB_CUDA(cudaGetLastError());
+        MSB_CUDA(cudaMemcpyAsync(offsets.data(), F.offsets.p, offsets.size() * 8, cudaMemcpyDeviceToHost, st));
+    }
+    live_counts_kernel<<<(unsigned) ((M->n + 255) / 256), 256, 0, st>>>(F.offsets.as<int64_t>(), d_dead, M->n, d_live);
+    MSB_CUDA(cudaGetLastError());
+    MSB_CUDA(cudaStreamSynchronize(st));
+    int64_t longest = 1;
+    for (int32_t m = 0; m < M->n; m++) longest = std::max(longest, offsets[m + 1] - offsets[m]);
+    MSB_TRY(launch_select(ctx, false, n_sites ? ctx->scores_sorted.p : ctx->sel_aux.p, F.offsets.as<int64_t>(), 0, M->n,
+                          ctx->ranks.as<int64_t>(), n_ranks, d_live, longest, ctx->sel.as<double>(), d_ok));
+    MSB_CUDA(cudaEventRecord(ctx->ev[7], st));
+    std::vector<int32_t> ok((size_t) M->n);
+    MSB_CUDA(cudaMemcpyAsync(out, ctx->sel.p, (size_t) M->n * n_ranks * 8, cudaMemcpyDeviceToHost, st));
+    MSB_CUDA(cudaMemcpyAsync(ok.data(), d_ok, (size_t) M->n * 4, cudaMemcpyDeviceToHost, st));
+    MSB_CUDA(cudaStreamSynchronize(st));
+    select_ms += ev_ms(ctx->ev[6], ctx->ev[7]);
+    int64_t redone = 0;
+    for (int32_t m = 0; m < M->n; m++)
+        if (!ok[m]) {   // too few candidates (or NaN scores): this motif the plain way
+            MSB_TRY(score_select_direct(ctx, M, S, strand, m, m + 1, n_ranks, out, &score_ms, &select_ms));
+            redone++;
+        }
+    ctx->c[MSB_C_RETRIES] = redone;
+    ctx->c[MSB_C_HITS] = n_sites;
     ctx->t[MSB_T_SCORE] = score_ms;
     ctx->t[MSB_T_SELECT] = select_ms;
     return MSB_OK;

@@ -405,6 +405,10 @@ prefilter_tc_kernel(const __grid_constant__ TcParams P) {
                         const int64_t left = (int64_t) __ldg(S.len + s) - j0;
                         const int nvalid = left <= 0 ? 0 : (left >= 32 ? 32 : (int) left);
                         uint32_t valid = nvalid >= 32 ? 0xffffffffu : ((1u << nvalid) - 1u);
+                        if (S.limit) {   // windows may only start at the first limit[s] positions of the sequence
+                            const int64_t lim = (int64_t) __ldg(S.limit + s) - j0;
+                            valid &= lim >= 32 ? 0xffffffffu : (lim <= 0 ? 0u : ((1u << (int) lim) - 1u));
+                        }
                         // range scans: starts outside [pos_lo, pos_hi) belong to another call
                         if (q0 < P.pos_lo) valid &= P.pos_lo - q0 >= 32 ? 0u : ~((1u << (int) (P.pos_lo - q0)) - 1u);
                         if (q0 + 32 > P.pos_hi) valid &= P.pos_hi <= q0 ? 0u : ((1u << (int) (P.pos_hi - q0)) - 1u);

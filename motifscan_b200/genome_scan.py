@@ -209,8 +209,11 @@ class ShardedSites(GenomeSites):
 
     def __init__(self, chroms, n_motifs, counts, parts):
         # parts: list of (ScanResult, piece chromosome index array, piece start array), in genome order
-        GenomeSites.__init__(self, chroms, n_motifs, counts, None, None, None, None, None)
-        self._parts = parts
+        self.chroms = list(chroms)
+        self.n_motifs = n_motifs
+        self.counts = counts
+        self._motif = None
+        self._parts = parts          # chrom_idx / start / score / strand appear on first use (__getattr__)
         self._merged = False
 
     def _merge(self):
@@ -304,16 +307,17 @@ class GenomeScanner:
                     if i + 1 < len(units):        # the next unit's planes travel while this one is scanned
                         nxt = self._upload(ctx, units[i + 1], True)
                 ranges = [(j, 0, b - a) for j, (_, a, b, _) in enumerate(unit.pieces)]
-                if collect_sites:
-                    res = engine.scan_ranges(ctx, motifs, sset, self.strand, ranges, async_=True)
-                    parts.append((res, np.array([p[0] for p in unit.pieces]), np.array([p[1] for p in unit.pieces])))
-                else:
-                    engine.scan_ranges_device(ctx, motifs, sset, self.strand, ranges, counts_only=not order_sites)
-                    counts += ctx.site_counts(n_motifs)
-                t = ctx.timings()
+                with ctx._lock:   # the counts / timings read below belong to THIS scan even if the context is shared
+                    if collect_sites:
+                        res = engine.scan_ranges(ctx, motifs, sset, self.strand, ranges, async_=True)
+                        parts.append((res, np.array([p[0] for p in unit.pieces]), np.array([p[1] for p in unit.pieces])))
+                    else:
+                        engine.scan_ranges_device(ctx, motifs, sset, self.strand, ranges, counts_only=not order_sites)
+                        counts += ctx.site_counts(n_motifs)
+                    t = ctx.timings()
+                    c = ctx.counters()
                 for name in ("prefilter", "exact", "order"):
                     stats[name] = stats.get(name, 0.0) + t[name]
-                c = ctx.counters()
                 for name in ("launches", "prefilter_launches", "candidates", "hits"):
                     stats[name] = stats.get(name, 0) + c[name]
                 if self.keep_resident and kept is None:

@@ -355,6 +355,44 @@ def test_score_select_matches_sorted_order_statistics(eng):
     sset.close(), motifs.close()
 
 
+def test_score_select_pilot_path_equals_sorting_every_score(eng):
+    """msb_score_select on a large sample takes the pilot + scan + radix-select path (no score matrix): the
+    order statistics must be the bits a full descending sort of the oracle's scores gives, for ordinary
+    motifs, for motifs with a handful of distinct scores (heavy ties at every rank), for a motif whose scores
+    are all NaN (0 / 0) and one whose windows all score the same, on every strand; and the same as the plain
+    form (select_pilot = 0)."""
+    from motifscan_b200 import _lib, synth
+    rng = np.random.default_rng(170)
+    pwms = synth_pwms(rng, 10) + synth_pwms(rng, 3, lmin=2, lmax=3)
+    pwms.append([[0.0] * 5] * 4)                                   # max_raw = 0: every score is 0 / 0 = NaN
+    pwms.append([[0.25] * 7] * 4)                                  # every window scores exactly 1
+    pwms.append(np.around(rng.normal(0, 1, size=(4, 30)), 5).tolist())
+    n = 300000
+    blob, off = synth.background_samples(n, 30, seed=5)
+    blob = blob.copy()
+    blob[30 * 7 + 3] = ord("N")                                    # a sample with a non-ACGT base
+    raw = blob.tobytes()
+    seqs = [raw[off[i]:off[i + 1]].decode() for i in range(n)]
+    ranks = [int(n * 0.1 ** e) - 1 for e in range(2, min(len(str(n)), 7))] + [0]
+    ctx = eng.Context(0)
+    motifs = eng.MotifSet(ctx, pwms)
+    sset = eng.SequenceSet(ctx, blob=blob, seq_off=off)
+    for strand in (3, 1, 2):
+        want = np.sort(oracle.score_arrays(pwms, seqs, strand), axis=1)[:, ::-1][:, ranks]
+        got = eng.score_select(ctx, motifs, sset, strand, ranks)
+        redone = ctx.counters()["retries"]
+        ctx.set_option("select_pilot", 0)
+        plain = eng.score_select(ctx, motifs, sset, strand, ranks)
+        ctx.set_option("select_pilot", 1)
+        finite = ~np.isnan(want).any(axis=1)
+        assert finite.sum() == len(pwms) - 1
+        assert np.array_equal(got[finite].view(np.uint64), np.ascontiguousarray(want[finite]).view(np.uint64)), strand
+        assert np.array_equal(got.view(np.uint64), plain.view(np.uint64))      # NaN rows: the same bits either way
+        assert np.isnan(got[~finite]).all()
+        assert 1 <= redone <= 3, redone                                         # the NaN motif (and nothing ordinary) is redone
+    sset.close(), motifs.close(), ctx.close()
+
+
 def test_scan_ascii_sliced_upload_equals_two_step_scan(eng):
     """msb_scan_ascii (upload cut into slices that overlap the scan; >= 8 MB takes the sliced path)
     == msb_seqs_from_ascii + msb_scan, from pinned and from pageable memory, with and without
