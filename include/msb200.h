@@ -171,7 +171,8 @@ int msb_scan_ascii(msb_ctx *ctx, const msb_motifs *motifs, int64_t n_seqs, const
  * of its sequence, exactly as if the whole sequence had been scanned (cscore.c:336-340), so the
  * union over a partition of a chromosome into ranges equals the unchunked scan and no overlap has
  * to be shipped.  `end` is clipped at the sequence length; ranges must not overlap (MSB_EINVAL).
- * seq_idx / start of the sites refer to `seqs`. */
+ * seq_idx / start of the sites refer to `seqs`.  MSB_SCAN_DEDUP is rejected (MSB_EINVAL): the reference
+ * de-duplicates over a whole region's site list (scanner.py:171-193), which a range boundary would cut. */
 int msb_scan_ranges(msb_ctx *ctx, const msb_motifs *motifs, const msb_seqs *seqs, int strand,
                     int flags, int64_t n_ranges, const int64_t *seq_idx, const int64_t *start,
                     const int64_t *end, msb_result **out);

@@ -490,7 +490,8 @@ __device__ __forceinline__ void exact_record(const ExactParams &E, const uint4 r
         const int L = __ldg(E.mot.len + m);
         if (j + L > slen) continue;   // cscore.c:340
         const double *pw = E.mot.pwm + 4 * (int64_t) __ldg(E.mot.col_off + m);
-        test_and_emit(E, m, p, rev, exact_raw_w(w, pw, L, rev));   // prefilter motifs have L <= 32
+        // the register window holds 32 bases; a longer motif (prefiltered on its first 32 columns) reads memory
+        test_and_emit(E, m, p, rev, L <= kMaxFastLen ? exact_raw_w(w, pw, L, rev) : exact_raw(E.seq, pw, L, p, rev));
     }
 }
 
@@ -553,7 +554,8 @@ exact_dirty_kernel(ExactParams E, const int64_t *__restrict__ pos, int64_t n_pos
         const uint32_t m = (uint32_t) __ldg(motif_ids + k0 + kl);
         const int L = __ldg(E.mot.len + m);
         const float *src = E.mot.pwm32 + 4 * (int64_t) __ldg(E.mot.col_off + m);
-        for (int i = lane; i < 4 * L; i += 32) s_pw[kl * kDirtyStride + i] = __ldg(src + i);
+        if (L <= kMaxFastLen)   // longer motifs are not screened: they go straight to the fp64 path below
+            for (int i = lane; i < 4 * L; i += 32) s_pw[kl * kDirtyStride + i] = __ldg(src + i);
         if (lane == 0) { s_len[kl] = L; s_floor[kl] = __ldg(E.mot.floor32 + m); s_motif[kl] = m; }
     }
     __syncthreads();
@@ -573,6 +575,15 @@ exact_dirty_kernel(ExactParams E, const int64_t *__restrict__ pos, int64_t n_pos
     }
     for (int32_t kl = 0; kl < n_here; kl++) {
         const int L = s_len[kl];
+        if (L > kMaxFastLen) {   // warp-uniform: a long motif, scored from memory with the reference's arithmetic
+            if (L <= left) {
+                const uint32_t m = s_motif[kl];
+                const double *pw = E.mot.pwm + 4 * (int64_t) __ldg(E.mot.col_off + m);
+                if (E.strand & 1) test_and_emit(E, m, p, 0, exact_raw(E.seq, pw, L, p, 0));
+                if (E.strand & 2) test_and_emit(E, m, p, 1, exact_raw(E.seq, pw, L, p, 1));
+            }
+            continue;
+        }
         const float *pw32 = s_pw + kl * kDirtyStride;
         // fp32 screen of both strands (FP64 issues at a fraction of the FP32 rate and the division in
         // test_and_emit is a subroutine): a score below the floor cannot pass
@@ -669,7 +680,12 @@ region_counts_kernel(const uint64_t *__restrict__ key, const int32_t *__restrict
 // if its score is strictly higher (`curr.score >= next.score` keeps curr, scanner.py:163).
 // The surviving forward and reverse sites keep their (start, forward-first) order, which is the
 // reference's `fwd + rev` followed by a stable sort on start (scanner.py:190-191).
-// One thread per segment head walks its (short) segment.
+//
+// The walk only carries state across same-strand sites that are closer than the motif length to their
+// predecessor (the survivor is never behind the predecessor's predecessor chain), so a segment falls
+// apart into independent CHAINS at every same-strand gap >= L.  One thread per site: it looks back (at most
+// the few sites within L positions) to see whether it opens a chain, and if so walks that chain.  Whole
+// chromosomes de-duplicate as fast as 1 kb regions; only a run of overlapping sites is sequential.
 // ---------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256)
 dedup_flags_kernel(const uint64_t *__restrict__ key, const int32_t *__restrict__ seq_idx,
@@ -680,21 +696,26 @@ dedup_flags_kernel(const uint64_t *__restrict__ key, const int32_t *__restrict__
     if (i >= n) return;
     const uint32_t m = site_motif(key[i], key_shift);
     const int32_t s = seq_idx[i];
-    if (i > 0 && site_motif(key[i - 1], key_shift) == m && seq_idx[i - 1] == s) return;  // not a segment head
-    int64_t e = i + 1;
-    while (e < n && site_motif(key[e], key_shift) == m && seq_idx[e] == s) e++;
     const int32_t L = __ldg(mlen + m);
-    for (int8_t which = 1; which <= 2; which++) {
-        int64_t cur = -1;
-        for (int64_t t = i; t < e; t++) {
-            if (strand[t] != which) continue;
-            if (cur >= 0 && start[t] - start[cur] < L) {
-                if (score[cur] >= score[t]) { keep[t] = 0; continue; }
-                keep[cur] = 0;
-            }
-            keep[t] = 1;
-            cur = t;
+    const int8_t which = strand[i];
+    for (int64_t t = i - 1; t >= 0; t--) {   // does a same-strand site of this segment sit less than L before this one?
+        if (site_motif(key[t], key_shift) != m || seq_idx[t] != s) break;
+        if (start[i] - start[t] >= L) break;
+        if (strand[t] == which) return;      // not a chain head: the head's thread reaches this site
+    }
+    int64_t cur = i, last = i;
+    keep[i] = 1;
+    for (int64_t t = i + 1; t < n; t++) {
+        if (site_motif(key[t], key_shift) != m || seq_idx[t] != s) break;
+        if (strand[t] != which) continue;
+        if (start[t] - start[last] >= L) break;   // the next chain
+        last = t;
+        if (start[t] - start[cur] < L) {
+            if (score[cur] >= score[t]) { keep[t] = 0; continue; }
+            keep[cur] = 0;
         }
+        keep[t] = 1;
+        cur = t;
     }
 }
 
@@ -897,15 +918,6 @@ live_counts_kernel(const int64_t *__restrict__ offsets, const unsigned long long
 __global__ void __launch_bounds__(256) fill_i32_kernel(int32_t *__restrict__ p, int64_t n, int32_t v) {
     const int64_t i = (int64_t) blockIdx.x * blockDim.x + threadIdx.x;
     if (i < n) p[i] = v;
-}
-
-__global__ void __launch_bounds__(256)
-gather_ranks_kernel(const double *__restrict__ sorted, int64_t n_seqs, int32_t n_motifs_chunk,
-                    const int64_t *__restrict__ ranks, int32_t n_ranks, double *__restrict__ out) {
-    const int t = blockIdx.x * blockDim.x + threadIdx.x;
-    if (t >= n_motifs_chunk * n_ranks) return;
-    const int m = t / n_ranks, k = t - m * n_ranks;
-    out[t] = sorted[(int64_t) m * n_seqs + ranks[k]];
 }
 
 }  // namespace msb

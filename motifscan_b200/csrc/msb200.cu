@@ -414,8 +414,9 @@ int msb_ctx_counters(const msb_ctx *ctx, int64_t *v, int n) {
 // raw score accumulated in fp32 from the fp32-rounded matrix is below floor32[m] cannot satisfy the
 // reference's predicate.  T is the conservative bound on the exact raw score that the prefilter
 // tables use (see "Prefilter tables" below); the fp32 path is off by at most
-// sum_c |v_c| 2^-24 (rounding the entries) + (L - 1) 2^-24 max|partial sum| <= L 2^-23 abs_sum, and
-// the margin taken here is 2^-17 (abs_sum + |T| + 1), 64 times that for L = 32.
+// sum_c |v_c| 2^-24 (rounding the entries) + (L - 1) 2^-24 max|partial sum| <= L 2^-23 abs_sum
+// (= 2^-18 abs_sum for L = 32), and the margin taken here is 2^-17 (abs_sum + |T| + 1): at least twice the
+// worst case, about four times the typical one.
 static int upload_floors(msb_motifs *M) {
     std::vector<float> floors((size_t) std::max<int32_t>(M->n, 1), std::numeric_limits<float>::infinity());
     for (int32_t m = 0; m < M->n; m++) {
@@ -896,9 +897,12 @@ int msb_seqs_destroy(msb_seqs *S) {
 // ------------------------------------------------------------------------------------------------
 namespace msb {
 
-static bool motif_is_fast(const msb_motifs *M, int32_t m) {
+// Motifs the prefilters can take.  The table prefilter holds at most kMaxFastLen columns; the tensor-core
+// prefilter takes any length: it looks at the first kMaxFastLen columns of a strand only (tc_fill_column) and
+// the exact stage scores the whole window.
+static bool motif_is_fast(const msb_motifs *M, int32_t m, bool tensor = false) {
     const int L = M->lens[m];
-    if (L < 1 || L > kMaxFastLen) return false;
+    if (L < 1 || (!tensor && L > kMaxFastLen)) return false;
     const double *mat = M->mats.data() + M->mat_off[m];
     for (int k = 0; k < 4 * L; k++)
         if (!std::isfinite(mat[k])) return false;
@@ -1091,8 +1095,13 @@ static void tc_fill_column(const msb_motifs *M, int32_t m, int rev, uint8_t *til
     const double max_raw = M->max_raw[m];
     const double cutoff = M->cutoffs[m];
     if (!(max_raw > 0) || std::isnan(cutoff) || (std::isinf(cutoff) && cutoff > 0)) { tc_fill_never(tile, col); return; }
+    // A motif longer than kMaxFastLen columns is prefiltered on its first kMaxFastLen columns (of this strand)
+    // alone: the columns behind them are taken at their best (deficit 0), which can only admit more
+    // windows -- the budget D below still comes from the whole motif, and sum over the kept columns of d <=
+    // sum over all columns of d <= D for every window the reference accepts.
+    const int kept = std::min(L, kMaxFastLen);
     double cms = 0, abs_sum = 0;
-    double colmax[kMaxFastLen];
+    std::vector<double> colmax((size_t) L);
     for (int c = 0; c < L; c++) {
         double mx = -INFINITY, a = 0;
         for (int b = 0; b < 4; b++) { mx = std::max(mx, V(b, c)); a = std::max(a, std::fabs(V(b, c))); }
@@ -1109,12 +1118,12 @@ static void tc_fill_column(const msb_motifs *M, int32_t m, int rev, uint8_t *til
         D += 1e-12 * (std::fabs(cms) + std::fabs(T) + abs_sum);
         if (D < 0) { tc_fill_never(tile, col); return; }  // even the best window is below the cutoff
     }
-    // beta: an e4m3 value near 384 / L (exactly representable, so the all-best window sums to C)
-    const double beta = (double) e4m3_value(e4m3_round_up(384.0 / L));
-    const double C = beta * L;
+    // beta: an e4m3 value near 384 / kept (exactly representable, so the all-best window sums to C)
+    const double beta = (double) e4m3_value(e4m3_round_up(384.0 / kept));
+    const double C = beta * kept;
     double s = std::isinf(D) ? 0.0 : (C - C / 64.0) / std::max(D, 1e-300);
     if (!(s < 1e30)) s = 1e30;
-    for (int c = 0; c < L; c++)
+    for (int c = 0; c < kept; c++)
         for (int b = 0; b < 4; b++) {
             const double d = colmax[c] - V(b, c);
             const double x = d > 0 ? beta - s * d : beta;
@@ -1134,10 +1143,10 @@ static int ensure_tc_tables(msb_ctx *ctx, msb_motifs *M, int strand, TcTableSet 
     T.any_zero_hit = 0;
     std::vector<int32_t> fast;
     for (int32_t m = 0; m < M->n; m++) {
-        if (motif_is_fast(M, m)) fast.push_back(m);
+        if (motif_is_fast(M, m, true)) fast.push_back(m);
         else if (M->lens[m] >= 1) T.slow.push_back(m);
     }
-    auto ksteps = [&](int32_t m) { return (M->lens[m] + 7) / 8; };
+    auto ksteps = [&](int32_t m) { return (std::min(M->lens[m], kMaxFastLen) + 7) / 8; };
     std::stable_sort(fast.begin(), fast.end(), [&](int32_t a, int32_t b) { return M->lens[a] < M->lens[b]; });
     T.order = fast;
     const int cols_per_motif = strand == 3 ? 2 : 1;
@@ -1655,6 +1664,12 @@ int msb_scan_ranges_device(msb_ctx *ctx, const msb_motifs *M, const msb_seqs *S,
                            int64_t n_ranges, const int64_t *seq_idx, const int64_t *start, const int64_t *end,
                            int64_t *n_sites) {
     if (!S) { set_error("msb_scan_ranges: null seqs"); return MSB_EINVAL; }
+    if (flags & MSB_SCAN_DEDUP) {
+        // the reference de-duplicates over a whole region's site list (scanner.py:171-193); a range boundary
+        // would cut a chain of overlapping sites in two and the halves would be resolved independently
+        set_error("msb_scan_ranges: MSB_SCAN_DEDUP is not defined across range boundaries; scan whole sequences");
+        return MSB_EINVAL;
+    }
     RangeList ranges;
     MSB_TRY(make_ranges(S, n_ranges, seq_idx, start, end, &ranges));
     MSB_TRY(scan_device(ctx, const_cast<msb_motifs *>(M), S, strand, flags, &ranges));

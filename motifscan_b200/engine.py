@@ -402,23 +402,25 @@ def _ranges(ranges):
     return (len(r), np.ascontiguousarray(r[:, 0]), np.ascontiguousarray(r[:, 1]), np.ascontiguousarray(r[:, 2]))
 
 
-def scan_ranges(ctx, motifs, seqs, strand, ranges, remove_dup=False, async_=False):
+def scan_ranges(ctx, motifs, seqs, strand, ranges, async_=False):
     """Scan only the windows that start in the given (sequence index, start, end) ranges of a
-    resident sequence set; sites refer to the sequences of `seqs` (msb_scan_ranges)."""
+    resident sequence set; sites refer to the sequences of `seqs` (msb_scan_ranges).  There is no
+    de-duplication here: it is defined over a whole region's site list (scanner.py:171-193), not
+    across range boundaries."""
     n, a, b, c = _ranges(ranges)
     h = ctypes.c_void_p()
-    flags = _flags(remove_dup, async_=async_)
+    flags = _flags(False, async_=async_)
     with ctx._lock:
         check(ctx._lib.msb_scan_ranges(ctx._h, motifs._h, seqs._h, int(strand), flags, n, ptr(a, ctypes.c_int64),
                                        ptr(b, ctypes.c_int64), ptr(c, ctypes.c_int64), ctypes.byref(h)))
     return ScanResult(ctx, h, motifs.n)
 
 
-def scan_ranges_device(ctx, motifs, seqs, strand, ranges, remove_dup=False, counts_only=False):
+def scan_ranges_device(ctx, motifs, seqs, strand, ranges, counts_only=False):
     """The same, results left on the device (`ctx.site_counts`); returns the number of sites."""
     n, a, b, c = _ranges(ranges)
     total = ctypes.c_int64(0)
-    flags = _flags(remove_dup, counts_only)
+    flags = _flags(False, counts_only)
     with ctx._lock:
         check(ctx._lib.msb_scan_ranges_device(ctx._h, motifs._h, seqs._h, int(strand), flags, n, ptr(a, ctypes.c_int64),
                                               ptr(b, ctypes.c_int64), ptr(c, ctypes.c_int64), ctypes.byref(total)))

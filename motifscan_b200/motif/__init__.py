@@ -130,25 +130,51 @@ class MotifPwms(list):
                                              cutoffs=rec["cutoffs"]))
 
 
+_PFM_HEADER = re.compile(r"^>\s*(\S+)(\s+(\S+))?")          # id, optional name = the next token only
+_PFM_ROW_NEW = re.compile(r"\s*([ACGT])\s*\[\s*(.+)\s*\]")     # `A  [ 3 0 0 ]`
+_PFM_ROW_OLD = re.compile(r"\s*(.+)\s*")                        # bare counts, rows in A C G T order
+
+
 def read_jaspar_pfms(path):
-    """JASPAR text PFMs (motif/__init__.py:71-140): `>ID<TAB>NAME` then `A [ n n ... ]` x 4.
-    Returns a list of (matrix_id, name, int array 4 x L)."""
+    """JASPAR text PFMs with the reference's grammar (motif/__init__.py:71-140): a header `>ID [NAME]`
+    (the name is the first token after the id, so it can be written back as `>ID<TAB>NAME<TAB>PWM`), then
+    exactly four count rows, either `A [ n n ... ]` (rows must come as A, C, G, T) or the old bare-number
+    form; blank lines anywhere.  A row where a header is due, a header inside a matrix, a non-integer count
+    or a truncated last record raise ValueError naming the line (the reference raises PfmsJasparFormatError
+    at the same line).  Returns a list of (matrix_id, name, int array 4 x L)."""
     out = []
+    want_header = True
+    num = 0
+    matrix_id = name = None
+    rows = []
     with open(path) as fh:
-        lines = [ln.strip() for ln in fh if ln.strip()]
-    i = 0
-    while i < len(lines):
-        if not lines[i].startswith(">") or len(lines) - i < 5:
-            raise ValueError(f"invalid JASPAR PFM record at line {i + 1}: {lines[i]!r}")
-        head = lines[i][1:].split(None, 1)
-        rows = []
-        for k, base in enumerate(BASES):
-            m = re.match(r"^([ACGT])\s*\[\s*(.*?)\s*\]$", lines[i + 1 + k])
-            if not m or m.group(1) != base:
-                raise ValueError(f"invalid JASPAR PFM row at line {i + 2 + k}: {lines[i + 1 + k]!r}")
-            rows.append([int(v) for v in m.group(2).split()])
-        out.append((head[0], head[1] if len(head) > 1 else None, np.asarray(rows, dtype=np.int64)))
-        i += 5
+        for num, raw in enumerate(fh, 1):
+            line = raw.strip()
+            if not line:
+                continue
+            head = _PFM_HEADER.match(line)
+            if bool(head) != want_header:
+                raise ValueError(f"invalid JASPAR PFM record at line {num}: {line!r}")
+            if head:
+                matrix_id, name, rows = head.group(1), head.group(3), []
+                want_header = False
+                continue
+            new = _PFM_ROW_NEW.match(line)
+            if new:
+                if new.group(1) != BASES[len(rows)]:
+                    raise ValueError(f"invalid JASPAR PFM row at line {num}: {line!r}")
+                tokens = new.group(2).split()
+            else:
+                tokens = _PFM_ROW_OLD.match(line).group(1).split()
+            try:
+                rows.append([int(v) for v in tokens])
+            except ValueError:
+                raise ValueError(f"invalid JASPAR PFM row at line {num}: {line!r}") from None
+            if len(rows) == 4:
+                out.append((matrix_id, name, np.asarray(rows, dtype=np.int64)))
+                want_header = True
+    if not want_header:
+        raise ValueError(f"invalid JASPAR PFM record at line {num + 1}: the last matrix is incomplete")
     return out
 
 

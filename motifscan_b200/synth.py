@@ -15,13 +15,16 @@ HG19_SIZES = [249250621, 243199373, 198022430, 191154276, 180915260, 171115067, 
 HG19_NAMES = [f"chr{i}" for i in range(1, 23)] + ["chrX", "chrY", "chrM"]
 
 
-def motif_set(n=750, seed=2020, lmin=6, lmax=30):
+def motif_set(n=750, seed=2020, lmin=6, lmax=30, n_long=0):
     """JASPAR-shaped PFMs pushed through the reference's PFM -> PPM(pseudo 0.001) -> PWM(bg,
-    round 5) rules.  Returns (pfms, pwms, ids)."""
+    round 5) rules.  Returns (pfms, pwms, ids).  The last `n_long` motifs are 33-40 columns long
+    (composite / dimer matrices): longer than the 32 columns the prefilters hold."""
     rng = np.random.default_rng(seed)
     pfms, pwms, ids = [], [], []
     for k in range(n):
         L = int(rng.integers(lmin, lmax + 1))
+        if k >= n - n_long:
+            L = 33 + (k - (n - n_long)) % 8
         depth = float(np.exp(rng.uniform(np.log(20), np.log(5000))))
         pfm = np.round(depth * rng.dirichlet([0.3] * 4, size=L).T).astype(np.int64)
         empty = pfm.sum(axis=0) == 0

@@ -1,0 +1,1 @@
+"""Placeholder package so the shim resolves as motifscan.motif.cscore in tests (not part of the shim)."""

@@ -413,9 +413,58 @@ def gen_host_cases():
     return cases
 
 
+JASPAR_TEXTS = {
+    "new_format": ">MA0006.1\tAhr::Arnt\nA  [     3      0      0 ]\nC  [     8      0     23 ]\nG  [     2     23      0 ]\nT  [    11      1      1 ]\n",
+    "two_records_blank_lines": "\n>M1 first\nA [1 2]\nC [3 4]\n\nG [5 6]\nT [7 8]\n\n>M2\tsecond\nA [9]\nC [8]\nG [7]\nT [6]\n\n",
+    "multi_token_header": ">MA0001.1 AGL3 extra tokens here\nA [0 3]\nC [94 75]\nG [1 0]\nT [2 19]\n",
+    "header_without_name": ">MA0002.1\nA [1]\nC [2]\nG [3]\nT [4]\n",
+    "header_with_space_after_gt": ">  MA0003.1   NAME\nA [1]\nC [2]\nG [3]\nT [4]\n",
+    "old_format_rows": ">MA0004.1 Arnt\n4 19 0 0\n16 0 20 0\n0 1 0 20\n0 0 0 0\n",
+    "mixed_old_and_new_rows": ">MA0005.1 x\nA [1 2]\n3 4\nG [5 6]\n7 8\n",
+    "rows_out_of_order": ">M x\nC [1]\nA [2]\nG [3]\nT [4]\n",
+    "row_before_header": "A [1]\n>M x\nA [1]\nC [2]\nG [3]\nT [4]\n",
+    "header_inside_matrix": ">M x\nA [1]\nC [2]\n>N y\nG [3]\nT [4]\n",
+    "non_integer_count": ">M x\nA [1.5]\nC [2]\nG [3]\nT [4]\n",
+    "truncated_last_record": ">M x\nA [1]\nC [2]\nG [3]\nT [4]\n>N y\nA [1]\nC [2]\n",
+    "empty_file": "",
+    "fifth_row": ">M x\nA [1]\nC [2]\nG [3]\nT [4]\nA [5]\n",
+}
+
+
+def gen_jaspar_cases():
+    """The reference's own JASPAR PFM parser (motif/__init__.py:71-140) on well-formed and malformed texts:
+    parsed (id, name, values) records, or the line number its PfmsJasparFormatError names."""
+    import tempfile
+    from motifscan.exceptions import PfmsJasparFormatError
+    from motifscan.motif import MotifPfms
+    cases = []
+    for label, text in JASPAR_TEXTS.items():
+        with tempfile.NamedTemporaryFile("w", suffix=".jaspar", delete=False) as fh:
+            fh.write(text)
+            path = fh.name
+        try:
+            pfms = MotifPfms._parse_jaspar_pfms(path)
+            cases.append(dict(label=label, text=text,
+                              records=[[p.matrix_id, p.name, np.asarray(p.matrix).tolist()] for p in pfms]))
+        except PfmsJasparFormatError as e:
+            cases.append(dict(label=label, text=text, error_line=int(str(e).split(' at line ')[1].split(':')[0])))
+        except ValueError as e:     # the matrix class rejects e.g. ragged rows after parsing
+            cases.append(dict(label=label, text=text, error=type(e).__name__))
+        finally:
+            os.unlink(path)
+    return cases
+
+
 def main():
     ref = import_reference()
+    if "--jaspar-only" in sys.argv:
+        path = os.path.join(HERE, "jaspar_cases.json")
+        with open(path, "w") as fh:
+            json.dump(gen_jaspar_cases(), fh, separators=(",", ":"))
+        print(f"wrote {path} ({os.path.getsize(path)} bytes)")
+        return
     out = {
+        "jaspar_cases.json": gen_jaspar_cases(),
         "cscore_cases.json": gen_cscore_cases(ref),
         "scanner_toy.json": gen_scanner_cases(),
         "dedup_cases.json": gen_dedup_cases(),

@@ -57,3 +57,23 @@ def test_product_does_not_import_oracle():
                 text = open(os.path.join(dirpath, f)).read()
                 assert not re.search(r"^\s*(import|from)\s+oracle\b", text, flags=re.M), f
                 assert "liboracle" not in text, f
+
+
+def test_shim_module_resolves_without_a_gpu():
+    """shim/motifscan/motif/cscore.py is the file a maintainer drops over the reference's extension: under
+    the reference's module name it exposes exactly c_score and c_scan_motif (cscore.c:479-482)."""
+    import sys
+    shim = os.path.join(ROOT, "shim")
+    saved = {k: v for k, v in sys.modules.items() if k == "motifscan" or k.startswith("motifscan.")}
+    for k in saved:
+        del sys.modules[k]
+    sys.path.insert(0, shim)
+    try:
+        import motifscan.motif.cscore as mod
+        from motifscan_b200.motif import cscore as ours
+        assert mod.c_score is ours.c_score and mod.c_scan_motif is ours.c_scan_motif
+    finally:
+        sys.path.remove(shim)
+        for k in [k for k in sys.modules if k == "motifscan" or k.startswith("motifscan.")]:
+            del sys.modules[k]
+        sys.modules.update(saved)

@@ -212,6 +212,28 @@ def test_arbitrary_float_int_and_degenerate_pwms(eng):
     sset.close(), motifs.close()
 
 
+@pytest.mark.parametrize("tc", [1, 0])
+def test_long_motifs_production_shape(eng, tc):
+    """Motifs longer than 32 columns: the tensor-core prefilter looks at the first 32 columns of each strand
+    and the exact stage scores the whole window from memory (N anywhere in it, also behind base 32); with the
+    table prefilter they take the every-position exact kernel.  Same sites either way, bit for bit."""
+    rng = np.random.default_rng(121)
+    pwms = synth_pwms(rng, 24, lmin=33, lmax=64) + synth_pwms(rng, 40, lmin=6, lmax=32)
+    seqs = synth_seqs(rng, 80, 200, 1500, p_n=0.004, n_blocks=True) + ["ACGT" * 8 + "A", "N" * 70, "acgt" * 16 + "N" + "acgt" * 9]
+    cutoffs = cutoffs_for(pwms, seqs, 3e-3)
+    ctx = eng.Context(0)
+    ctx.set_option("prefilter_tc", tc)
+    motifs = eng.MotifSet(ctx, pwms, cutoffs)
+    sset = eng.SequenceSet(ctx, seqs)
+    for strand in (3, 1, 2):
+        expect = oracle.scan_arrays(pwms, cutoffs, seqs, strand, n_threads=8)
+        res = eng.scan(ctx, motifs, sset, strand)
+        assert_scan_equal(res, expect)
+        assert int(expect[0][:24].sum()) > 200          # the long motifs do have sites
+        res.close()
+    sset.close(), motifs.close(), ctx.close()
+
+
 def test_dense_hits_overflow_retry(eng):
     """Cutoffs so low that candidates overflow the first buffers: results must not change."""
     rng = np.random.default_rng(13)
@@ -353,6 +375,77 @@ def test_score_select_matches_sorted_order_statistics(eng):
     want = np.sort(want, axis=1)[:, ::-1][:, ranks]
     assert np.array_equal(got.view(np.uint64), np.ascontiguousarray(want).view(np.uint64))
     sset.close(), motifs.close()
+
+
+@pytest.mark.parametrize("nudge", ["exact", "plus_1e-10", "next_double_up", "minus_half_quantum"])
+def test_cutoffs_placed_on_window_scores_lose_no_site(eng, nudge):
+    """The tensor-core prefilter must flag a SUPERSET of the reference's hits although it works with e4m3 entries
+    and f16 accumulators (one rounding per K step, prefilter_tc.cuh).  Adversarial placement: every motif's
+    cutoff sits exactly on the score of real windows of the input (so whole groups of windows are borderline:
+    score - cutoff = 0, or -1e-10 exactly, or one ulp short), or half an e4m3 quantum below them.  A window the
+    prefilter dropped could not come back, so equality with the oracle at site level is the superset property
+    at candidate level; the candidate counter is checked to be at least the number of sites as well."""
+    rng = np.random.default_rng(190)
+    pwms = synth_pwms(rng, 120, lmin=4, lmax=32)
+    seqs = synth_seqs(rng, 60, 500, 900, p_n=0.002, n_blocks=True)
+    loose = cutoffs_for(pwms, seqs, 5e-3)
+    counts, _, _, score, _ = oracle.scan_arrays(pwms, loose, seqs, 3, n_threads=8)
+    off = np.concatenate([[0], np.cumsum(counts)])
+    cutoffs = []
+    for m, p in enumerate(pwms):
+        sc = np.sort(score[off[m]:off[m + 1]])
+        if len(sc) == 0:
+            cutoffs.append(loose[m])
+            continue
+        c = float(sc[len(sc) // 2])                       # the score of actual windows of this input
+        if nudge == "plus_1e-10":
+            c = c + 1e-10
+        elif nudge == "next_double_up":
+            c = float(np.nextafter(c, np.inf))
+        elif nudge == "minus_half_quantum":
+            # one e4m3 step of the prefilter entries is ~1/16 of an entry; in score units that is about
+            # (sum colmax - T) / (C * 16) / max_raw with C = L * beta ~ 384
+            mat = np.asarray(p)
+            c = c - 0.5 * float(np.abs(mat).max(axis=0).sum()) / (384 * 16) / max(oracle.max_raw_score(p), 1e-9)
+        cutoffs.append(c)
+    ctx = eng.default_context(0)
+    motifs = eng.MotifSet(ctx, pwms, cutoffs)
+    sset = eng.SequenceSet(ctx, seqs)
+    for strand in (3, 1, 2):
+        expect = oracle.scan_arrays(pwms, cutoffs, seqs, strand, n_threads=8)
+        res = eng.scan(ctx, motifs, sset, strand)
+        assert_scan_equal(res, expect)
+        c = ctx.counters()
+        assert c["hits"] == int(expect[0].sum()) > 2000
+        # a candidate record covers a (window, 64-column chunk): every site needs a flagged column in one
+        assert c["candidates"] + c["dirty"] * len(pwms) * 2 >= np.count_nonzero(expect[0])
+        res.close()
+    sset.close(), motifs.close()
+
+
+def test_long_sequence_dedup_equals_reference_rule(eng):
+    """Device de-duplication walks chains of overlapping sites, not whole (motif, sequence) segments: on a few
+    long sequences (many sites per segment, runs of N whose all-zero windows tie) it must keep exactly the sites
+    the reference's pass keeps (scanner.py:156-193)."""
+    rng = np.random.default_rng(191)
+    pwms = synth_pwms(rng, 30, lmin=4, lmax=20)
+    seqs = synth_seqs(rng, 3, 60000, 90000, p_n=0.0005, n_blocks=True)
+    seqs[1] = seqs[1][:20000] + "N" * 3000 + seqs[1][23000:]
+    cutoffs = cutoffs_for(pwms, seqs, 2e-2)
+    cutoffs[0] = 0.0          # every all-N window of motif 0 is a site with score 0: one long chain of ties
+    ctx = eng.default_context(0)
+    motifs = eng.MotifSet(ctx, pwms, cutoffs)
+    sset = eng.SequenceSet(ctx, seqs)
+    res = eng.scan(ctx, motifs, sset, 3, remove_dup=True)
+    raw = oracle.c_scan_motif(pwms, cutoffs, seqs, 3, 8)
+    want = oracle.deduplicate_motif_sites(oracle.make_motif_sites(raw, [0] * len(seqs)), [len(p[0]) for p in pwms])
+    flat = [(m, r, s.start, s.score, 1 if s.strand == "+" else 2) for m, per in enumerate(want) for r, cell in enumerate(per) for s in cell]
+    assert res.n_sites == len(flat) > 5000 and res.n_sites < sum(len(x) for x in raw)
+    assert np.array_equal(res.seq_idx, np.array([f[1] for f in flat], dtype=np.int32))
+    assert np.array_equal(res.start, np.array([f[2] for f in flat], dtype=np.int32))
+    assert np.array_equal(res.strand, np.array([f[4] for f in flat], dtype=np.int8))
+    assert np.array_equal(res.score.view(np.uint64), np.array([f[3] for f in flat]).view(np.uint64))
+    res.close(), sset.close(), motifs.close()
 
 
 def test_score_select_pilot_path_equals_sorting_every_score(eng):

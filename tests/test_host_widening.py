@@ -126,3 +126,24 @@ def test_cli_parser_defaults():
     assert (args.n_random, args.n_repeat, args.max_n, args.seed) == (1000000, 1, 0, None)
     with pytest.raises(SystemExit):
         cli.make_parser().parse_args(["scan", "-i", "a.bed", "-m", "set", "-g", "hg19", "-o", "out", "-p", "1e-7"])
+
+
+def test_jaspar_parser_matches_the_reference_parser(tmp_path):
+    """tests/golden/jaspar_cases.json: the reference's own parser (motif/__init__.py:71-140) run on well-formed
+    and malformed texts -- multi-token headers (name = first token), old bare-number rows, blank lines, and
+    every malformed case with the line number its error names."""
+    import re
+    from conftest import load_golden
+    from motifscan_b200.motif import read_jaspar_pfms
+    cases = load_golden("jaspar_cases.json")
+    assert len(cases) >= 12
+    for c in cases:
+        path = tmp_path / (c["label"] + ".jaspar")
+        path.write_text(c["text"])
+        if "records" in c:
+            got = [[mid, name, m.tolist()] for mid, name, m in read_jaspar_pfms(str(path))]
+            assert got == c["records"], c["label"]
+        else:
+            with pytest.raises(ValueError) as err:
+                read_jaspar_pfms(str(path))
+            assert int(re.search(r"at line (\d+)", str(err.value)).group(1)) == c["error_line"], c["label"]
