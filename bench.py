@@ -51,7 +51,8 @@ P_VALUE = "1e-4"
 N_BACKGROUND = 100000
 GENOME_SEED = 19
 N_FRACTION = 0.07
-UNIT_BP = 1 << 26
+UNIT_BP = 1 << 26                 # largest unit; a share is cut into at least 8 units so that the first upload and the
+MIN_UNIT_BP = 1 << 24             # last download (the only copies nothing hides) stay small next to the share
 # secondary block (configs[1])
 N_REGIONS = 50000
 REGION_BP = 1000
@@ -497,6 +498,7 @@ def run_ours(args, rank, local_rank, world):
         dist.all_reduce(t)
         return int(t[0])
 
+    cpus = _lib.bind_thread_near(local_rank)     # before any pinned allocation: stay on this GPU's side of the host
     stream = torch.cuda.Stream()                 # the context launches on a stream torch can put events on
     ctx = engine.Context(local_rank, stream=stream.cuda_stream)
     pwms = motif_workload()
@@ -526,7 +528,8 @@ def run_ours(args, rank, local_rank, world):
     fp8 = measure_fp8_peak() if rank == 0 else None
 
     # ---- leg 1: device-resident -------------------------------------------------------------------------
-    gs = GenomeScanner(pg, pwms, cutoffs=cutoffs, contexts=[ctx], world=world, rank=rank, unit_bp=UNIT_BP, resident=True)
+    unit_bp = int(min(UNIT_BP, max(MIN_UNIT_BP, genome_bp // world // 8)))
+    gs = GenomeScanner(pg, pwms, cutoffs=cutoffs, contexts=[ctx], world=world, rank=rank, unit_bp=unit_bp, resident=True)
     share_bp = sum(u.owned_bp for u in gs.shares[0])
 
     def resident_step():
@@ -564,7 +567,7 @@ def run_ours(args, rank, local_rank, world):
     gs.close()
 
     # ---- leg 2: end to end (host planes in, host sites / counts out) -----------------------------------------
-    gs = GenomeScanner(pg, pwms, cutoffs=cutoffs, contexts=[ctx], world=world, rank=rank, unit_bp=UNIT_BP, resident=False)
+    gs = GenomeScanner(pg, pwms, cutoffs=cutoffs, contexts=[ctx], world=world, rank=rank, unit_bp=unit_bp, resident=False)
     h2d_bytes = sum(12 * (u.upload1 - u.block0) for u in gs.shares[0])
 
     def e2e_leg(collect_sites):
@@ -657,8 +660,9 @@ def run_ours(args, rank, local_rank, world):
                        "cutoffs": f"p={P_VALUE} from {N_BACKGROUND} background samples, floored at 1e-6 ({cut_src})",
                        "l2": "inputs larger than L2 (0.375 B/bp packed genome share, >= 145 MB per rank, streamed once per step)",
                        "parallelism": f"position space cut into {world} contiguous share(s), one process per GPU, units of "
-                                      f"{UNIT_BP} bp; gather = all-reduce of {N_MOTIFS} int64 counts over gloo inside every step",
-                       "genome_generation_s": gen_s},
+                                      f"{unit_bp} bp; gather = all-reduce of {N_MOTIFS} int64 counts over gloo inside every step",
+                       "genome_generation_s": gen_s,
+                       "host_cores_rank0": f"{len(cpus)} NUMA-local cores" if cpus else "unbound"},
             "phase_ms": {k: sum(v) / len(v) for k, v in phases.items()},
             "wall_ms_per_step": wall_ms, "units_per_step_rank0": n_units,
             "sites_per_step": n_sites_total, "candidates_per_step_rank0": candidates,

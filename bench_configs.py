@@ -59,6 +59,17 @@ def bench_build(args):
         dev = device_ms(ctx, "score", "select")
         sset.close()
     e2e = min(times[1:])
+    counters = ctx.counters()
+    # the plain form (every sample scored for every motif, select over the full rows) for comparison
+    ctx.set_option("select_pilot", 0)
+    sset = engine.SequenceSet(ctx, blob=blob, seq_off=off)
+    t0 = time.perf_counter()
+    plain = engine.score_select(ctx, motifs, sset, 3, [ranks[k] for k in keys])
+    plain_s = time.perf_counter() - t0
+    plain_dev = device_ms(ctx, "score", "select")
+    sset.close()
+    ctx.set_option("select_pilot", 1)
+    same_as_plain = bool(np.array_equal(sel.view(np.uint64), plain.view(np.uint64)))
     # parity on a bounded sample: the same pipeline on the first n samples vs the CPU reference
     kind, ext = cpu_ext()
     n = args.cpu_samples
@@ -75,7 +86,9 @@ def bench_build(args):
     return {"config": f"configs[2]: motif --build cutoffs, {args.motifs} motifs x {args.n_random} samples x {lmax} bp, "
                       f"p=1e-2..1e-{len(keys) + 1}",
             "metric": "motif*samples scored and ranked per second", "e2e_s": e2e,
-            "value": units / e2e, "device_ms": dev,
+            "value": units / e2e, "device_ms": dev, "device_ms_total": dev["score"] + dev["select"],
+            "candidate_sites": counters["hits"], "motifs_redone_the_plain_way": counters["retries"],
+            "plain_form": {"e2e_s": plain_s, "device_ms": plain_dev, "same_bits_as_pilot_form": same_as_plain},
             "cutoffs_p1e-4_head": np.around(sel[:3, keys.index("1e-4")], 8).tolist(),
             "cpu_baseline": {"kind": kind, "cores": os.cpu_count(), "sample": f"{n} samples (c_score + sort)",
                              "value": args.motifs * n / cpu_s, "seconds": cpu_s},

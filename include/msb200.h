@@ -51,6 +51,9 @@ typedef struct msb_result msb_result; /* host-resident sites of one scan, refere
 const char *msb_last_error(void);
 int msb_version(void);
 int msb_device_count(int *count);
+/* PCI bus id of a device ("0000:1b:00.0"): hosts use it to find the GPU's NUMA-local cores
+ * (/sys/bus/pci/devices/<id>/local_cpulist) before they allocate pinned buffers for it. */
+int msb_device_pci_bus_id(int device, char *out, int len);
 
 /* ---- context ------------------------------------------------------------------------------ */
 /* `stream` is an optional cudaStream_t (as void*) to launch on, e.g. torch's current stream;
@@ -206,6 +209,14 @@ int msb_result_destroy(msb_result *res);
  * Pure host code (memcpy on up to n_threads threads); no device, no context. */
 int msb_merge_motif_major(int32_t n_parts, int32_t n_motifs, const int64_t *counts, const void *const *src,
                           void *dst, int32_t elem_size, const int64_t *add_i32, int32_t n_threads);
+/* The same for whole site lists in one pass, with the parts' local sequence numbering translated on the way:
+ * part p's sequence q (a piece of a chromosome in a sharded genome scan, a region of a block in a multi-GPU
+ * region scan) becomes group seq_to_group[p][q] (its chromosome / global region) and its starts are shifted by
+ * seq_offset[p][q] (the piece's first base); either table may be NULL (identity / no shift). */
+int msb_merge_sites(int32_t n_parts, int32_t n_motifs, const int64_t *counts, const int32_t *const *seq_idx,
+                    const int32_t *const *start, const double *const *score, const int8_t *const *strand,
+                    const int32_t *const *seq_to_group, const int32_t *const *seq_offset, int32_t *out_group,
+                    int32_t *out_start, double *out_score, int8_t *out_strand, int32_t n_threads);
 
 /* ---- score (replaces motif_score_thread + motif_score, cscore.c:174-302) -------------------- */
 /* out is n_motifs x n_seqs row-major: the offset-0 window score of every sequence. */

@@ -31,6 +31,7 @@ SIGNATURES = {
     "msb_last_error": (ctypes.c_char_p, []),
     "msb_version": (ctypes.c_int, []),
     "msb_device_count": (ctypes.c_int, [ctypes.POINTER(ctypes.c_int)]),
+    "msb_device_pci_bus_id": (ctypes.c_int, [ctypes.c_int, ctypes.c_char_p, ctypes.c_int]),
     "msb_ctx_create": (ctypes.c_int, [ctypes.c_int, c_vp, ctypes.POINTER(c_vp)]),
     "msb_ctx_destroy": (ctypes.c_int, [c_vp]),
     "msb_ctx_sync": (ctypes.c_int, [c_vp]),
@@ -70,6 +71,8 @@ SIGNATURES = {
     "msb_result_wait": (ctypes.c_int, [c_vp]),
     "msb_merge_motif_major": (ctypes.c_int, [ctypes.c_int32, ctypes.c_int32, c_i64p, ctypes.POINTER(c_vp), c_vp,
                                              ctypes.c_int32, c_i64p, ctypes.c_int32]),
+    "msb_merge_sites": (ctypes.c_int, [ctypes.c_int32, ctypes.c_int32, c_i64p] + [ctypes.POINTER(c_vp)] * 6 +
+                        [c_vp, c_vp, c_vp, c_vp, ctypes.c_int32]),
     "msb_result_total": (ctypes.c_int, [c_vp, c_i64p]),
     "msb_result_counts": (ctypes.c_int, [c_vp, c_i64p]),
     "msb_result_arrays": (ctypes.c_int, [c_vp, ctypes.POINTER(c_i32p), ctypes.POINTER(c_i32p),
@@ -125,6 +128,27 @@ def device_count():
     n = ctypes.c_int(0)
     check(load().msb_device_count(ctypes.byref(n)))
     return n.value
+
+
+def bind_thread_near(device):
+    """Pin the calling host thread to the cores that are NUMA-local to a GPU (its PCI device's
+    `local_cpulist`), so that the pinned buffers it allocates next and its copies stay on that GPU's side
+    of the host.  Returns the core list, or None when the topology cannot be read (nothing is changed)."""
+    try:
+        buf = ctypes.create_string_buffer(32)
+        check(load().msb_device_pci_bus_id(int(device), buf, 32))
+        path = f"/sys/bus/pci/devices/{buf.value.decode().lower()}/local_cpulist"
+        cpus = set()
+        for part in open(path).read().strip().split(","):
+            a, _, b = part.partition("-")
+            cpus.update(range(int(a), int(b or a) + 1))
+        cpus &= os.sched_getaffinity(0)
+        if not cpus:
+            return None
+        os.sched_setaffinity(0, cpus)        # pid 0 = the calling thread
+        return sorted(cpus)
+    except Exception:
+        return None
 
 
 def flatten_pwms(pwms):

@@ -307,6 +307,12 @@ int msb_device_count(int *count) {
     return MSB_OK;
 }
 
+int msb_device_pci_bus_id(int device, char *out, int len) {
+    if (!out || len < 16) { set_error("msb_device_pci_bus_id: buffer too small"); return MSB_EINVAL; }
+    MSB_CUDA(cudaDeviceGetPCIBusId(out, len, device));
+    return MSB_OK;
+}
+
 int msb_pinned_alloc(int64_t bytes, void **ptr) {
     if (!ptr || bytes < 0) { set_error("msb_pinned_alloc: bad argument"); return MSB_EINVAL; }
     MSB_CUDA(cudaHostAlloc(ptr, (size_t) std::max<int64_t>(bytes, 1), cudaHostAllocDefault));
@@ -1893,21 +1899,19 @@ int msb_result_destroy(msb_result *R) {
 // 425-436); here several GPUs (or several batches of one) each return a motif-major array over THEIR
 // sequences, in ascending sequence order across parts, so the gathered list of motif m is part 0's slice,
 // then part 1's, ...: a copy, no sort, no pickling.  Host threads split the motifs by bytes.
-int msb_merge_motif_major(int32_t n_parts, int32_t n_motifs, const int64_t *counts, const void *const *src,
-                          void *dst, int32_t elem_size, const int64_t *add_i32, int32_t n_threads) {
-    if (n_parts < 0 || n_motifs < 0 || elem_size < 1 || (n_parts > 0 && n_motifs > 0 && (!counts || !src))) {
-        set_error("msb_merge_motif_major: bad argument");
-        return MSB_EINVAL;
-    }
-    if (add_i32 && elem_size != 4) { set_error("msb_merge_motif_major: an addend needs 4-byte elements"); return MSB_EINVAL; }
-    if (n_parts == 0 || n_motifs == 0) return MSB_OK;
-    // source offset of (part, motif) and destination offset of motif
+}  // extern "C"
+
+// Shared skeleton of the gathers: per-motif destination offsets, motifs split over host threads by output
+// size, `copy(part, src entry offset, dst entry offset, count)` moves one (motif, part) slice.
+template <typename Copy>
+static int merge_plan_run(int32_t n_parts, int32_t n_motifs, const int64_t *counts, int32_t n_threads, int64_t bytes_per_entry,
+                          Copy copy) {
     std::vector<int64_t> src_off((size_t) n_parts * n_motifs), dst_off((size_t) n_motifs + 1, 0);
     for (int32_t p = 0; p < n_parts; p++) {
         int64_t at = 0;
         for (int32_t m = 0; m < n_motifs; m++) {
             const int64_t c = counts[(size_t) p * n_motifs + m];
-            if (c < 0) { set_error("msb_merge_motif_major: negative count"); return MSB_EINVAL; }
+            if (c < 0) { set_error("msb_merge: negative count"); return MSB_EINVAL; }
             src_off[(size_t) p * n_motifs + m] = at;
             at += c;
             dst_off[m + 1] += c;
@@ -1916,9 +1920,8 @@ int msb_merge_motif_major(int32_t n_parts, int32_t n_motifs, const int64_t *coun
     for (int32_t m = 0; m < n_motifs; m++) dst_off[m + 1] += dst_off[m];
     const int64_t total = dst_off[n_motifs];
     if (total == 0) return MSB_OK;
-    if (!dst) { set_error("msb_merge_motif_major: null destination"); return MSB_EINVAL; }
     int nt = std::max(1, std::min<int>(n_threads, 64));
-    if ((int64_t) total * elem_size < (4 << 20)) nt = 1;
+    if (total * bytes_per_entry < (4 << 20)) nt = 1;
     auto work = [&](int t) {
         // motifs [m0, m1): boundaries at equal shares of the output
         const int64_t lo = total * t / nt, hi = total * (t + 1) / nt;
@@ -1929,16 +1932,7 @@ int msb_merge_motif_major(int32_t n_parts, int32_t n_motifs, const int64_t *coun
             for (int32_t p = 0; p < n_parts; p++) {
                 const int64_t c = counts[(size_t) p * n_motifs + m];
                 if (!c) continue;
-                const char *from = (const char *) src[p] + src_off[(size_t) p * n_motifs + m] * elem_size;
-                char *to = (char *) dst + at * elem_size;
-                if (add_i32 && add_i32[p]) {
-                    const int32_t add = (int32_t) add_i32[p];
-                    const int32_t *f = (const int32_t *) from;
-                    int32_t *o = (int32_t *) to;
-                    for (int64_t i = 0; i < c; i++) o[i] = f[i] + add;
-                } else {
-                    std::memcpy(to, from, (size_t) c * elem_size);
-                }
+                copy(p, src_off[(size_t) p * n_motifs + m], at, c);
                 at += c;
             }
         }
@@ -1949,6 +1943,59 @@ int msb_merge_motif_major(int32_t n_parts, int32_t n_motifs, const int64_t *coun
     work(0);
     for (auto &th : pool) th.join();
     return MSB_OK;
+}
+
+extern "C" {
+
+int msb_merge_motif_major(int32_t n_parts, int32_t n_motifs, const int64_t *counts, const void *const *src,
+                          void *dst, int32_t elem_size, const int64_t *add_i32, int32_t n_threads) {
+    if (n_parts < 0 || n_motifs < 0 || elem_size < 1 || (n_parts > 0 && n_motifs > 0 && (!counts || !src))) {
+        set_error("msb_merge_motif_major: bad argument");
+        return MSB_EINVAL;
+    }
+    if (add_i32 && elem_size != 4) { set_error("msb_merge_motif_major: an addend needs 4-byte elements"); return MSB_EINVAL; }
+    if (n_parts == 0 || n_motifs == 0) return MSB_OK;
+    int64_t total = 0;
+    for (size_t i = 0; i < (size_t) n_parts * n_motifs; i++) total += counts[i];
+    if (total > 0 && !dst) { set_error("msb_merge_motif_major: null destination"); return MSB_EINVAL; }
+    return merge_plan_run(n_parts, n_motifs, counts, n_threads, elem_size, [&](int32_t p, int64_t from_at, int64_t to_at, int64_t c) {
+        const char *from = (const char *) src[p] + from_at * elem_size;
+        char *to = (char *) dst + to_at * elem_size;
+        if (add_i32 && add_i32[p]) {
+            const int32_t add = (int32_t) add_i32[p];
+            const int32_t *f = (const int32_t *) from;
+            int32_t *o = (int32_t *) to;
+            for (int64_t i = 0; i < c; i++) o[i] = f[i] + add;
+        } else {
+            std::memcpy(to, from, (size_t) c * elem_size);
+        }
+    });
+}
+
+int msb_merge_sites(int32_t n_parts, int32_t n_motifs, const int64_t *counts, const int32_t *const *seq_idx,
+                    const int32_t *const *start, const double *const *score, const int8_t *const *strand,
+                    const int32_t *const *seq_to_group, const int32_t *const *seq_offset, int32_t *out_group,
+                    int32_t *out_start, double *out_score, int8_t *out_strand, int32_t n_threads) {
+    if (n_parts < 0 || n_motifs < 0 || (n_parts > 0 && n_motifs > 0 && (!counts || !seq_idx || !start || !score || !strand))) {
+        set_error("msb_merge_sites: bad argument");
+        return MSB_EINVAL;
+    }
+    if (n_parts == 0 || n_motifs == 0) return MSB_OK;
+    int64_t total = 0;
+    for (size_t i = 0; i < (size_t) n_parts * n_motifs; i++) total += counts[i];
+    if (total > 0 && (!out_group || !out_start || !out_score || !out_strand)) { set_error("msb_merge_sites: null destination"); return MSB_EINVAL; }
+    return merge_plan_run(n_parts, n_motifs, counts, n_threads, 17, [&](int32_t p, int64_t from_at, int64_t to_at, int64_t c) {
+        const int32_t *sq = seq_idx[p] + from_at, *st = start[p] + from_at;
+        const int32_t *grp = seq_to_group ? seq_to_group[p] : nullptr, *off = seq_offset ? seq_offset[p] : nullptr;
+        int32_t *og = out_group + to_at, *os = out_start + to_at;
+        for (int64_t i = 0; i < c; i++) {
+            const int32_t q = sq[i];
+            og[i] = grp ? grp[q] : q;
+            os[i] = off ? st[i] + off[q] : st[i];
+        }
+        std::memcpy(out_score + to_at, score[p] + from_at, (size_t) c * 8);
+        std::memcpy(out_strand + to_at, strand[p] + from_at, (size_t) c);
+    });
 }
 
 // ---- c_score -----------------------------------------------------------------------------------
@@ -2042,7 +2089,7 @@ static int score_select_direct(msb_ctx *ctx, const msb_motifs *M, const msb_seqs
 //
 // The reference scores every background sample for every motif (750 x 1e6 doubles = 6 GB), sorts each row and
 // reads five indices, all in the top 1 %.  Here:
-//   1. pilot: the first 32,768 samples are scored for all motifs (score0_kernel) and a radix select reads, per
+//   1. pilot: the first 24,576 samples are scored for all motifs (score0_kernel) and a radix select reads, per
 //      motif, the pilot score tau_m at 1.5 x the deepest wanted quantile;
 //   2. the scan path -- tensor-core prefilter + exact fp64 re-score -- runs over ALL samples with the tau_m as
 //      cutoffs and a start limit of 1 (only the offset-0 window of a sample is a window of the distribution,
@@ -2069,7 +2116,7 @@ int msb_score_select(msb_ctx *ctx, const msb_motifs *M, const msb_seqs *S, int s
     MSB_TRY(ctx->ranks.ensure((size_t) n_ranks * 8));
     MSB_CUDA(cudaMemcpyAsync(ctx->ranks.p, ranks, (size_t) n_ranks * 8, cudaMemcpyHostToDevice, st));
     double score_ms = 0, select_ms = 0;
-    const int64_t kPilot = 32768;
+    const int64_t kPilot = kSelSmemKeys;   // a pilot row fits the select kernel's shared-memory staging
     const bool pilot = ctx->opt_select_pilot && ctx->opt_prefilter_tc && S->n >= 8 * kPilot && (deepest + 1) * 32 <= S->n;
     ctx->c[MSB_C_RETRIES] = 0;
     if (!pilot) {

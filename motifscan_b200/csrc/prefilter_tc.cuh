@@ -328,9 +328,11 @@ prefilter_tc_kernel(const __grid_constant__ TcParams P) {
             mbar_wait_a(B.stream_full + 8 * slot, (it / kTcSlots) & 1);
             t_ws += now() - c0;
             fence_after();
-            if (!s_skip[slot]) {
+            {
+                const uint32_t skipmask = s_skip[slot];   // bit s: no live window starts at a position = s (mod 4) in this tile
 #pragma unroll 1
                 for (uint32_t s = 0; s < 4; s++) {
+                    if ((skipmask >> s) & 1u) continue;
                     const uint32_t a_lo = a_lo0 + ((slot * kTcSlotBytes + s * kTcStreamBytes) >> 4);
                     uint2 tile = s_tile[0];
 #pragma unroll 1
@@ -434,8 +436,14 @@ prefilter_tc_kernel(const __grid_constant__ TcParams P) {
                     }
                     s_ignore[slot * 16 + lane] = ign;
                 }
-                const bool all_ign = __all_sync(0xffffffffu, ign == 0xffffffffu);
-                if (lane == 0) s_skip[slot] = all_ign ? 1u : 0u;
+                // shift s of the tile holds the windows starting at positions = s (mod 4): when all of them are
+                // ignored (N runs, padding, a start limit that leaves only offset 0 of each sequence) its
+                // MMAs are not issued at all
+                uint32_t skipmask = 0;
+#pragma unroll
+                for (int sft = 0; sft < 4; sft++)
+                    skipmask |= (__all_sync(0xffffffffu, (ign | ~(0x11111111u << sft)) == 0xffffffffu) ? 1u : 0u) << sft;
+                if (lane == 0) s_skip[slot] = skipmask;
             }
             asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
             __syncwarp();
@@ -458,18 +466,24 @@ prefilter_tc_kernel(const __grid_constant__ TcParams P) {
             const long long cs = now();
             mbar_wait_a(B.stream_full + 8 * slot, (it / kTcSlots) & 1);
             t_wsf += now() - cs;
-            const uint32_t skip = s_skip[slot];
+            const uint32_t skipmask = s_skip[slot];
             const uint32_t ign4 = (s_ignore[slot * 16 + (row >> 3)] >> ((row & 7) * 4)) & 0xFu;
             __syncwarp();
             if (lane == 0) mbar_arrive_a(B.stream_empty + 8 * slot);
-            if (skip) continue;
+            if (skipmask == 0xFu) continue;
             const int64_t tile_start = t * kTcTileBases;
-            // units of this tile: v = 0 .. 4 NT - 1 (shift s = v / NT, tile nt = v % NT); 4 NT is even, so
-            // the TMEM buffer of unit u + v is v & 1 and this warp set reads v = set, set + 2, ...
-            uint32_t sh = 0, nt = (uint32_t) set;
-            while (nt >= NT) { nt -= NT; sh++; }
+            // units of this tile, in the issuer's order: for every shift that is not skipped, the NT tiles.
+            // Unit u + v lands in TMEM buffer (u + v) & 1; this warp set reads the ones in buffer `set`.
+            uint32_t act = 0, n_act = 0;                       // act: the active shifts, 2 bits each
+            for (uint32_t sft = 0; sft < 4; sft++)
+                if (!((skipmask >> sft) & 1u)) { act |= sft << (2 * n_act); n_act++; }
+            const uint32_t n_units = n_act * NT;
+            const uint32_t v0 = ((uint32_t) set ^ u) & 1u;
+            uint32_t ai = 0, nt = v0;
+            while (nt >= NT) { nt -= NT; ai++; }
 #pragma unroll 1
-            for (uint32_t v = (uint32_t) set; v < 4 * NT; v += 2) {
+            for (uint32_t v = v0; v < n_units; v += 2) {
+                const uint32_t sh = (act >> (2 * ai)) & 3u;
                 const uint32_t uu = u + v;
                 const bool live = !((ign4 >> sh) & 1u);
                 const int64_t p = tile_start + 4 * row + sh;
@@ -507,9 +521,9 @@ prefilter_tc_kernel(const __grid_constant__ TcParams P) {
                     }
                 }
                 nt += 2;
-                while (nt >= NT) { nt -= NT; sh++; }
+                while (nt >= NT) { nt -= NT; ai++; }
             }
-            u += 4 * NT;
+            u += n_units;
         }
         P.lane_count[lane_id] = out.n;
         if (kProf && P.prof && warp == 4 && lane == 0) {

@@ -366,6 +366,32 @@ def scan_ascii(ctx, motifs, blob, seq_off, strand, remove_dup=False, async_=Fals
     return ScanResult(ctx, h, motifs.n)
 
 
+def merge_sites(counts, seq_idx, start, score, strand, seq_to_group=None, seq_offset=None, n_threads=None):
+    """Gather the site lists of several scans (parts in ascending sequence order) into one motif-major list in
+    ONE pass over the data (msb_merge_sites), translating each part's local sequence numbers: sequence q of
+    part p becomes `seq_to_group[p][q]` and its starts move by `seq_offset[p][q]`.  Returns
+    (group int32, start int32, score float64, strand int8)."""
+    import os
+    counts = np.ascontiguousarray(np.asarray(counts, dtype=np.int64))
+    n_parts, n_motifs = counts.shape
+    total = int(counts.sum())
+    out = (np.empty(total, np.int32), np.empty(total, np.int32), np.empty(total, np.float64), np.empty(total, np.int8))
+    if n_parts == 0 or total == 0:
+        return out
+
+    def table(arrays, dtype):
+        if arrays is None:
+            return None, None
+        keep = [np.ascontiguousarray(a, dtype=dtype) for a in arrays]
+        return keep, (ctypes.c_void_p * n_parts)(*[ctypes.c_void_p(a.ctypes.data if a.size else 0) for a in keep])
+    keep = [table(seq_idx, np.int32), table(start, np.int32), table(score, np.float64), table(strand, np.int8),
+            table(seq_to_group, np.int32), table(seq_offset, np.int32)]
+    check(_lib.load().msb_merge_sites(n_parts, n_motifs, ptr(counts, ctypes.c_int64), *[k[1] for k in keep],
+                                      *[ctypes.c_void_p(o.ctypes.data) for o in out],
+                                      int(n_threads or min(os.cpu_count() or 1, 16))))
+    return out
+
+
 class PinnedArray:
     """A uint8 numpy view of page-locked host memory (msb_pinned_alloc); `.array` is the view."""
 

@@ -109,6 +109,24 @@ class Genome:
     def fetch_sequence(self, chrom, start, end):
         return self.fetch_bytes(chrom, start, end).decode("ascii")
 
+    def count_n(self, chroms, starts, length):
+        """`seq.count('N') + seq.count('n')` (genome/__init__.py:172-175) of the windows [start, start + length)
+        of the named chromosomes, for many windows at once: one gather from the memory-mapped FASTA instead of
+        one fetch per window (windows are clipped at the chromosome end like fetch)."""
+        starts = np.asarray(starts, dtype=np.int64)
+        out = np.zeros(len(starts), dtype=np.int64)
+        if len(starts) == 0 or length <= 0:
+            return out
+        data = np.frombuffer(self._mm, dtype=np.uint8)
+        meta = np.array([self._index[c] for c in chroms], dtype=np.int64).reshape(-1, 4)   # length, offset, bases, width
+        size, offset, bases, width = meta[:, 0], meta[:, 1], np.maximum(meta[:, 2], 1), meta[:, 3]
+        pos = starts[:, None] + np.arange(length, dtype=np.int64)[None, :]
+        inside = (pos >= 0) & (pos < size[:, None])
+        pos = np.where(inside, pos, 0)
+        at = offset[:, None] + (pos // bases[:, None]) * width[:, None] + pos % bases[:, None]
+        byte = data[np.minimum(at, data.size - 1)]
+        return (((byte == ord("N")) | (byte == ord("n"))) & inside).sum(axis=1)
+
     def random_sequences(self, n_times, length, max_n=0, random_seed=None):
         """Background sampling with the reference's exact RNG call sequence
         (genome/__init__.py:159-176): legacy `np.random.seed`, one `np.random.choice` of `n_times`
@@ -261,6 +279,21 @@ class PackedGenome:
     def fetch_sequence(self, chrom, start, end):
         return self.fetch_bytes(chrom, start, end).decode("ascii")
 
+    def count_n(self, chroms, starts, length):
+        """N / n count of many windows (the background sampler's acceptance test): the source genome's when there
+        is one; the planes' own mask otherwise (every masked base decodes to `N`)."""
+        g = self.__dict__.get("genome")
+        if g is not None and hasattr(g, "count_n"):
+            return g.count_n(chroms, starts, length)
+        starts = np.asarray(starts, dtype=np.int64)
+        cidx = np.array([self.chrom_index[c] for c in chroms], dtype=np.int64)
+        size = np.array([self.chrom_sizes[c] for c in chroms], dtype=np.int64)
+        pos = starts[:, None] + np.arange(length, dtype=np.int64)[None, :]
+        inside = (pos >= 0) & (pos < size[:, None])
+        pos = np.where(inside, pos, 0)
+        word = np.asarray(self.nmask)[self.block_off[cidx][:, None] + pos // 32]
+        return ((((word >> (pos % 32).astype(np.uint32)) & 1) == 1) & inside).sum(axis=1)
+
     def close(self):
         self._pin = None
 
@@ -334,9 +367,15 @@ class DeviceGenome:
             starts = np.random.randint(sizes[idx] - length)
             ncount = self.seqs.window_ncount(idx, starts, length)
             ok = ncount <= max_n
-            for k in np.flatnonzero(~ok):                            # may still pass by the reference's own count
-                seq = self.genome.fetch_sequence(self.chroms[idx[k]], int(starts[k]), int(starts[k]) + length)
-                ok[k] = seq.count("N") + seq.count("n") <= max_n
+            again = np.flatnonzero(~ok)                              # may still pass by the reference's own count:
+            if len(again):                                           # it counts 'N' and 'n' only, the mask every non-ACGT byte
+                count_n = getattr(self.genome, "count_n", None)
+                if count_n is not None:
+                    ok[again] = count_n([self.chroms[i] for i in idx[again]], starts[again], length) <= max_n
+                else:
+                    for k in again:
+                        seq = self.genome.fetch_sequence(self.chroms[idx[k]], int(starts[k]), int(starts[k]) + length)
+                        ok[k] = seq.count("N") + seq.count("n") <= max_n
             cum = np.cumsum(ok)
             need = n_times - got
             if cum[-1] >= need:

@@ -225,18 +225,9 @@ class ShardedSites(GenomeSites):
             self.score, self.strand = np.zeros(0, np.float64), np.zeros(0, np.int8)
         else:
             cnt = np.stack([p[0].counts for p in parts])
-            first_piece = np.zeros(len(parts), dtype=np.int64)        # global piece number of a part's piece 0
-            np.cumsum([len(p[1]) for p in parts[:-1]], out=first_piece[1:])
-            piece = engine.merge_motif_major(cnt, [p[0].seq_idx for p in parts], add=first_piece)
-            start = engine.merge_motif_major(cnt, [p[0].start for p in parts])
-            self.score = engine.merge_motif_major(cnt, [p[0].score for p in parts])
-            self.strand = engine.merge_motif_major(cnt, [p[0].strand for p in parts])
-            piece_chrom = np.concatenate([p[1] for p in parts]).astype(np.int32)
-            piece_start = np.concatenate([p[2] for p in parts]).astype(np.int32)
-            self.chrom_idx = piece_chrom[piece]
-            if piece_start.any():
-                start += piece_start[piece]
-            self.start = start
+            self.chrom_idx, self.start, self.score, self.strand = engine.merge_sites(
+                cnt, [p[0].seq_idx for p in parts], [p[0].start for p in parts], [p[0].score for p in parts],
+                [p[0].strand for p in parts], seq_to_group=[p[1] for p in parts], seq_offset=[p[2] for p in parts])
         for p in self._parts:
             p[0].close()
         self._parts = []
@@ -292,6 +283,8 @@ class GenomeScanner:
 
     def _scan_share(self, k, collect_sites, order_sites=False):
         ctx, motifs, units = self.ctxs[k], self.motifs[k], self.shares[k]
+        if len(self.devices) > 1:
+            _lib.bind_thread_near(ctx.device)     # worker thread of one GPU: stay on that GPU's side of the host
         n_motifs = len(self.matrices)
         counts = np.zeros(n_motifs, dtype=np.int64)
         parts, stats = [], {}

@@ -24,7 +24,7 @@ _STRAND_ARG = {"+": 1, "-": 2, "both": 3}  # scanner.py:118-123
 class _MergedResult:
     """The gathered arrays of several devices' ScanResults, shaped like one (what MotifSites reads)."""
 
-    def __init__(self, results, block_starts, n_motifs):
+    def __init__(self, results, block_starts, n_motifs, n_seqs):
         counts = np.stack([r.counts for r in results]) if results else np.zeros((0, n_motifs), dtype=np.int64)
         self.counts = counts.sum(axis=0) if len(results) else np.zeros(n_motifs, dtype=np.int64)
         self.offsets = np.zeros(n_motifs + 1, dtype=np.int64)
@@ -32,10 +32,10 @@ class _MergedResult:
         self.n_sites = int(self.counts.sum())
         # per motif: device 0's sites, then device 1's, ... -- the devices hold ascending blocks of regions,
         # so this is the reference's (motif, region, start) order; region indices become global on the way
-        self.seq_idx = engine.merge_motif_major(counts, [r.seq_idx for r in results], add=block_starts)
-        self.start = engine.merge_motif_major(counts, [r.start for r in results])
-        self.score = engine.merge_motif_major(counts, [r.score for r in results])
-        self.strand = engine.merge_motif_major(counts, [r.strand for r in results])
+        groups = [np.arange(a, b, dtype=np.int32) for a, b in zip(block_starts, list(block_starts[1:]) + [n_seqs])]
+        self.seq_idx, self.start, self.score, self.strand = engine.merge_sites(
+            counts, [r.seq_idx for r in results], [r.start for r in results], [r.score for r in results],
+            [r.strand for r in results], seq_to_group=groups)
         for r in results:
             r.close()
 
@@ -160,7 +160,7 @@ class Scanner:
             import concurrent.futures
             with concurrent.futures.ThreadPoolExecutor(max_workers=len(ctxs)) as pool:
                 results = list(pool.map(scan_block, range(len(ctxs))))
-            res = _MergedResult(results, bounds[:-1], len(matrices))
+            res = _MergedResult(results, bounds[:-1], len(matrices), n)
         return MotifSites(res, len(matrices), self.seq_starts, lengths)
 
     def _packed_on(self, ctx):

@@ -137,3 +137,24 @@ def test_two_rank_sharded_count_gather():
         p.join(timeout=120)
         assert p.exitcode == 0
     assert q.get(timeout=5) is True and q.get(timeout=5) is True
+
+
+def test_merge_sites_translates_local_sequence_numbers():
+    from motifscan_b200 import engine
+    rng = np.random.default_rng(3)
+    for n_parts, n_motifs, scale in ((1, 4, 20), (5, 60, 3000), (3, 750, 50)):
+        counts = rng.integers(0, scale + 1, size=(n_parts, n_motifs)).astype(np.int64)
+        n_seq = [int(rng.integers(1, 9)) for _ in range(n_parts)]
+        seq = [rng.integers(0, n_seq[p], size=int(counts[p].sum())).astype(np.int32) for p in range(n_parts)]
+        start = [rng.integers(0, 10**6, size=len(s)).astype(np.int32) for s in seq]
+        score = [rng.normal(size=len(s)) for s in seq]
+        strand = [rng.integers(1, 3, size=len(s)).astype(np.int8) for s in seq]
+        group = [rng.integers(0, 25, size=n).astype(np.int32) for n in n_seq]
+        offset = [rng.integers(0, 10**8, size=n).astype(np.int32) for n in n_seq]
+        order = np.argsort(np.concatenate([np.repeat(np.arange(n_motifs), counts[p]) for p in range(n_parts)]), kind="stable")
+        g, st, sc, sd = engine.merge_sites(counts, seq, start, score, strand, seq_to_group=group, seq_offset=offset)
+        assert np.array_equal(g, np.concatenate([group[p][seq[p]] for p in range(n_parts)])[order])
+        assert np.array_equal(st, np.concatenate([start[p] + offset[p][seq[p]] for p in range(n_parts)])[order])
+        assert np.array_equal(sc, np.concatenate(score)[order]) and np.array_equal(sd, np.concatenate(strand)[order])
+        g2, st2, _, _ = engine.merge_sites(counts, seq, start, score, strand)
+        assert np.array_equal(g2, np.concatenate(seq)[order]) and np.array_equal(st2, np.concatenate(start)[order])
