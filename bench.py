@@ -19,7 +19,7 @@ One "step" = one pass over the whole genome:
   e2e          host buffers in, host buffers out, through the product API (`GenomeScanner.scan`, i.e. the C-ABI
                calls msb_seqs_from_packed / msb_scan_ranges / msb_result_*): every step uploads the share's
                packed planes from pinned host memory (0.375 B/bp), scans it unit by unit and copies ALL sites
-               (score, chromosome piece, start, strand: 17 B each) to pinned host memory, upload and download
+               (score + packed position and strand: 12 B each, MSB_SCAN_COMPACT) to pinned host memory, upload and download
                overlapping the scan of the neighbouring unit; then the count gather.  Wall clock between
                synchronisations, max over ranks.  `e2e.variants.counts_out` is the same with only the
                per-motif counts coming back (MSB_SCAN_COUNTS).
@@ -593,7 +593,7 @@ def run_ours(args, rank, local_rank, world):
     counts_ms, _, total_b, _ = e2e_leg(False)
     sites_ms, sites_here, total_c, kept = e2e_leg(True)
     clocks = sampler.stop()
-    d2h_sites = 17 * sites_here + 8 * (N_MOTIFS + 1) * len(gs.shares[0])
+    d2h_sites = 12 * sites_here + 8 * (N_MOTIFS + 1) * len(gs.shares[0])
     d2h_counts = 8 * N_MOTIFS * len(gs.shares[0])
     assert np.array_equal(total_b, total_counts) and np.array_equal(total_c, total_counts), "legs disagree on the per-motif counts"
     merge_ms = None
@@ -777,7 +777,7 @@ def configs1_block(args, engine, ctx, pg, pwms, cutoffs, torch, barrier, max_ove
 
     def e2e_step(prev):
         w = resident.extract(idx, starts, starts + REGION_BP)
-        res = engine.scan(ctx, motifs, w, 3, async_=True)
+        res = engine.scan(ctx, motifs, w, 3, async_=True, compact=True)
         w.close()
         if prev is not None:
             prev.wait()
@@ -805,8 +805,9 @@ def configs1_block(args, engine, ctx, pg, pwms, cutoffs, torch, barrier, max_ove
         "timing": "sum of the three phases' CUDA-event times per step (prefilter + exact + order), L2 flushed between steps",
         "phase_ms": {k: sum(v) / len(v) for k, v in phase.items()}, "sites_per_step_rank0": int(n_sites),
         "e2e": {"value": world * units / (e2e_ms / 1e3), "unit": UNIT, "ms_per_step": e2e_ms,
-                "h2d_bytes_per_step": world * 20 * n_regions, "d2h_bytes_per_step": world * (17 * int(sites) + 8 * (N_MOTIFS + 1)),
-                "what": "region descriptors up, windows cut from the resident chromosome on the device, scan, all sites down; "
+                "h2d_bytes_per_step": world * 20 * n_regions, "d2h_bytes_per_step": world * (12 * int(sites) + 8 * (N_MOTIFS + 1)),
+                "what": "region descriptors up, windows cut from the resident chromosome on the device, scan, all sites down (12 B each: "
+                        "score + packed position and strand, MSB_SCAN_COMPACT); "
                         "steps pipelined with MSB_SCAN_ASYNC, wall clock over the steps until the last sites are on the host"},
         "_launches": launches,
     }

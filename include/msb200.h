@@ -160,6 +160,13 @@ int msb_scan(msb_ctx *ctx, const msb_motifs *motifs, const msb_seqs *seqs, int s
  * context's copy stream; the next scan on the same context overlaps it.  msb_result_total is valid at
  * once; msb_result_wait (or msb_result_counts / msb_result_arrays, which wait) makes the arrays valid. */
 #define MSB_SCAN_ASYNC 4
+/* MSB_SCAN_COMPACT: sites come back as 12 bytes (score + a uint32 holding packed position << 1 | strand bit)
+ * instead of 17: a third less PCIe traffic, which is what bounds an all-sites genome-wide scan on 8 GPUs of
+ * one host.  msb_result_compact hands out the raw arrays + the sequence layout that decodes them;
+ * msb_result_arrays still works (the first call decodes on the host); msb_merge_sites_compact gathers such
+ * results directly.  Ignored with MSB_SCAN_DEDUP and for sequence sets of 2^31 packed positions or more
+ * (the result is then an ordinary one: msb_result_compact returns a NULL array). */
+#define MSB_SCAN_COMPACT 8
 int msb_scan_ex(msb_ctx *ctx, const msb_motifs *motifs, const msb_seqs *seqs, int strand,
                 int flags, msb_result **out);
 /* c_scan_motif in one call with persistent motifs (cscore.c:399-476: strings in, sites out):
@@ -198,6 +205,11 @@ int msb_result_counts(const msb_result *res, int64_t *counts /* n_motifs */);
 /* Borrowed pointers into the result (valid until msb_result_destroy): n_sites entries each. */
 int msb_result_arrays(const msb_result *res, const int32_t **seq_idx, const int32_t **start,
                       const double **score, const int8_t **strand /* 1 or 2 */);
+/* Compact results (MSB_SCAN_COMPACT): pos_strand[i] >> 1 is the site's packed position p, sequence s owns it
+ * iff poff[s] <= p < poff[s + 1] (poff: n_seqs + 1 entries, multiples of 32), start = p - poff[s];
+ * pos_strand[i] & 1 = 0 forward, 1 reverse.  *pos_strand is NULL for a result that is not compact. */
+int msb_result_compact(const msb_result *res, const uint32_t **pos_strand, const double **score, const int64_t **poff,
+                       int64_t *n_seqs);
 int msb_result_destroy(msb_result *res);
 
 /* ---- host-side gather of several results (replaces the reference's per-motif result lists filled by
@@ -217,6 +229,11 @@ int msb_merge_sites(int32_t n_parts, int32_t n_motifs, const int64_t *counts, co
                     const int32_t *const *start, const double *const *score, const int8_t *const *strand,
                     const int32_t *const *seq_to_group, const int32_t *const *seq_offset, int32_t *out_group,
                     int32_t *out_start, double *out_score, int8_t *out_strand, int32_t n_threads);
+/* msb_merge_sites over compact results (msb_result_compact's arrays and layout per part). */
+int msb_merge_sites_compact(int32_t n_parts, int32_t n_motifs, const int64_t *counts, const uint32_t *const *pos_strand,
+                            const double *const *score, const int64_t *const *poff, const int64_t *n_seqs,
+                            const int32_t *const *seq_to_group, const int32_t *const *seq_offset, int32_t *out_group,
+                            int32_t *out_start, double *out_score, int8_t *out_strand, int32_t n_threads);
 
 /* ---- score (replaces motif_score_thread + motif_score, cscore.c:174-302) -------------------- */
 /* out is n_motifs x n_seqs row-major: the offset-0 window score of every sequence. */

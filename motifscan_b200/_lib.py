@@ -16,6 +16,7 @@ MSB_OK, MSB_EINVAL, MSB_ENOMEM, MSB_ECUDA, MSB_ESHORT = 0, -1, -2, -3, -4
 MSB_SCAN_DEDUP = 1
 MSB_SCAN_COUNTS = 2
 MSB_SCAN_ASYNC = 4
+MSB_SCAN_COMPACT = 8
 MSB_SEQS_ASYNC = 1
 T_NAMES = ("h2d", "encode", "prefilter", "exact", "order", "d2h", "score", "select")
 C_NAMES = ("candidates", "dirty", "hits", "launches", "retries", "prefilter_launches")
@@ -73,6 +74,10 @@ SIGNATURES = {
                                              ctypes.c_int32, c_i64p, ctypes.c_int32]),
     "msb_merge_sites": (ctypes.c_int, [ctypes.c_int32, ctypes.c_int32, c_i64p] + [ctypes.POINTER(c_vp)] * 6 +
                         [c_vp, c_vp, c_vp, c_vp, ctypes.c_int32]),
+    "msb_merge_sites_compact": (ctypes.c_int, [ctypes.c_int32, ctypes.c_int32, c_i64p] + [ctypes.POINTER(c_vp)] * 3 + [c_i64p] +
+                                [ctypes.POINTER(c_vp)] * 2 + [c_vp, c_vp, c_vp, c_vp, ctypes.c_int32]),
+    "msb_result_compact": (ctypes.c_int, [c_vp, ctypes.POINTER(ctypes.POINTER(ctypes.c_uint32)), ctypes.POINTER(c_f64p),
+                                          ctypes.POINTER(c_i64p), c_i64p]),
     "msb_result_total": (ctypes.c_int, [c_vp, c_i64p]),
     "msb_result_counts": (ctypes.c_int, [c_vp, c_i64p]),
     "msb_result_arrays": (ctypes.c_int, [c_vp, ctypes.POINTER(c_i32p), ctypes.POINTER(c_i32p),

@@ -626,6 +626,14 @@ decode_sites_kernel(SeqView S, const uint64_t *__restrict__ key, int64_t n, int 
     strand[i] = (int8_t) (key_rev(k) + 1);  // 1 forward, 2 reverse (cscore.c:359,376)
 }
 
+// MSB_SCAN_COMPACT: a site's packed position and strand are the low key_shift (<= 32) bits of its sorted key
+// (make_site_key); 4 bytes per site cross PCIe instead of 9 and the host finds the owning sequence.
+__global__ void __launch_bounds__(256)
+compact_sites_kernel(const uint64_t *__restrict__ key, int64_t n, int key_shift, uint32_t *__restrict__ out) {
+    const int64_t i = (int64_t) blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) out[i] = (uint32_t) (key[i] & ((1ull << key_shift) - 1ull));
+}
+
 // offsets[m] = first sorted site whose motif id is >= m  (m = 0..n_motifs): CSR over motifs.
 __global__ void __launch_bounds__(256)
 motif_offsets_kernel(const uint64_t *__restrict__ key, int64_t n, int32_t n_motifs, int key_shift,

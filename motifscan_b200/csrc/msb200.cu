@@ -89,6 +89,8 @@ struct msb_ctx {
     } fin[2];
     int fin_cur = 0;
     bool last_counts_only = false;
+    bool last_compact = false;             // MSB_SCAN_COMPACT: fin[].start holds (packed position << 1 | strand) as uint32
+    const msb_seqs *last_seqs = nullptr;   // the sequence set of the last scan (its layout decodes compact sites)
     cudaStream_t d2h_stream = nullptr;
     // final site arrays of the last scan (point into fin[fin_cur])
     uint64_t *fin_key = nullptr;
@@ -203,6 +205,9 @@ struct msb_result {
     double *score = nullptr;
     int8_t *strand = nullptr;
     int64_t *offsets = nullptr;
+    uint32_t *compact = nullptr;            // MSB_SCAN_COMPACT: packed position << 1 | strand bit, instead of the three arrays
+    std::vector<int64_t> poff;              // compact: packed start of every sequence of the scanned set (+ end)
+    std::vector<char> decoded;              // compact: seq_idx | start | strand, filled by the first msb_result_arrays
     std::vector<int64_t> counts;
     cudaEvent_t t0 = nullptr, done = nullptr;   // on the context's d2h stream around the copies
     bool pending = false;                       // MSB_SCAN_ASYNC: the copies may still be in flight
@@ -1312,6 +1317,8 @@ static int scan_device(msb_ctx *ctx, msb_motifs *M, const msb_seqs *S, int stran
     msb_ctx::FinSet &F = ctx->fin[fin_set];
     if (F.pending) { MSB_CUDA(cudaStreamWaitEvent(st, F.read_done, 0)); F.pending = false; }
     const bool counts_only = (flags & MSB_SCAN_COUNTS) && !(flags & MSB_SCAN_DEDUP);
+    ctx->last_compact = false;
+    ctx->last_seqs = S;
     MSB_TRY(F.offsets.ensure((size_t) (M->n + 1) * 8));  // CSR offsets over motifs
     MSB_CUDA(cudaMemsetAsync(F.offsets.p, 0, (size_t) (M->n + 1) * 8, st));
     ctx->fin_key = nullptr;
@@ -1555,8 +1562,14 @@ static int scan_device(msb_ctx *ctx, msb_motifs *M, const msb_seqs *S, int stran
         MSB_CUDA(cub::DeviceRadixSort::SortPairs(ctx->sort_tmp.p, tmp_bytes, ctx->hit_key.as<uint64_t>(), s_key.as<uint64_t>(),
                                                  ctx->hit_score.as<double>(), s_score.as<double>(), n_hits, 0, end_bit, st));
         const unsigned grid = (unsigned) ((n_hits + 255) / 256);
-        decode_sites_kernel<<<grid, 256, 0, st>>>(sv, s_key.as<uint64_t>(), n_hits, key_shift, s_seq.as<int32_t>(),
-                                                  s_start.as<int32_t>(), s_strand.as<int8_t>());
+        const bool compact = (flags & MSB_SCAN_COMPACT) && !dedup && key_shift <= 32;
+        if (compact) {
+            compact_sites_kernel<<<grid, 256, 0, st>>>(s_key.as<uint64_t>(), n_hits, key_shift, s_start.as<uint32_t>());
+            ctx->last_compact = true;
+        } else {
+            decode_sites_kernel<<<grid, 256, 0, st>>>(sv, s_key.as<uint64_t>(), n_hits, key_shift, s_seq.as<int32_t>(),
+                                                      s_start.as<int32_t>(), s_strand.as<int8_t>());
+        }
         MSB_CUDA(cudaGetLastError());
         ctx->c[MSB_C_LAUNCHES] += 2;  // sort (several CUB kernels, counted once) + decode
         if (dedup) {
@@ -1654,6 +1667,7 @@ int msb_scan_device_region_counts(msb_ctx *ctx, int64_t *counts, int32_t n_motif
     MSB_CUDA(cudaSetDevice(ctx->device));
     std::fill(counts, counts + n_motifs, (int64_t) 0);
     if (ctx->last_counts_only) { set_error("msb_scan_device_region_counts: the last scan kept per-motif counts only (MSB_SCAN_COUNTS)"); return MSB_EINVAL; }
+    if (ctx->last_compact) { set_error("msb_scan_device_region_counts: the last scan kept compact sites (MSB_SCAN_COMPACT)"); return MSB_EINVAL; }
     if (ctx->last_sites == 0) return MSB_OK;
     cudaStream_t st = ctx->stream;
     MSB_TRY(ctx->sel.ensure((size_t) n_motifs * 8));
@@ -1816,14 +1830,20 @@ static int collect_result(msb_ctx *ctx, const msb_motifs *M, int flags, msb_resu
     R->n_motifs = M->n;
     R->counts.assign((size_t) M->n, 0);
     const int64_t n = R->n_sites;
-    const size_t off_at = ((size_t) 17 * (size_t) n + 7) & ~(size_t) 7;
+    const bool compact = ctx->last_compact && n > 0;
+    const size_t off_at = ((size_t) (compact ? 12 : 17) * (size_t) n + 7) & ~(size_t) 7;
     int rc = pinned_get(ctx, off_at + (size_t) (M->n + 1) * 8, &R->block);
     if (rc != MSB_OK) { delete R; return rc; }
     char *base = (char *) R->block.p;
     R->score = (double *) base;
-    R->seq_idx = (int32_t *) (base + 8 * n);
-    R->start = (int32_t *) (base + 12 * n);
-    R->strand = (int8_t *) (base + 16 * n);
+    if (compact) {
+        R->compact = (uint32_t *) (base + 8 * n);
+        R->poff = ctx->last_seqs->poff;
+    } else {
+        R->seq_idx = (int32_t *) (base + 8 * n);
+        R->start = (int32_t *) (base + 12 * n);
+        R->strand = (int8_t *) (base + 16 * n);
+    }
     R->offsets = (int64_t *) (base + off_at);
     cudaStream_t st = ctx->stream, cs = ctx->d2h_stream;
     cudaError_t e = cudaEventCreate(&R->t0);
@@ -1834,9 +1854,13 @@ static int collect_result(msb_ctx *ctx, const msb_motifs *M, int flags, msb_resu
     step(cudaEventRecord(R->t0, cs));
     if (n) {
         step(cudaMemcpyAsync(R->score, ctx->fin_score, (size_t) n * 8, cudaMemcpyDeviceToHost, cs));
-        step(cudaMemcpyAsync(R->seq_idx, ctx->fin_seq, (size_t) n * 4, cudaMemcpyDeviceToHost, cs));
-        step(cudaMemcpyAsync(R->start, ctx->fin_start, (size_t) n * 4, cudaMemcpyDeviceToHost, cs));
-        step(cudaMemcpyAsync(R->strand, ctx->fin_strand, (size_t) n, cudaMemcpyDeviceToHost, cs));
+        if (compact) {
+            step(cudaMemcpyAsync(R->compact, ctx->fin_start, (size_t) n * 4, cudaMemcpyDeviceToHost, cs));
+        } else {
+            step(cudaMemcpyAsync(R->seq_idx, ctx->fin_seq, (size_t) n * 4, cudaMemcpyDeviceToHost, cs));
+            step(cudaMemcpyAsync(R->start, ctx->fin_start, (size_t) n * 4, cudaMemcpyDeviceToHost, cs));
+            step(cudaMemcpyAsync(R->strand, ctx->fin_strand, (size_t) n, cudaMemcpyDeviceToHost, cs));
+        }
     }
     step(cudaMemcpyAsync(R->offsets, F.offsets.p, (size_t) (M->n + 1) * 8, cudaMemcpyDeviceToHost, cs));
     step(cudaEventRecord(R->done, cs));
@@ -1876,12 +1900,48 @@ int msb_result_arrays(const msb_result *R, const int32_t **seq_idx, const int32_
                       const double **score, const int8_t **strand) {
     if (!R) { set_error("null result"); return MSB_EINVAL; }
     MSB_TRY(result_finish(const_cast<msb_result *>(R)));
+    if (R->compact && !R->seq_idx) {   // first look at a compact result: find every site's sequence on the host
+        msb_result *W = const_cast<msb_result *>(R);
+        const int64_t n = R->n_sites;
+        W->decoded.resize((size_t) 9 * n + 16);
+        W->seq_idx = (int32_t *) W->decoded.data();
+        W->start = W->seq_idx + n;
+        W->strand = (int8_t *) (W->start + n);
+        const std::vector<int64_t> &poff = R->poff;
+        const int nt = n < (1 << 20) ? 1 : (int) std::min<unsigned>(std::max(1u, std::thread::hardware_concurrency()), 16u);
+        auto work = [&](int t) {
+            int64_t s = 0;   // sites of one motif ascend in position: the previous site's sequence is a good first guess
+            for (int64_t i = n * t / nt; i < n * (t + 1) / nt; i++) {
+                const int64_t p = (int64_t) (R->compact[i] >> 1);
+                if (!(poff[s] <= p && p < poff[s + 1]))
+                    s = (int64_t) (std::upper_bound(poff.begin(), poff.end() - 1, p) - poff.begin()) - 1;
+                W->seq_idx[i] = (int32_t) s;
+                W->start[i] = (int32_t) (p - poff[s]);
+                W->strand[i] = (int8_t) ((R->compact[i] & 1u) + 1);
+            }
+        };
+        std::vector<std::thread> pool;
+        for (int t = 1; t < nt; t++) pool.emplace_back(work, t);
+        work(0);
+        for (auto &th : pool) th.join();
+    }
     if (seq_idx) *seq_idx = R->seq_idx;
     if (start) *start = R->start;
     if (score) *score = R->score;
     if (strand) *strand = R->strand;
     return MSB_OK;
 }
+int msb_result_compact(const msb_result *R, const uint32_t **pos_strand, const double **score, const int64_t **poff,
+                       int64_t *n_seqs) {
+    if (!R) { set_error("null result"); return MSB_EINVAL; }
+    MSB_TRY(result_finish(const_cast<msb_result *>(R)));
+    if (pos_strand) *pos_strand = R->compact;           // NULL: the result is not compact
+    if (score) *score = R->score;
+    if (poff) *poff = R->poff.empty() ? nullptr : R->poff.data();
+    if (n_seqs) *n_seqs = R->poff.empty() ? 0 : (int64_t) R->poff.size() - 1;
+    return MSB_OK;
+}
+
 int msb_result_destroy(msb_result *R) {
     if (!R) return MSB_OK;
     cudaSetDevice(R->device);
@@ -1995,6 +2055,37 @@ int msb_merge_sites(int32_t n_parts, int32_t n_motifs, const int64_t *counts, co
         }
         std::memcpy(out_score + to_at, score[p] + from_at, (size_t) c * 8);
         std::memcpy(out_strand + to_at, strand[p] + from_at, (size_t) c);
+    });
+}
+
+int msb_merge_sites_compact(int32_t n_parts, int32_t n_motifs, const int64_t *counts, const uint32_t *const *pos_strand,
+                            const double *const *score, const int64_t *const *poff, const int64_t *n_seqs,
+                            const int32_t *const *seq_to_group, const int32_t *const *seq_offset, int32_t *out_group,
+                            int32_t *out_start, double *out_score, int8_t *out_strand, int32_t n_threads) {
+    if (n_parts < 0 || n_motifs < 0 || (n_parts > 0 && n_motifs > 0 && (!counts || !pos_strand || !score || !poff || !n_seqs))) {
+        set_error("msb_merge_sites_compact: bad argument");
+        return MSB_EINVAL;
+    }
+    if (n_parts == 0 || n_motifs == 0) return MSB_OK;
+    int64_t total = 0;
+    for (size_t i = 0; i < (size_t) n_parts * n_motifs; i++) total += counts[i];
+    if (total > 0 && (!out_group || !out_start || !out_score || !out_strand)) { set_error("msb_merge_sites_compact: null destination"); return MSB_EINVAL; }
+    return merge_plan_run(n_parts, n_motifs, counts, n_threads, 17, [&](int32_t p, int64_t from_at, int64_t to_at, int64_t c) {
+        const uint32_t *ps = pos_strand[p] + from_at;
+        const int64_t *po = poff[p];
+        const int64_t ns = n_seqs[p];
+        const int32_t *grp = seq_to_group ? seq_to_group[p] : nullptr, *off = seq_offset ? seq_offset[p] : nullptr;
+        int32_t *og = out_group + to_at, *os = out_start + to_at;
+        int8_t *od = out_strand + to_at;
+        int64_t q = 0;   // positions ascend within a (motif, part) slice: the previous site's sequence is the first guess
+        for (int64_t i = 0; i < c; i++) {
+            const int64_t pos = (int64_t) (ps[i] >> 1);
+            if (!(po[q] <= pos && pos < po[q + 1])) q = (int64_t) (std::upper_bound(po, po + ns, pos) - po) - 1;
+            og[i] = grp ? grp[q] : (int32_t) q;
+            os[i] = (int32_t) (pos - po[q]) + (off ? off[q] : 0);
+            od[i] = (int8_t) ((ps[i] & 1u) + 1);
+        }
+        std::memcpy(out_score + to_at, score[p] + from_at, (size_t) c * 8);
     });
 }
 

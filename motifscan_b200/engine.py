@@ -291,6 +291,17 @@ class ScanResult:
             return self.__dict__[name]
         raise AttributeError(name)
 
+    def compact(self):
+        """The raw arrays of a compact result (`compact=True` scans): (pos_strand uint32[n], score float64[n],
+        poff int64[n_seqs + 1]) -- see msb_result_compact -- or None when the result is an ordinary one."""
+        ps, sc, po = ctypes.POINTER(ctypes.c_uint32)(), _lib.c_f64p(), _lib.c_i64p()
+        ns = ctypes.c_int64(0)
+        check(self._lib.msb_result_compact(self._h, ctypes.byref(ps), ctypes.byref(sc), ctypes.byref(po), ctypes.byref(ns)))
+        if not ps or self.n_sites == 0:
+            return None
+        return (np.ctypeslib.as_array(ps, shape=(self.n_sites,)), np.ctypeslib.as_array(sc, shape=(self.n_sites,)),
+                np.ctypeslib.as_array(po, shape=(ns.value + 1,)))
+
     def detach(self):
         """Copy the arrays out of the pinned block and release it."""
         self.wait()
@@ -313,9 +324,9 @@ class ScanResult:
             pass
 
 
-def _flags(remove_dup=False, counts_only=False, async_=False):
+def _flags(remove_dup=False, counts_only=False, async_=False, compact=False):
     return ((_lib.MSB_SCAN_DEDUP if remove_dup else 0) | (_lib.MSB_SCAN_COUNTS if counts_only else 0)
-            | (_lib.MSB_SCAN_ASYNC if async_ else 0))
+            | (_lib.MSB_SCAN_ASYNC if async_ else 0) | (_lib.MSB_SCAN_COMPACT if compact else 0))
 
 
 def merge_motif_major(counts, arrays, add=None, n_threads=None):
@@ -340,12 +351,12 @@ def merge_motif_major(counts, arrays, add=None, n_threads=None):
     return out
 
 
-def scan(ctx, motifs, seqs, strand, remove_dup=False, async_=False):
+def scan(ctx, motifs, seqs, strand, remove_dup=False, async_=False, compact=False):
     """Scan; with remove_dup the reference's adjacent-site de-duplication (scanner.py:156-193)
     runs on the device before the sites are copied back.  `async_`: return while the copy of the
     sites is still in flight (the next scan on `ctx` overlaps it; `ScanResult.wait`)."""
     h = ctypes.c_void_p()
-    flags = _flags(remove_dup, async_=async_)
+    flags = _flags(remove_dup, async_=async_, compact=compact)
     with ctx._lock:
         check(ctx._lib.msb_scan_ex(ctx._h, motifs._h, seqs._h, int(strand), flags, ctypes.byref(h)))
     return ScanResult(ctx, h, motifs.n)
@@ -392,6 +403,35 @@ def merge_sites(counts, seq_idx, start, score, strand, seq_to_group=None, seq_of
     return out
 
 
+def merge_sites_compact(counts, results, seq_to_group=None, seq_offset=None, n_threads=None):
+    """`merge_sites` straight from compact results (`ScanResult.compact()` of every part): the owning sequence
+    of a site is found while it is copied."""
+    import os
+    counts = np.ascontiguousarray(np.asarray(counts, dtype=np.int64))
+    n_parts, n_motifs = counts.shape
+    total = int(counts.sum())
+    out = (np.empty(total, np.int32), np.empty(total, np.int32), np.empty(total, np.float64), np.empty(total, np.int8))
+    if n_parts == 0 or total == 0:
+        return out
+    raw = [r.compact() for r in results]
+
+    def table(arrays, dtype):
+        if arrays is None:
+            return None, None
+        keep = [np.ascontiguousarray(a, dtype=dtype) for a in arrays]
+        return keep, (ctypes.c_void_p * n_parts)(*[ctypes.c_void_p(a.ctypes.data if a.size else 0) for a in keep])
+    empty = (np.zeros(1, np.uint32), np.zeros(1, np.float64), np.zeros(2, np.int64))
+    raw = [x if x is not None else empty for x in raw]
+    keep = [table([x[0] for x in raw], np.uint32), table([x[1] for x in raw], np.float64), table([x[2] for x in raw], np.int64),
+            table(seq_to_group, np.int32), table(seq_offset, np.int32)]
+    n_seqs = np.array([len(x[2]) - 1 for x in raw], dtype=np.int64)
+    check(_lib.load().msb_merge_sites_compact(n_parts, n_motifs, ptr(counts, ctypes.c_int64), keep[0][1], keep[1][1], keep[2][1],
+                                              ptr(n_seqs, ctypes.c_int64), keep[3][1], keep[4][1],
+                                              *[ctypes.c_void_p(o.ctypes.data) for o in out],
+                                              int(n_threads or min(os.cpu_count() or 1, 16))))
+    return out
+
+
 class PinnedArray:
     """A uint8 numpy view of page-locked host memory (msb_pinned_alloc); `.array` is the view."""
 
@@ -428,14 +468,14 @@ def _ranges(ranges):
     return (len(r), np.ascontiguousarray(r[:, 0]), np.ascontiguousarray(r[:, 1]), np.ascontiguousarray(r[:, 2]))
 
 
-def scan_ranges(ctx, motifs, seqs, strand, ranges, async_=False):
+def scan_ranges(ctx, motifs, seqs, strand, ranges, async_=False, compact=False):
     """Scan only the windows that start in the given (sequence index, start, end) ranges of a
     resident sequence set; sites refer to the sequences of `seqs` (msb_scan_ranges).  There is no
     de-duplication here: it is defined over a whole region's site list (scanner.py:171-193), not
     across range boundaries."""
     n, a, b, c = _ranges(ranges)
     h = ctypes.c_void_p()
-    flags = _flags(False, async_=async_)
+    flags = _flags(False, async_=async_, compact=compact)
     with ctx._lock:
         check(ctx._lib.msb_scan_ranges(ctx._h, motifs._h, seqs._h, int(strand), flags, n, ptr(a, ctypes.c_int64),
                                        ptr(b, ctypes.c_int64), ptr(c, ctypes.c_int64), ctypes.byref(h)))

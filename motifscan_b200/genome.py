@@ -244,6 +244,19 @@ class PackedGenome:
             raise AttributeError(name)
         return getattr(g, name)
 
+    def work_prefix(self):
+        """Cumulative per-block scan cost (B + 1 entries): the number of A/C/G/T bases of a block plus a small
+        constant -- windows inside N runs are dropped by whole position tiles, so the non-N bases are what a
+        share costs.  `genome_scan.plan_units` cuts shares at equal increments of it."""
+        w = self.__dict__.get("_work_prefix")
+        if w is None:
+            acgt = 32 - np.bitwise_count(np.asarray(self.nmask)).astype(np.int64)
+            # the last block of a chromosome holds fewer than 32 bases; the constant stands for the per-tile overhead
+            w = np.zeros(self.n_blocks + 1, dtype=np.int64)
+            np.cumsum(acgt + 1, out=w[1:])
+            self.__dict__["_work_prefix"] = w
+        return w
+
     def planes(self, block0, block1):
         """Views of the planes of blocks [block0, block1) (no copy: they go to the device as they are)."""
         return self.codes[2 * block0:2 * block1], self.nmask[block0:block1]

@@ -169,16 +169,29 @@ class Unit:
         return sum(b - a for _, a, b, _ in self.pieces)
 
 
-def plan_units(block_off, chrom_sizes, n_shares, unit_blocks, halo_bases):
+def plan_units(block_off, chrom_sizes, n_shares, unit_blocks, halo_bases, work_prefix=None):
     """Cut the packed block space [0, B) into `n_shares` contiguous shares of (almost) equal size and every
     share into units of at most `unit_blocks` blocks.  Returns a list (per share) of lists of `Unit`.
     Every base of every chromosome is owned by exactly one unit; share and unit boundaries are multiples
-    of 32 bases inside a chromosome, so a unit's planes are a plain slice of the genome's."""
+    of 32 bases inside a chromosome, so a unit's planes are a plain slice of the genome's.
+
+    `work_prefix` (B + 1 cumulative per-block weights, e.g. `PackedGenome.work_prefix()`): shares are cut at
+    equal WORK instead of equal size -- position tiles that hold nothing but N cost the device nothing, and
+    assembly gaps are not spread evenly over a genome."""
     n_blocks = int(block_off[-1])
     halo = (max(int(halo_bases), 0) + 31) // 32
+    if work_prefix is not None and n_blocks:
+        total = float(work_prefix[-1])
+        cuts = [int(np.searchsorted(work_prefix, total * k / n_shares, side="left")) for k in range(n_shares + 1)]
+        cuts[0], cuts[-1] = 0, n_blocks
+        cuts = [min(max(c, 0), n_blocks) for c in cuts]
+        for k in range(1, len(cuts)):
+            cuts[k] = max(cuts[k], cuts[k - 1])
+    else:
+        cuts = [n_blocks * k // n_shares for k in range(n_shares + 1)]
     shares = []
     for k in range(n_shares):
-        s0, s1 = n_blocks * k // n_shares, n_blocks * (k + 1) // n_shares
+        s0, s1 = cuts[k], cuts[k + 1]
         n_units = max(1, -(-(s1 - s0) // max(int(unit_blocks), 1)))
         units = []
         for u in range(n_units):
@@ -225,9 +238,13 @@ class ShardedSites(GenomeSites):
             self.score, self.strand = np.zeros(0, np.float64), np.zeros(0, np.int8)
         else:
             cnt = np.stack([p[0].counts for p in parts])
-            self.chrom_idx, self.start, self.score, self.strand = engine.merge_sites(
-                cnt, [p[0].seq_idx for p in parts], [p[0].start for p in parts], [p[0].score for p in parts],
-                [p[0].strand for p in parts], seq_to_group=[p[1] for p in parts], seq_offset=[p[2] for p in parts])
+            if all(p[0].compact() is not None for p in parts):      # 12-byte sites: decoded while they are gathered
+                self.chrom_idx, self.start, self.score, self.strand = engine.merge_sites_compact(
+                    cnt, [p[0] for p in parts], seq_to_group=[p[1] for p in parts], seq_offset=[p[2] for p in parts])
+            else:
+                self.chrom_idx, self.start, self.score, self.strand = engine.merge_sites(
+                    cnt, [p[0].seq_idx for p in parts], [p[0].start for p in parts], [p[0].score for p in parts],
+                    [p[0].strand for p in parts], seq_to_group=[p[1] for p in parts], seq_offset=[p[2] for p in parts])
         for p in self._parts:
             p[0].close()
         self._parts = []
@@ -256,7 +273,7 @@ class GenomeScanner:
     thread pool over motifs, cscore.c:323-328, 425-436)."""
 
     def __init__(self, pg, pwms, cutoffs=None, p_value="1e-4", strand="both", devices=None, world=1, rank=0,
-                 unit_bp=1 << 26, resident=False, contexts=None):
+                 unit_bp=1 << 26, resident=False, contexts=None, compact=True):
         self.pg = pg
         self.matrices = [getattr(pwm, "matrix", pwm) for pwm in pwms]
         if cutoffs is None:
@@ -269,12 +286,15 @@ class GenomeScanner:
         self.world, self.rank = int(world), int(rank)
         lmax = max([np.asarray(m).shape[1] for m in self.matrices] + [1])
         sizes = [pg.chrom_sizes[c] for c in pg.chroms]
-        shares = plan_units(pg.block_off, sizes, self.world * len(self.devices), max(int(unit_bp) // 32, 1), lmax - 1)
+        n_shares = self.world * len(self.devices)
+        work = pg.work_prefix() if n_shares > 1 and hasattr(pg, "work_prefix") else None
+        shares = plan_units(pg.block_off, sizes, n_shares, max(int(unit_bp) // 32, 1), lmax - 1, work_prefix=work)
         self.shares = shares[self.rank * len(self.devices):(self.rank + 1) * len(self.devices)]
         self.ctxs = list(contexts) if contexts is not None else [engine.default_context(d) for d in self.devices]
         self.motifs = [engine.MotifSet(ctx, self.matrices, self.cutoffs) for ctx in self.ctxs]
         self.resident = [None] * len(self.devices)     # per device: the uploaded units, kept between scans
         self.keep_resident = bool(resident)
+        self.compact = bool(compact)          # 12-byte site records over PCIe (MSB_SCAN_COMPACT)
         self.last_stats = None
 
     def _upload(self, ctx, unit, async_):
@@ -302,7 +322,7 @@ class GenomeScanner:
                 ranges = [(j, 0, b - a) for j, (_, a, b, _) in enumerate(unit.pieces)]
                 with ctx._lock:   # the counts / timings read below belong to THIS scan even if the context is shared
                     if collect_sites:
-                        res = engine.scan_ranges(ctx, motifs, sset, self.strand, ranges, async_=True)
+                        res = engine.scan_ranges(ctx, motifs, sset, self.strand, ranges, async_=True, compact=self.compact)
                         parts.append((res, np.array([p[0] for p in unit.pieces]), np.array([p[1] for p in unit.pieces])))
                     else:
                         engine.scan_ranges_device(ctx, motifs, sset, self.strand, ranges, counts_only=not order_sites)

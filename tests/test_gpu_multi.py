@@ -90,8 +90,22 @@ def test_counts_only_and_async_scans():
     for res, (_, _, expect) in reversed(list(zip(results, jobs))):
         assert_scan_equal(res, expect)
         res.close()
-    # de-duplication + async
+    # compact site records (12 bytes over PCIe): decoded on the host to the same arrays; raw form = position << 1 | strand
+    for (seqs, cutoffs, expect), sset in zip(jobs[:2], ssets[:2]):
+        motifs.set_cutoffs(cutoffs)
+        res = engine.scan(ctx, motifs, sset, 3, async_=True, compact=True)
+        ps, sc, poff = res.compact()
+        assert len(poff) == len(seqs) + 1 and np.array_equal(sc.view(np.uint64), expect[3].view(np.uint64))
+        owner = np.searchsorted(poff, ps >> 1, side="right") - 1
+        assert np.array_equal(owner, expect[1]) and np.array_equal((ps >> 1) - poff[owner], expect[2])
+        assert np.array_equal((ps & 1) + 1, expect[4])
+        assert_scan_equal(res, expect)
+        res.close()
+    # de-duplication + async (+ compact, which de-duplication overrides)
     motifs.set_cutoffs(jobs[0][1])
+    c = engine.scan(ctx, motifs, ssets[0], 3, remove_dup=True, compact=True)
+    assert c.compact() is None
+    c.close()
     a = engine.scan(ctx, motifs, ssets[0], 3, remove_dup=True, async_=True)
     b = engine.scan(ctx, motifs, ssets[0], 3, remove_dup=True)
     assert np.array_equal(a.start, b.start) and np.array_equal(a.seq_idx, b.seq_idx) and a.n_sites < jobs[0][2][0].sum()
@@ -129,7 +143,7 @@ def test_sharded_genome_scan_equals_reference(toy, unit_bp):
     for devices in device_lists():
         if unit_bp == 64 and len(devices) > 1:
             continue
-        gs = GenomeScanner(pg, pwms, cutoffs=cutoffs, devices=devices, unit_bp=unit_bp)
+        gs = GenomeScanner(pg, pwms, cutoffs=cutoffs, devices=devices, unit_bp=unit_bp, compact=(unit_bp != 50000))
         try:
             sites = gs.scan()
             assert_genome_equal(sites, expect)

@@ -61,6 +61,27 @@ def test_plan_units_partitions_hg19():
             assert all(spans[i][1] == spans[i + 1][0] for i in range(len(spans) - 1))
 
 
+def test_plan_units_balanced_by_work():
+    """Shares cut at equal work (non-N bases) still own every base exactly once, and even out the work."""
+    from motifscan_b200 import synth
+    from motifscan_b200.genome_scan import plan_units
+    pg = synth.packed_genome([200000, 120000, 50000, 90000, 40], seed=4)
+    sizes = [pg.chrom_sizes[c] for c in pg.chroms]
+    w = pg.work_prefix()
+    acgt = sum(sizes) - sum(pg.decode_bytes(c, 0, 1 << 40).count(b"N") for c in pg.chroms)
+    assert 0 <= w[-1] - (acgt + pg.n_blocks) < 32 * len(sizes)     # the padding behind a chromosome's last base counts as bases
+    for n in (1, 2, 3, 8):
+        shares = plan_units(pg.block_off, sizes, n, 500, 29, work_prefix=w)
+        assert sum(u.owned_bp for units in shares for u in units) == sum(sizes)
+        flat = [u for units in shares for u in units]
+        assert flat[0].block0 == 0 and flat[-1].block1 == pg.n_blocks
+        assert all(a.block1 == b.block0 for a, b in zip(flat, flat[1:]))
+        work = np.array([sum(w[u.block1] - w[u.block0] for u in units) for units in shares], dtype=float)
+        by_size = plan_units(pg.block_off, sizes, n, 500, 29)
+        work_by_size = np.array([sum(w[u.block1] - w[u.block0] for u in units) for units in by_size], dtype=float)
+        assert work.max() / work.mean() < 1.002 and work.max() <= work_by_size.max() + 1
+
+
 def test_packed_layout_restatement_and_decode():
     from motifscan_b200 import synth
     import oracle
