@@ -258,6 +258,9 @@ class ScanResult:
         self._loaded = False
 
     def wait(self):
+        """Block until the copies have landed; `counts` / `offsets` are valid afterwards.  The site arrays are
+        bound on first use (`seq_idx`, `start`, `score`, `strand`): for a compact result that first use
+        decodes the positions on the host, which a caller that gathers with `merge_sites_compact` never pays."""
         if self._loaded:
             return self
         n_motifs = self.n_motifs
@@ -266,6 +269,11 @@ class ScanResult:
         self.counts = counts[:n_motifs]
         self.offsets = np.zeros(n_motifs + 1, dtype=np.int64)
         np.cumsum(self.counts, out=self.offsets[1:])
+        self._loaded = True
+        return self
+
+    def _bind_arrays(self):
+        self.wait()
         p_seq, p_start = _lib.c_i32p(), _lib.c_i32p()
         p_score, p_strand = _lib.c_f64p(), _lib.c_i8p()
         check(self._lib.msb_result_arrays(self._h, ctypes.byref(p_seq), ctypes.byref(p_start),
@@ -281,13 +289,13 @@ class ScanResult:
             self.start = np.zeros(0, dtype=np.int32)
             self.score = np.zeros(0, dtype=np.float64)
             self.strand = np.zeros(0, dtype=np.int8)
-        self._loaded = True
-        return self
 
     def __getattr__(self, name):
-        # counts / offsets / seq_idx / start / score / strand exist once the copies have landed
-        if name in ("counts", "offsets", "seq_idx", "start", "score", "strand") and not self.__dict__.get("_loaded", True):
+        if name in ("counts", "offsets") and not self.__dict__.get("_loaded", True):
             self.wait()
+            return self.__dict__[name]
+        if name in ("seq_idx", "start", "score", "strand") and "_h" in self.__dict__ and "seq_idx" not in self.__dict__:
+            self._bind_arrays()
             return self.__dict__[name]
         raise AttributeError(name)
 
