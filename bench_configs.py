@@ -288,7 +288,7 @@ def bench_enrich(args):
     from motifscan_b200.scanner import MotifSites
     from motifscan_b200.stats import enrichment_from_counts
     ctx = engine.default_context(0)
-    _, pwms, ids = synth.motif_set(args.motifs, seed=2020)
+    _, pwms, ids = synth.motif_set(args.motifs, seed=2020, n_long=20)     # 20 motifs of 33-40 columns: longer than the prefilter's 32
     motifs = engine.MotifSet(ctx, pwms)
     lmax = max(p.shape[1] for p in pwms)
     bblob, boff = synth.background_samples(100000, lmax, seed=1)
@@ -351,9 +351,114 @@ def bench_enrich(args):
             "parity": {"regions_with_site_counts_identical_on_sample": bool(np.array_equal(got, want))}}
 
 
+def bench_cli(args):
+    """configs[4] through the command line: `python -m motifscan_b200 scan` on 200k target + 200k control 1 kb regions x
+    1,900 motifs (20 of them 33-40 columns long), a synthetic genome directory with a packed-genome cache next to
+    the FASTA; wall time and peak RSS of the whole process (region parsing, scans, both site tables -- 1,900 columns
+    x 200,000 rows each -- and the enrichment table).  The first `--cpu-regions` rows of the tables are compared with
+    the reference pipeline (its extension on the CPU, its regrouping, de-duplication and writers restated)."""
+    import resource
+    import shutil
+    import subprocess
+    import tempfile
+    import oracle
+    import bench
+    from motifscan_b200 import engine, synth
+    from motifscan_b200 import io as msio
+    from motifscan_b200.motif import MotifPwms, PositionWeightMatrix
+    from motifscan_b200.scanner import MotifSite
+    root = tempfile.mkdtemp(prefix="msb_cli_")
+    gdir, mdir = os.path.join(root, "synth"), os.path.join(root, "jaspar_all")
+    os.makedirs(gdir), os.makedirs(mdir)
+    t0 = time.perf_counter()
+    pg = bench.make_genome(0, args.genome_scale)
+    with open(os.path.join(gdir, "synth.fa"), "wb") as fh:          # one line per chromosome
+        for c in pg.chroms:
+            fh.write(f">{c}\n".encode())
+            fh.write(pg.decode_bytes(c, 0, pg.chrom_sizes[c]))
+            fh.write(b"\n")
+    pg.save(os.path.join(gdir, "synth.packed"))
+    with open(os.path.join(gdir, "synth_bg_freq.txt"), "w") as fh:
+        fh.write("Base\tFrequency\n" + "".join(f"{b}\t{v}\n" for b, v in synth.BG.items()))
+    _, mats, ids = synth.motif_set(args.motifs, seed=2020, n_long=20)
+    ctx = engine.default_context(0)
+    mset = engine.MotifSet(ctx, mats)
+    bblob, boff = synth.background_samples(100000, 40, seed=1)
+    bg = engine.SequenceSet(ctx, blob=bblob, seq_off=boff)
+    cutoffs = np.maximum(np.around(engine.score_select(ctx, mset, bg, 3, [int(100000 * 1e-4) - 1])[:, 0], 8), 1e-6)
+    bg.close(), mset.close()
+    pwms = MotifPwms(name="jaspar_all", genome="synth")
+    for m, k, c in zip(mats, ids, cutoffs):
+        pwms.append(PositionWeightMatrix(m, name="TF" + k[2:6], matrix_id=k, cutoffs={"1e-4": float(c)}))
+    pwms.write_motifscan_pwms(os.path.join(mdir, "jaspar_all_synth_pwms.motifscan"))
+    rng = np.random.default_rng(77)
+    big = [c for c in pg.chroms if pg.chrom_sizes[c] > 20000]
+    sizes = np.array([pg.chrom_sizes[c] for c in big], dtype=np.float64)
+    for name in ("targets.bed", "controls.bed"):
+        ci = rng.choice(len(big), size=args.regions, p=sizes / sizes.sum())
+        st = (rng.random(args.regions) * (sizes[ci] - 2000)).astype(np.int64)
+        with open(os.path.join(root, name), "w") as fh:
+            for i in range(args.regions):
+                fh.write(f"{big[ci[i]]}\t{st[i]}\t{st[i] + 1000}\tr{i}\t{1 + i % 50}\n")
+    setup_s = time.perf_counter() - t0
+    out = os.path.join(root, "out")
+    cmd = [sys.executable, "-m", "motifscan_b200", "scan", "-i", os.path.join(root, "targets.bed"), "-c", os.path.join(root, "controls.bed"),
+           "-m", mdir, "-g", gdir, "-o", out, "-w", "0", "-p", "1e-4", "--gpus", str(args.gpus)]
+    runs = []
+    for _ in range(2):
+        shutil.rmtree(out, ignore_errors=True)
+        before = resource.getrusage(resource.RUSAGE_CHILDREN).ru_maxrss
+        t0 = time.perf_counter()
+        proc = subprocess.run(cmd, cwd=ROOT, capture_output=True, text=True)
+        dt = time.perf_counter() - t0
+        if proc.returncode != 0:
+            raise SystemExit("motifscan scan failed:\n" + proc.stderr[-2000:])
+        runs.append((dt, max(resource.getrusage(resource.RUSAGE_CHILDREN).ru_maxrss, before) / 1024.0))
+    wall_s, rss_mb = min(r[0] for r in runs), runs[-1][1]
+    # parity sample: the first rows of the two tables vs the reference pipeline
+    n = args.cpu_regions
+    kind, ext = cpu_ext()
+    regions = []
+    with open(os.path.join(root, "targets.bed")) as fh:
+        for line in fh:
+            f = line.split("\t")
+            regions.append((f[0], int(f[1]), int(f[2])))
+            if len(regions) == n:
+                break
+    seqs = [pg.decode_bytes(c, a, b).decode() for c, a, b in regions]
+    t0 = time.perf_counter()
+    raw = ext.c_scan_motif([m.tolist() for m in mats], cutoffs.tolist(), seqs, 3, os.cpu_count() or 1)
+    cpu_s = time.perf_counter() - t0
+    nested = oracle.deduplicate_motif_sites(oracle.make_motif_sites(raw, [a for _, a, _ in regions]), [m.shape[1] for m in mats])
+    nested = [[[MotifSite(*s) for s in cell] for cell in per] for per in nested]
+
+    class Region:
+        def __init__(self, c, a, b):
+            self.chrom, self.start, self.end = c, a, b
+    ref_dir = os.path.join(root, "ref")
+    msio.write_sites_table(ref_dir, pwms, [Region(*r) for r in regions], nested)
+    same = True
+    for name in ("motif_sites_number.xls", "motif_sites_score.xls"):
+        with open(os.path.join(ref_dir, name)) as a, open(os.path.join(out, name)) as b:
+            for _ in range(n + 1):
+                same = same and a.readline() == b.readline()
+    sizes_out = {name: os.path.getsize(os.path.join(out, name)) for name in sorted(os.listdir(out))}
+    shutil.rmtree(root, ignore_errors=True)
+    return {"config": f"configs[4] through the CLI: motifscan scan, {args.regions} target + {args.regions} control 1 kb regions x {args.motifs} motifs "
+                      f"(20 of 33-40 columns), genome {sum(pg.chrom_sizes.values())} bp with a packed cache, --gpus {args.gpus}",
+            "metric": "wall seconds of the whole command (parse, scan, 2 site tables, enrichment table)", "wall_s": wall_s,
+            "runs_s": [r[0] for r in runs], "peak_rss_mb": rss_mb, "output_bytes": sizes_out, "setup_s": setup_s,
+            "value": args.motifs * 2 * args.regions * 1000 / wall_s,
+            "cpu_baseline": {"kind": kind, "cores": os.cpu_count(), "sample": f"{n} regions x all motifs (extension call only)",
+                             "value": args.motifs * n * 1000 / cpu_s, "seconds": cpu_s},
+            "parity": {f"first_{n}_rows_of_both_site_tables_identical_to_the_reference_pipeline": bool(same)}}
+
+
 def main():
     ap = argparse.ArgumentParser()
-    ap.add_argument("which", choices=["build", "genome", "enrich"])
+    ap.add_argument("which", choices=["build", "genome", "enrich", "cli"])
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--genome-scale", dest="genome_scale", type=float, default=0.1)
     ap.add_argument("--steps", type=int, default=2)
     ap.add_argument("--motifs", type=int, default=None)
     ap.add_argument("--n-random", dest="n_random", type=int, default=1000000)
@@ -367,8 +472,8 @@ def main():
     ap.add_argument("--cpu-regions", dest="cpu_regions", type=int, default=4000)
     args = ap.parse_args()
     if args.motifs is None:
-        args.motifs = 1900 if args.which == "enrich" else 750
-    out = {"build": bench_build, "genome": bench_genome, "enrich": bench_enrich}[args.which](args)
+        args.motifs = 1900 if args.which in ("enrich", "cli") else 750
+    out = {"build": bench_build, "genome": bench_genome, "enrich": bench_enrich, "cli": bench_cli}[args.which](args)
     if out is not None:
         print(json.dumps(out))
 

@@ -235,6 +235,17 @@ int msb_merge_sites_compact(int32_t n_parts, int32_t n_motifs, const int64_t *co
                             const int32_t *const *seq_to_group, const int32_t *const *seq_offset, int32_t *out_group,
                             int32_t *out_start, double *out_score, int8_t *out_strand, int32_t n_threads);
 
+/* ---- result tables (host code; the reference builds them from nested lists, io/__init__.py:12-38) ------- */
+/* Rows [r0, r1) of motif_sites_number.xls and motif_sites_score.xls as text, from a scan's motif-major arrays
+ * (offsets: CSR over motifs; seq_idx ascending within a motif): row r = lead[lead_off[r - r0] .. lead_off[r - r0 + 1])
+ * (the caller's "chr<TAB>start<TAB>end<TAB>") followed by one tab-separated cell per motif -- the number of sites
+ * of the region, resp. the best score (`NA` without a site; doubles printed like Python's str()) -- and "\n".
+ * The two buffers are malloc'ed; release them with msb_text_free.  Up to n_threads host threads. */
+int msb_format_site_tables(int32_t n_motifs, const int64_t *offsets, const int32_t *seq_idx, const double *score,
+                           int64_t r0, int64_t r1, const char *lead, const int64_t *lead_off, char **num_text,
+                           int64_t *num_len, char **score_text, int64_t *score_len, int32_t n_threads);
+int msb_text_free(char *text);
+
 /* ---- score (replaces motif_score_thread + motif_score, cscore.c:174-302) -------------------- */
 /* out is n_motifs x n_seqs row-major: the offset-0 window score of every sequence. */
 int msb_score(msb_ctx *ctx, const msb_motifs *motifs, const msb_seqs *seqs, int strand,

@@ -78,6 +78,9 @@ SIGNATURES = {
                                 [ctypes.POINTER(c_vp)] * 2 + [c_vp, c_vp, c_vp, c_vp, ctypes.c_int32]),
     "msb_result_compact": (ctypes.c_int, [c_vp, ctypes.POINTER(ctypes.POINTER(ctypes.c_uint32)), ctypes.POINTER(c_f64p),
                                           ctypes.POINTER(c_i64p), c_i64p]),
+    "msb_format_site_tables": (ctypes.c_int, [ctypes.c_int32, c_i64p, c_i32p, c_f64p, ctypes.c_int64, ctypes.c_int64, ctypes.c_char_p,
+                                              c_i64p, ctypes.POINTER(c_vp), c_i64p, ctypes.POINTER(c_vp), c_i64p, ctypes.c_int32]),
+    "msb_text_free": (ctypes.c_int, [c_vp]),
     "msb_result_total": (ctypes.c_int, [c_vp, c_i64p]),
     "msb_result_counts": (ctypes.c_int, [c_vp, c_i64p]),
     "msb_result_arrays": (ctypes.c_int, [c_vp, ctypes.POINTER(c_i32p), ctypes.POINTER(c_i32p),

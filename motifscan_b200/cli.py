@@ -49,6 +49,37 @@ def load_genome(name):
     return Genome(short, path=path)
 
 
+PACKED_MIN_BP = 1 << 26    # scans of at least this many window bases go through the packed, device-resident genome
+
+
+def packed_genome(genome, window_bp, device=0):
+    """The genome's packed planes (`genome.PackedGenome`, 0.375 B/bp) for a scan of `window_bp` bases, or None to
+    fetch region strings from the FASTA as the reference does (scanner.py:76-87).  A cache written next to the
+    FASTA (`<name>.packed.*`, like the `.fai`) is always used; without one the genome is encoded on the GPU and
+    the cache written when the scan is large enough to pay for it (one pass over the FASTA)."""
+    from . import engine
+    from .genome import PackedGenome
+    prefix = os.path.join(genome.path, f"{genome.name}.packed") if genome.path else None
+    if prefix and os.path.isfile(prefix + ".chroms.tsv"):
+        try:
+            pg = PackedGenome.load(prefix, genome=genome)
+            if pg.chrom_sizes == genome.chrom_sizes:
+                return pg
+            logger.warning("packed genome cache does not match the FASTA index: ignored")
+        except (OSError, ValueError) as err:
+            logger.warning(f"packed genome cache unreadable ({err}): ignored")
+    if window_bp < PACKED_MIN_BP:
+        return None
+    logger.info("Packing the genome (2 bits per base + N mask) on the device")
+    pg = PackedGenome.from_genome(genome, engine.default_context(device))
+    if prefix:
+        try:
+            pg.save(prefix)
+        except OSError:
+            pass
+    return pg
+
+
 def pwms_path(motif_dir, name, genome_name):
     return os.path.join(motif_dir, f"{name}_{genome_name}_pwms.motifscan")   # motif/__init__.py:22
 
@@ -75,7 +106,9 @@ def run_scan(args):
     regions = load_motifscan_regions(args.input_file, args.input_format)
     logger.info("===== Scanning motifs =====")
     devices = _devices(args.n_gpus)
-    common = dict(genome=genome, window_size=args.window_size, strand=args.strand, p_value=args.p_value,
+    window_bp = sum((args.window_size if args.window_size > 0 else r.end - r.start) for r in regions)
+    source = packed_genome(genome, window_bp * (1 if args.no_enrich else 2), devices[0]) or genome
+    common = dict(genome=source, window_size=args.window_size, strand=args.strand, p_value=args.p_value,
                   remove_dup=True, n_threads=args.n_threads, devices=devices)
     sites = Scanner(regions=regions, **common).scan_motifs(pwms)
     logger.info("Saving the result tables")

@@ -18,6 +18,7 @@
 #include <mutex>
 #include <new>
 #include <numeric>
+#include <charconv>
 #include <thread>
 
 #include "kernels.cuh"
@@ -2087,6 +2088,183 @@ int msb_merge_sites_compact(int32_t n_parts, int32_t n_motifs, const int64_t *co
         }
         std::memcpy(out_score + to_at, score[p] + from_at, (size_t) c * 8);
     });
+}
+
+}  // extern "C"
+
+// ---- result tables ------------------------------------------------------------------------------
+// `motifscan scan` writes one row per region and one column per motif twice (site counts, best scores:
+// io/__init__.py:12-38).  At 200,000 regions x 1,900 motifs that is 3.8e8 cells per table: the reference
+// builds them from nested Python lists.  Here a block of rows is filled straight from the scan's
+// motif-major arrays and formatted to text on host threads; numbers look exactly like Python's str().
+namespace msb {
+
+// str(float) of CPython (repr, shortest digits that round-trip; float_repr_style 'short'): fixed notation
+// while -4 < decimal point position <= 16, else d.ddde+XX; always a ".0" on integral values in fixed form.
+static int py_float_str(double v, char *out) {
+    if (std::isnan(v)) { std::memcpy(out, "nan", 3); return 3; }
+    if (std::isinf(v)) { const char *t = v < 0 ? "-inf" : "inf"; const int n = (int) std::strlen(t); std::memcpy(out, t, n); return n; }
+    char buf[48];
+    const auto res = std::to_chars(buf, buf + sizeof(buf), v, std::chars_format::scientific);
+    const char *p = buf, *end = res.ptr;
+    char *o = out;
+    if (*p == '-') { *o++ = '-'; p++; }
+    char digits[32];
+    int nd = 0;
+    while (p < end && *p != 'e') { if (*p != '.') digits[nd++] = *p; p++; }
+    int e10 = 0;
+    if (p < end) { p++; const bool neg = *p == '-'; if (*p == '+' || *p == '-') p++; while (p < end) e10 = e10 * 10 + (*p++ - '0'); if (neg) e10 = -e10; }
+    while (nd > 1 && digits[nd - 1] == '0') nd--;          // to_chars never pads, but be safe
+    const int decpt = e10 + 1;                              // value = 0.d1d2... x 10^decpt
+    if (v == 0) { std::memcpy(o, "0.0", 3); return (int) (o - out) + 3; }
+    if (decpt <= -4 || decpt > 16) {
+        *o++ = digits[0];
+        if (nd > 1) { *o++ = '.'; std::memcpy(o, digits + 1, nd - 1); o += nd - 1; }
+        *o++ = 'e';
+        *o++ = e10 < 0 ? '-' : '+';
+        const int a = e10 < 0 ? -e10 : e10;
+        if (a >= 100) *o++ = (char) ('0' + a / 100);
+        *o++ = (char) ('0' + (a / 10) % 10);
+        *o++ = (char) ('0' + a % 10);
+    } else if (decpt <= 0) {
+        *o++ = '0'; *o++ = '.';
+        for (int i = 0; i < -decpt; i++) *o++ = '0';
+        std::memcpy(o, digits, nd); o += nd;
+    } else if (decpt >= nd) {
+        std::memcpy(o, digits, nd); o += nd;
+        for (int i = nd; i < decpt; i++) *o++ = '0';
+        *o++ = '.'; *o++ = '0';
+    } else {
+        std::memcpy(o, digits, decpt); o += decpt;
+        *o++ = '.';
+        std::memcpy(o, digits + decpt, nd - decpt); o += nd - decpt;
+    }
+    return (int) (o - out);
+}
+
+static inline int fmt_int(int64_t v, char *out) {
+    char tmp[24];
+    int n = 0;
+    uint64_t a = v < 0 ? (uint64_t) (-v) : (uint64_t) v;
+    do { tmp[n++] = (char) ('0' + a % 10); a /= 10; } while (a);
+    int k = 0;
+    if (v < 0) out[k++] = '-';
+    while (n) out[k++] = tmp[--n];
+    return k;
+}
+
+}  // namespace msb
+
+extern "C" {
+
+int msb_format_site_tables(int32_t n_motifs, const int64_t *offsets, const int32_t *seq_idx, const double *score,
+                           int64_t r0, int64_t r1, const char *lead, const int64_t *lead_off, char **num_text,
+                           int64_t *num_len, char **score_text, int64_t *score_len, int32_t n_threads) {
+    if (n_motifs < 0 || r1 < r0 || !offsets || !lead_off || !num_text || !num_len || !score_text || !score_len ||
+        (offsets[n_motifs] > 0 && (!seq_idx || !score))) {
+        set_error("msb_format_site_tables: bad argument");
+        return MSB_EINVAL;
+    }
+    *num_text = *score_text = nullptr;
+    *num_len = *score_len = 0;
+    const int64_t n_rows = r1 - r0;
+    if (n_rows == 0) return MSB_OK;
+    const size_t cells = (size_t) n_rows * (size_t) n_motifs;
+    std::vector<int32_t> counts;
+    std::vector<double> best;
+    try { counts.assign(cells, 0); best.assign(cells, -std::numeric_limits<double>::infinity()); }
+    catch (const std::bad_alloc &) { set_error("out of host memory"); return MSB_ENOMEM; }
+    const int nt = std::max(1, std::min<int>(n_threads, 64));
+    // 1. the block's cells: a motif's sites are sorted by region, so its part of [r0, r1) is one slice.  A thread
+    //    owns a contiguous range of motifs (= a contiguous run of cells in every row: no cache line ping-pong).
+    auto fill = [&](int t) {
+        for (int32_t m = (int32_t) ((int64_t) n_motifs * t / nt); m < (int32_t) ((int64_t) n_motifs * (t + 1) / nt); m++) {
+            const int32_t *a = seq_idx + offsets[m], *b = seq_idx + offsets[m + 1];
+            const int32_t *lo = std::lower_bound(a, b, (int32_t) r0), *hi = std::lower_bound(lo, b, (int32_t) std::min<int64_t>(r1, 0x7fffffff));
+            for (const int32_t *q = lo; q < hi; q++) {
+                const size_t cell = (size_t) (*q - r0) * n_motifs + m;
+                counts[cell]++;
+                const double sc = score[q - seq_idx];
+                if (counts[cell] == 1 || sc > best[cell]) best[cell] = sc;   // max() keeps the first of equal scores
+            }
+        }
+    };
+    // 2. rows -> text, a contiguous range of rows per thread, written with a bump pointer into a buffer sized for
+    //    the worst case (a count has at most 11 characters, a double at most 24)
+    struct Part { char *num = nullptr, *score = nullptr; size_t n_num = 0, n_score = 0; };
+    std::vector<Part> parts((size_t) nt);
+    bool oom = false;
+    auto format = [&](int t) {
+        const int64_t a = n_rows * t / nt, b = n_rows * (t + 1) / nt;
+        if (b <= a) return;
+        const size_t lead_bytes = (size_t) (lead_off[b] - lead_off[a]);
+        Part &P = parts[t];
+        P.num = (char *) std::malloc(lead_bytes + (size_t) (b - a) * ((size_t) n_motifs * 12 + 2));
+        P.score = (char *) std::malloc(lead_bytes + (size_t) (b - a) * ((size_t) n_motifs * 26 + 2));
+        if (!P.num || !P.score) { oom = true; return; }
+        char *pn = P.num, *ps = P.score;
+        for (int64_t r = a; r < b; r++) {
+            const char *l = lead + lead_off[r];
+            const size_t ln = (size_t) (lead_off[r + 1] - lead_off[r]);
+            std::memcpy(pn, l, ln); pn += ln;
+            std::memcpy(ps, l, ln); ps += ln;
+            const int32_t *c = counts.data() + (size_t) r * n_motifs;
+            const double *s = best.data() + (size_t) r * n_motifs;
+            for (int32_t m = 0; m < n_motifs; m++) {
+                if (m) { *pn++ = '\t'; *ps++ = '\t'; }
+                const int32_t cnt = c[m];
+                if (cnt == 0) {
+                    *pn++ = '0';
+                    *ps++ = 'N'; *ps++ = 'A';
+                } else {
+                    pn += fmt_int(cnt, pn);
+                    ps += py_float_str(s[m], ps);
+                }
+            }
+            *pn++ = '\n';
+            *ps++ = '\n';
+        }
+        P.n_num = (size_t) (pn - P.num);
+        P.n_score = (size_t) (ps - P.score);
+    };
+    auto run = [&](auto &fn) {
+        std::vector<std::thread> pool;
+        for (int t = 1; t < nt; t++) pool.emplace_back(fn, t);
+        fn(0);
+        for (auto &th : pool) th.join();
+    };
+    run(fill);
+    run(format);
+    size_t total_num = 0, total_score = 0;
+    for (auto &P : parts) { total_num += P.n_num; total_score += P.n_score; }
+    char *out_num = oom ? nullptr : (char *) std::malloc(std::max<size_t>(total_num, 1));
+    char *out_score = oom ? nullptr : (char *) std::malloc(std::max<size_t>(total_score, 1));
+    if (!out_num || !out_score) {
+        for (auto &P : parts) { std::free(P.num); std::free(P.score); }
+        std::free(out_num); std::free(out_score);
+        set_error("out of host memory");
+        return MSB_ENOMEM;
+    }
+    std::vector<size_t> at_num((size_t) nt), at_score((size_t) nt);
+    size_t an = 0, as = 0;
+    for (int t = 0; t < nt; t++) { at_num[t] = an; at_score[t] = as; an += parts[t].n_num; as += parts[t].n_score; }
+    auto gather = [&](int t) {
+        if (parts[t].n_num) std::memcpy(out_num + at_num[t], parts[t].num, parts[t].n_num);
+        if (parts[t].n_score) std::memcpy(out_score + at_score[t], parts[t].score, parts[t].n_score);
+        std::free(parts[t].num);
+        std::free(parts[t].score);
+    };
+    run(gather);
+    *num_text = out_num;
+    *num_len = (int64_t) total_num;
+    *score_text = out_score;
+    *score_len = (int64_t) total_score;
+    return MSB_OK;
+}
+
+int msb_text_free(char *text) {
+    std::free(text);
+    return MSB_OK;
 }
 
 // ---- c_score -----------------------------------------------------------------------------------

@@ -44,10 +44,50 @@ def _cell_tables(motif_sites, n_pwms, n_regions):
     return counts, best
 
 
+def _write_sites_table_blocks(f_num, f_score, regions, motif_sites, n_pwms, block_rows=8192):
+    """The two tables block by block from the scan's arrays: the cells of a block of rows are filled and
+    formatted by the library on host threads (msb_format_site_tables; numbers look like Python's str()), so
+    200,000 regions x 1,900 motifs never exist as a dense table, let alone as Python objects."""
+    import ctypes
+    from . import _lib
+    lib = _lib.load()
+    off = np.ascontiguousarray(motif_sites._off, dtype=np.int64)
+    seq = np.ascontiguousarray(motif_sites._seq_idx, dtype=np.int32)
+    score = np.ascontiguousarray(motif_sites._score, dtype=np.float64)
+    if seq.size == 0:
+        seq, score = np.zeros(1, np.int32), np.zeros(1, np.float64)
+    n_threads = min(os.cpu_count() or 1, 32)
+    for r0 in range(0, len(regions), block_rows):
+        r1 = min(r0 + block_rows, len(regions))
+        leads = [f"{g.chrom}\t{g.start + 1}\t{g.end}\t".encode() for g in regions[r0:r1]]
+        lead_off = np.zeros(len(leads) + 1, dtype=np.int64)
+        np.cumsum([len(x) for x in leads], out=lead_off[1:])
+        p_num, p_score = ctypes.c_void_p(), ctypes.c_void_p()
+        n_num, n_score = ctypes.c_int64(0), ctypes.c_int64(0)
+        _lib.check(lib.msb_format_site_tables(n_pwms, _lib.ptr(off, ctypes.c_int64), _lib.ptr(seq, ctypes.c_int32),
+                                              _lib.ptr(score, ctypes.c_double), r0, r1, b"".join(leads),
+                                              _lib.ptr(lead_off, ctypes.c_int64), ctypes.byref(p_num), ctypes.byref(n_num),
+                                              ctypes.byref(p_score), ctypes.byref(n_score), n_threads))
+        try:
+            # straight from the library's buffers to the files, no copy into a bytes object
+            f_num.write((ctypes.c_char * n_num.value).from_address(p_num.value))
+            f_score.write((ctypes.c_char * n_score.value).from_address(p_score.value))
+        finally:
+            lib.msb_text_free(p_num)
+            lib.msb_text_free(p_score)
+
+
 def write_sites_table(output_dir, pwms, regions, motif_sites):
     os.makedirs(output_dir, exist_ok=True)
-    counts, best = _cell_tables(motif_sites, len(pwms), len(regions))
     header = "chr\tstart\tend\t" + "\t".join(_motif_names(pwms)) + "\n"
+    if hasattr(motif_sites, "_off"):     # a scan's arrays: streamed through the native formatter
+        with open(os.path.join(output_dir, "motif_sites_number.xls"), "wb") as f_num, \
+                open(os.path.join(output_dir, "motif_sites_score.xls"), "wb") as f_score:
+            f_num.write(header.encode())
+            f_score.write(header.encode())
+            _write_sites_table_blocks(f_num, f_score, list(regions), motif_sites, len(pwms))
+        return
+    counts, best = _cell_tables(motif_sites, len(pwms), len(regions))
     with open(os.path.join(output_dir, "motif_sites_number.xls"), "w") as f_num, \
             open(os.path.join(output_dir, "motif_sites_score.xls"), "w") as f_score:
         f_num.write(header)

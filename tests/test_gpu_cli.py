@@ -111,3 +111,44 @@ def test_build_then_scan_files_identical(workspace, tmp_path):
             n_files += 1
     assert n_files == 3 + len(built_pwms)
     assert sum(len(c) for per in sites for c in per) > 100   # the comparison is not vacuous
+
+
+def _tree(path):
+    out = {}
+    for root, _, names in os.walk(path):
+        for name in names:
+            full = os.path.join(root, name)
+            out[os.path.relpath(full, path)] = open(full, "rb").read()
+    return out
+
+
+def test_scan_through_the_packed_genome_and_on_several_gpus(workspace, tmp_path, monkeypatch):
+    """`scan` over the packed, device-resident genome (cache file next to the FASTA, windows cut on the device,
+    tables written by the native formatter) and `--gpus N` write byte for byte the files of the plain run that
+    fetches region strings from the FASTA like the reference."""
+    from motifscan_b200 import _lib
+    gdir, mdir = workspace / "toyg", workspace / "toym"
+    if not (mdir / "toym_toyg_pwms.motifscan").exists():
+        assert cli.main(["motif", "--build", str(mdir), "-g", str(gdir), "--n-random", "20000", "--seed", "1"]) == 0
+    for stale in gdir.glob("toyg.packed.*"):
+        stale.unlink()
+    base = ["scan", "-i", str(workspace / "peaks.bed"), "-m", str(mdir), "-g", str(gdir), "-p", "1e-3", "-w", "400",
+            "--site", "--n-random", "2", "--seed", "3"]
+    assert cli.main(base + ["-o", str(tmp_path / "plain")]) == 0
+    assert not list(gdir.glob("toyg.packed.*"))                      # a small scan does not pack the genome
+    monkeypatch.setattr(cli, "PACKED_MIN_BP", 1)
+    assert cli.main(base + ["-o", str(tmp_path / "packed")]) == 0    # packs on the device, writes the cache
+    assert (gdir / "toyg.packed.chroms.tsv").exists()
+    monkeypatch.setattr(cli, "PACKED_MIN_BP", 1 << 40)
+    assert cli.main(base + ["-o", str(tmp_path / "cached")]) == 0    # the cache alone switches the path on
+    want = _tree(tmp_path / "plain")
+    assert len(want) > 10
+    assert _tree(tmp_path / "packed") == want and _tree(tmp_path / "cached") == want
+    n = min(_lib.device_count(), 8)
+    if n >= 2:
+        assert cli.main(base + ["-o", str(tmp_path / "multi"), "--gpus", str(n)]) == 0
+        assert _tree(tmp_path / "multi") == want
+    with pytest.raises(SystemExit):
+        cli.main(base + ["-o", str(tmp_path / "toomany"), "--gpus", "64"])
+    for stale in gdir.glob("toyg.packed.*"):
+        stale.unlink()

@@ -179,3 +179,47 @@ def test_merge_sites_translates_local_sequence_numbers():
         assert np.array_equal(sc, np.concatenate(score)[order]) and np.array_equal(sd, np.concatenate(strand)[order])
         g2, st2, _, _ = engine.merge_sites(counts, seq, start, score, strand)
         assert np.array_equal(g2, np.concatenate(seq)[order]) and np.array_equal(st2, np.concatenate(start)[order])
+
+
+def test_native_site_tables_equal_the_python_writer(tmp_path):
+    """msb_format_site_tables (host code in the library) writes motif_sites_number.xls / motif_sites_score.xls byte
+    for byte like the list-based writer (io/__init__.py:12-38 restated): counts, `NA`, and doubles printed as
+    Python's str() prints them -- fixed / scientific switch, shortest round-trip digits, denormals, huge values."""
+    import struct
+    from motifscan_b200 import io as msio
+    from motifscan_b200.scanner import MotifSites
+    rng = np.random.default_rng(0)
+    n_pwms, n_regions = 23, 3000
+
+    class Region:
+        def __init__(self, c, a, b):
+            self.chrom, self.start, self.end = c, a, b
+
+    class Pwm:
+        def __init__(self, i):
+            self.matrix_id, self.name, self.length = f"MA{i:04d}.1", f"name{i}", 8
+    regions = [Region(f"chr{i % 5}", i * 10, i * 10 + 500) for i in range(n_regions)]
+    pwms = [Pwm(i) for i in range(n_pwms)]
+    counts = rng.integers(0, 2500, size=n_pwms)
+    counts[3] = 0
+    seqs = [np.sort(rng.integers(0, n_regions, size=c)).astype(np.int32) for c in counts]
+    vals = np.concatenate([rng.normal(0.5, 0.3, size=c) for c in counts])
+    special = [0.0001, 0.00001, 1e16, 1e15, 1.0, -0.0, 123456789.125, 1e-7, 0.1 + 0.2, 5e-324, 1.7976931348623157e308,
+               2.5, 100.0, 1e22, 1.5e-5, 0.3, 1 / 3, 2 / 3, 9.999999999999999e-05, 0.00010000000000000002]
+    vals[:len(special)] = special
+    bits = rng.integers(0, 2**63, size=2000, dtype=np.int64)        # arbitrary finite bit patterns
+    rnd = np.array([struct.unpack("<d", struct.pack("<q", int(b)))[0] for b in bits])
+    rnd = rnd[np.isfinite(rnd)]
+    vals[len(special):len(special) + len(rnd)] = rnd
+
+    class Res:
+        pass
+    res = Res()
+    res.offsets = np.concatenate([[0], np.cumsum(counts)]).astype(np.int64)
+    res.seq_idx, res.start = np.concatenate(seqs), np.zeros(len(vals), np.int32)
+    res.score, res.strand = vals, np.ones(len(vals), np.int8)
+    sites = MotifSites(res, n_pwms, [g.start for g in regions], [8] * n_pwms)
+    msio.write_sites_table(str(tmp_path / "native"), pwms, regions, sites)
+    msio.write_sites_table(str(tmp_path / "lists"), pwms, regions, sites.tolist())
+    for name in ("motif_sites_number.xls", "motif_sites_score.xls"):
+        assert (tmp_path / "native" / name).read_bytes() == (tmp_path / "lists" / name).read_bytes(), name
