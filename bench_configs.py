@@ -437,11 +437,19 @@ def bench_cli(args):
             self.chrom, self.start, self.end = c, a, b
     ref_dir = os.path.join(root, "ref")
     msio.write_sites_table(ref_dir, pwms, [Region(*r) for r in regions], nested)
-    same = True
+    same, first_diff = True, None
     for name in ("motif_sites_number.xls", "motif_sites_score.xls"):
         with open(os.path.join(ref_dir, name)) as a, open(os.path.join(out, name)) as b:
-            for _ in range(n + 1):
-                same = same and a.readline() == b.readline()
+            for row in range(n + 1):
+                la, lb = a.readline(), b.readline()
+                if la != lb:
+                    same = False
+                    if first_diff is None:
+                        fa, fb = la.rstrip("\n").split("\t"), lb.rstrip("\n").split("\t")
+                        cols = [k for k in range(min(len(fa), len(fb))) if fa[k] != fb[k]]
+                        first_diff = {"table": name, "row": row, "n_fields": [len(fa), len(fb)], "columns": cols[:8],
+                                      "reference": [fa[k] for k in cols[:8]], "ours": [fb[k] for k in cols[:8]],
+                                      "motif_lengths": [int(mats[k - 3].shape[1]) for k in cols[:8] if k >= 3]}
     sizes_out = {name: os.path.getsize(os.path.join(out, name)) for name in sorted(os.listdir(out))}
     shutil.rmtree(root, ignore_errors=True)
     return {"config": f"configs[4] through the CLI: motifscan scan, {args.regions} target + {args.regions} control 1 kb regions x {args.motifs} motifs "
@@ -451,7 +459,8 @@ def bench_cli(args):
             "value": args.motifs * 2 * args.regions * 1000 / wall_s,
             "cpu_baseline": {"kind": kind, "cores": os.cpu_count(), "sample": f"{n} regions x all motifs (extension call only)",
                              "value": args.motifs * n * 1000 / cpu_s, "seconds": cpu_s},
-            "parity": {f"first_{n}_rows_of_both_site_tables_identical_to_the_reference_pipeline": bool(same)}}
+            "parity": {f"first_{n}_rows_of_both_site_tables_identical_to_the_reference_pipeline": bool(same),
+                       "first_difference": first_diff}}
 
 
 def main():

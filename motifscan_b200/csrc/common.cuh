@@ -11,7 +11,8 @@
 namespace msb {
 
 // ---- limits of the fast (table prefilter) path ------------------------------------------------
-constexpr int kMaxFastLen = 32;               // motifs up to this length use the prefilter kernel
+constexpr int kMaxFastLen = 32;               // columns a prefilter looks at (the register window of the exact stage)
+constexpr int kMaxTcLen = 64;                 // longest motif the tensor-core path takes (prefiltered on kMaxFastLen columns)
 constexpr int kMaxGroups = kMaxFastLen / 2;   // 2-mer groups per motif (G = ceil(L/2))
 constexpr int kGroupWords = 16;               // 4^2 table entries per group, 32-bit each
 constexpr int kGroupBytes = kGroupWords * 4;  // 64 B: one group spans 16 banks, conflict-free

@@ -910,11 +910,11 @@ int msb_seqs_destroy(msb_seqs *S) {
 namespace msb {
 
 // Motifs the prefilters can take.  The table prefilter holds at most kMaxFastLen columns; the tensor-core
-// prefilter takes any length: it looks at the first kMaxFastLen columns of a strand only (tc_fill_column) and
-// the exact stage scores the whole window.
+// prefilter takes up to kMaxTcLen columns: it looks at the first kMaxFastLen columns of a strand only
+// (tc_fill_column), the exact stage scores the whole window, and the producer's all-N test spans kMaxTcLen bases.
 static bool motif_is_fast(const msb_motifs *M, int32_t m, bool tensor = false) {
     const int L = M->lens[m];
-    if (L < 1 || (!tensor && L > kMaxFastLen)) return false;
+    if (L < 1 || L > (tensor ? kMaxTcLen : kMaxFastLen)) return false;
     const double *mat = M->mats.data() + M->mat_off[m];
     for (int k = 0; k < 4 * L; k++)
         if (!std::isfinite(mat[k])) return false;

@@ -415,12 +415,18 @@ prefilter_tc_kernel(const __grid_constant__ TcParams P) {
                         if (q0 < P.pos_lo) valid &= P.pos_lo - q0 >= 32 ? 0u : ~((1u << (int) (P.pos_lo - q0)) - 1u);
                         if (q0 + 32 > P.pos_hi) valid &= P.pos_hi <= q0 ? 0u : ((1u << (int) (P.pos_hi - q0)) - 1u);
                         const uint64_t m64 = ((uint64_t) __ldg(S.nmask + blk + 1) << 32) | __ldg(S.nmask + blk);
+                        const uint64_t m64hi = (uint64_t) __ldg(S.nmask + blk + 2);   // bases 64..95 (zero padding behind the set)
+                        // a dirty window is dropped here only when EVERY base any motif can see is N (then every
+                        // motif scores exactly 0, cscore.c:346): for motifs longer than the 32-base horizon that
+                        // takes the longest motif's length (<= 64), not the horizon
+                        const uint64_t span = P.lmax_all >= 64 ? ~0ull : ((1ull << P.lmax_all) - 1ull);
                         uint32_t dirtym = 0, emitm = 0;
 #pragma unroll 1
                         for (int k = 0; k < 32; k++) {
                             const uint32_t bits = (uint32_t) (m64 >> k) & horizon;
+                            const uint64_t wide = ((m64 >> k) | (k ? m64hi << (64 - k) : 0ull)) & span;
                             dirtym |= (bits != 0 ? 1u : 0u) << k;
-                            emitm |= ((bits != 0 && !(bits == horizon && !P.any_zero_hit)) ? 1u : 0u) << k;
+                            emitm |= ((bits != 0 && !(wide == span && !P.any_zero_hit)) ? 1u : 0u) << k;
                         }
                         ign = dirtym | ~valid;
                         if (P.emit_dirty) {

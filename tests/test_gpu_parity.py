@@ -218,9 +218,13 @@ def test_long_motifs_production_shape(eng, tc):
     and the exact stage scores the whole window from memory (N anywhere in it, also behind base 32); with the
     table prefilter they take the every-position exact kernel.  Same sites either way, bit for bit."""
     rng = np.random.default_rng(121)
-    pwms = synth_pwms(rng, 24, lmin=33, lmax=64) + synth_pwms(rng, 40, lmin=6, lmax=32)
+    pwms = synth_pwms(rng, 24, lmin=33, lmax=64) + synth_pwms(rng, 40, lmin=6, lmax=32) + synth_pwms(rng, 2, lmin=65, lmax=80)
     seqs = synth_seqs(rng, 80, 200, 1500, p_n=0.004, n_blocks=True) + ["ACGT" * 8 + "A", "N" * 70, "acgt" * 16 + "N" + "acgt" * 9]
+    # runs of N followed by sequence: a window whose first 32 bases are N still scores > 0 for a longer motif
+    seqs += ["N" * 100 + s[:120] + "N" * 40 + s[120:300] for s in synth_seqs(rng, 12, 300, 300)]
     cutoffs = cutoffs_for(pwms, seqs, 3e-3)
+    for m in (0, 3, 7, 30):
+        cutoffs[m] = 1e-6          # nearly every window with a positive partial score is a site (incl. mostly-N ones)
     ctx = eng.Context(0)
     ctx.set_option("prefilter_tc", tc)
     motifs = eng.MotifSet(ctx, pwms, cutoffs)
