@@ -93,6 +93,8 @@ struct msb_ctx {
     bool last_compact = false;             // MSB_SCAN_COMPACT: fin[].start holds (packed position << 1 | strand) as uint32
     const msb_seqs *last_seqs = nullptr;   // the sequence set of the last scan (its layout decodes compact sites)
     cudaStream_t d2h_stream = nullptr;
+    cudaStream_t aux_stream = nullptr;     // exact_dirty_kernel beside exact_records_kernel
+    cudaEvent_t aux_fork = nullptr, aux_join = nullptr;
     // final site arrays of the last scan (point into fin[fin_cur])
     uint64_t *fin_key = nullptr;
     double *fin_score = nullptr;
@@ -367,6 +369,13 @@ int msb_ctx_create(int device, void *stream, msb_ctx **out) {
         return MSB_ENOMEM;
     }
     ctx->opt_tc_prof = std::getenv("MSB_TC_PROF") ? 1 : 0;
+    if (cudaStreamCreateWithFlags(&ctx->aux_stream, cudaStreamNonBlocking) != cudaSuccess ||
+        cudaEventCreateWithFlags(&ctx->aux_fork, cudaEventDisableTiming) != cudaSuccess ||
+        cudaEventCreateWithFlags(&ctx->aux_join, cudaEventDisableTiming) != cudaSuccess) {
+        cudaGetLastError();
+        if (ctx->aux_stream) cudaStreamDestroy(ctx->aux_stream);
+        ctx->aux_stream = nullptr;   // everything stays on the main stream
+    }
     cudaFuncSetAttribute(prefilter_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) ctx->smem_optin);
     cudaFuncSetAttribute(prefilter_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) ctx->smem_optin);
     cudaFuncSetAttribute(prefilter_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kTcSmemBytes);
@@ -393,6 +402,9 @@ int msb_ctx_destroy(msb_ctx *ctx) {
         if (f.read_done) cudaEventDestroy(f.read_done);
     }
     if (ctx->d2h_stream) cudaStreamDestroy(ctx->d2h_stream);
+    if (ctx->aux_stream) { cudaStreamSynchronize(ctx->aux_stream); cudaStreamDestroy(ctx->aux_stream); }
+    if (ctx->aux_fork) cudaEventDestroy(ctx->aux_fork);
+    if (ctx->aux_join) cudaEventDestroy(ctx->aux_join);
     for (auto &b : ctx->pinned_free) cudaFreeHost(b.p);
     for (auto &b : ctx->dev_free) b.release();
     if (ctx->h_counters) cudaFreeHost(ctx->h_counters);
@@ -1482,6 +1494,7 @@ static int scan_device(msb_ctx *ctx, msb_motifs *M, const msb_seqs *S, int stran
         MSB_TRY(ctx->hit_key.ensure((size_t) hit_cap * 8));
         MSB_TRY(ctx->hit_score.ensure((size_t) hit_cap * 8));
         MSB_CUDA(cudaMemsetAsync(ctx->counters.as<unsigned long long>() + 2, 0, sizeof(unsigned long long), st));
+        const bool forked = ctx->aux_stream && cudaEventRecord(ctx->aux_fork, st) == cudaSuccess;
         ExactParams E;
         E.seq = sv;
         E.mot = mv;
@@ -1504,11 +1517,22 @@ static int scan_device(msb_ctx *ctx, msb_motifs *M, const msb_seqs *S, int stran
             ctx->c[MSB_C_LAUNCHES]++;
         }
         if (n_dirty && n_fast) {
-            // one block = 8 warps x 32 positions x one chunk of kDirtyMotifs motifs
+            // one block = 8 warps x 32 positions x one chunk of kDirtyMotifs motifs.  The dirty windows of a scan are
+            // few (N-run edges) and this kernel is latency-bound at low occupancy: it runs beside exact_records on a
+            // second stream (both only append to the hit buffers), forked behind the counter reset and joined below.
             const int64_t blocks = ((n_dirty + 255) / 256) * ((n_fast + kDirtyMotifs - 1) / kDirtyMotifs);
             if (blocks > 0x7fffffffll) { set_error("msb_scan: too many dirty windows for one launch"); return MSB_EINVAL; }
-            exact_dirty_kernel<<<(unsigned) blocks, 256, 0, st>>>(E, ctx->dirty.as<int64_t>(), n_dirty, d_order, n_fast);
+            cudaStream_t ds = st;
+            if (ctx->aux_stream && forked) {
+                MSB_CUDA(cudaStreamWaitEvent(ctx->aux_stream, ctx->aux_fork, 0));
+                ds = ctx->aux_stream;
+            }
+            exact_dirty_kernel<<<(unsigned) blocks, 256, 0, ds>>>(E, ctx->dirty.as<int64_t>(), n_dirty, d_order, n_fast);
             MSB_CUDA(cudaGetLastError());
+            if (ds != st) {
+                MSB_CUDA(cudaEventRecord(ctx->aux_join, ds));
+                MSB_CUDA(cudaStreamWaitEvent(st, ctx->aux_join, 0));
+            }
             ctx->c[MSB_C_LAUNCHES]++;
         }
         if (n_slow)
