@@ -1495,6 +1495,7 @@ static int scan_device(msb_ctx *ctx, msb_motifs *M, const msb_seqs *S, int stran
         MSB_TRY(ctx->hit_score.ensure((size_t) hit_cap * 8));
         MSB_CUDA(cudaMemsetAsync(ctx->counters.as<unsigned long long>() + 2, 0, sizeof(unsigned long long), st));
         const bool forked = ctx->aux_stream && cudaEventRecord(ctx->aux_fork, st) == cudaSuccess;
+        bool join_aux = false;
         ExactParams E;
         E.seq = sv;
         E.mot = mv;
@@ -1504,6 +1505,26 @@ static int scan_device(msb_ctx *ctx, msb_motifs *M, const msb_seqs *S, int stran
         E.hit_score = ctx->hit_score.as<double>();
         E.hit_cap = hit_cap;
         E.counters = ctx->counters.as<unsigned long long>();
+        if (n_dirty && n_fast) {
+            // one block = 8 warps x 32 positions x one chunk of kDirtyMotifs motifs.  The dirty windows of a scan are
+            // few (N-run edges) and this kernel is latency-bound at low occupancy: it runs beside exact_records on a
+            // second stream (both only append to the hit buffers), forked behind the counter reset and joined below.
+            // It is launched FIRST so that its ~100 blocks hold their slots before exact_records' thousands arrive.
+            const int64_t blocks = ((n_dirty + 255) / 256) * ((n_fast + kDirtyMotifs - 1) / kDirtyMotifs);
+            if (blocks > 0x7fffffffll) { set_error("msb_scan: too many dirty windows for one launch"); return MSB_EINVAL; }
+            cudaStream_t ds = st;
+            if (ctx->aux_stream && forked) {
+                MSB_CUDA(cudaStreamWaitEvent(ctx->aux_stream, ctx->aux_fork, 0));
+                ds = ctx->aux_stream;
+            }
+            exact_dirty_kernel<<<(unsigned) blocks, 256, 0, ds>>>(E, ctx->dirty.as<int64_t>(), n_dirty, d_order, n_fast);
+            MSB_CUDA(cudaGetLastError());
+            if (ds != st) {
+                MSB_CUDA(cudaEventRecord(ctx->aux_join, ds));
+                join_aux = true;
+            }
+            ctx->c[MSB_C_LAUNCHES]++;
+        }
         if (use_tc && n_rec) {
             exact_records_kernel<<<(unsigned) (((int64_t) n_lanes * 32 + 255) / 256), 256, 0, st>>>(
                 E, ctx->cand.as<uint4>(), lane_cap, ctx->lane_count.as<uint32_t>(), n_lanes, d_order,
@@ -1516,25 +1537,7 @@ static int scan_device(msb_ctx *ctx, msb_motifs *M, const msb_seqs *S, int stran
             MSB_CUDA(cudaGetLastError());
             ctx->c[MSB_C_LAUNCHES]++;
         }
-        if (n_dirty && n_fast) {
-            // one block = 8 warps x 32 positions x one chunk of kDirtyMotifs motifs.  The dirty windows of a scan are
-            // few (N-run edges) and this kernel is latency-bound at low occupancy: it runs beside exact_records on a
-            // second stream (both only append to the hit buffers), forked behind the counter reset and joined below.
-            const int64_t blocks = ((n_dirty + 255) / 256) * ((n_fast + kDirtyMotifs - 1) / kDirtyMotifs);
-            if (blocks > 0x7fffffffll) { set_error("msb_scan: too many dirty windows for one launch"); return MSB_EINVAL; }
-            cudaStream_t ds = st;
-            if (ctx->aux_stream && forked) {
-                MSB_CUDA(cudaStreamWaitEvent(ctx->aux_stream, ctx->aux_fork, 0));
-                ds = ctx->aux_stream;
-            }
-            exact_dirty_kernel<<<(unsigned) blocks, 256, 0, ds>>>(E, ctx->dirty.as<int64_t>(), n_dirty, d_order, n_fast);
-            MSB_CUDA(cudaGetLastError());
-            if (ds != st) {
-                MSB_CUDA(cudaEventRecord(ctx->aux_join, ds));
-                MSB_CUDA(cudaStreamWaitEvent(st, ctx->aux_join, 0));
-            }
-            ctx->c[MSB_C_LAUNCHES]++;
-        }
+        if (join_aux) MSB_CUDA(cudaStreamWaitEvent(st, ctx->aux_join, 0));   // behind exact_records' launch: the two overlap
         if (n_slow)
             for (auto &r : *ranges)
                 MSB_TRY(launch_positions(ctx, E, nullptr, r.second - r.first, r.first, d_slow, n_slow));
