@@ -179,6 +179,8 @@ struct msb_seqs {
     DevBuf d_codes, d_nmask, d_poff, d_len, d_seq_off, d_blk_seq, d_limit;
     bool has_limit = false;
     std::vector<int32_t> lens32;          // host copy of d_len (source of an asynchronous upload)
+    PinnedBlock tables;                   // asynchronous upload: poff | seq_off | len staged in pinned memory, so that the
+                                          // copies neither block the host nor wait for the copy stream to drain
     // MSB_SEQS_ASYNC: the upload runs on the context's copy stream; the first call that reads the set makes
     // the main stream wait for `ready`
     mutable cudaEvent_t ready = nullptr;
@@ -222,7 +224,7 @@ static int pinned_get(msb_ctx *ctx, size_t bytes, PinnedBlock *out) {
         std::lock_guard<std::mutex> g(ctx->pinned_mu);
         int best = -1;
         for (size_t i = 0; i < ctx->pinned_free.size(); i++)
-            if (ctx->pinned_free[i].cap >= bytes &&
+            if (ctx->pinned_free[i].cap >= bytes && ctx->pinned_free[i].cap <= 4 * bytes + (64 << 10) &&   // a table does not take a result's block
                 (best < 0 || ctx->pinned_free[i].cap < ctx->pinned_free[best].cap))
                 best = (int) i;
         if (best >= 0) {
@@ -630,9 +632,20 @@ static int seqs_prepare(msb_ctx *ctx, int64_t n_seqs, const int64_t *seq_off, ms
     // the owner table comes out of the recycled pool too: msb_scan_ascii scans slice k before slice k + 1 is
     // encoded, and a position tile may reach into the next slice's blocks
     step(cudaMemsetAsync(S->d_blk_seq.p, 0, (size_t) std::max<int64_t>(n_blocks, 1) * 4, st));
-    step(cudaMemcpyAsync(S->d_poff.p, S->poff.data(), (size_t) (n_seqs + 1) * 8, cudaMemcpyHostToDevice, st));
-    step(cudaMemcpyAsync(S->d_seq_off.p, S->seq_off.data(), (size_t) (n_seqs + 1) * 8, cudaMemcpyHostToDevice, st));
-    if (n_seqs) step(cudaMemcpyAsync(S->d_len.p, lens.data(), (size_t) n_seqs * 4, cudaMemcpyHostToDevice, st));
+    const void *h_poff = S->poff.data(), *h_seq_off = S->seq_off.data(), *h_len = lens.data();
+    if (on_stream) {
+        const size_t a = (size_t) (n_seqs + 1) * 8, c = (size_t) std::max<int64_t>(n_seqs, 1) * 4;
+        if (pinned_get(ctx, 2 * a + c, &S->tables) == MSB_OK) {
+            char *t = (char *) S->tables.p;
+            std::memcpy(t, S->poff.data(), a);
+            std::memcpy(t + a, S->seq_off.data(), a);
+            if (n_seqs) std::memcpy(t + 2 * a, lens.data(), (size_t) n_seqs * 4);
+            h_poff = t; h_seq_off = t + a; h_len = t + 2 * a;
+        }
+    }
+    step(cudaMemcpyAsync(S->d_poff.p, h_poff, (size_t) (n_seqs + 1) * 8, cudaMemcpyHostToDevice, st));
+    step(cudaMemcpyAsync(S->d_seq_off.p, h_seq_off, (size_t) (n_seqs + 1) * 8, cudaMemcpyHostToDevice, st));
+    if (n_seqs) step(cudaMemcpyAsync(S->d_len.p, h_len, (size_t) n_seqs * 4, cudaMemcpyHostToDevice, st));
     if (e != cudaSuccess) {
         msb_seqs_destroy(S);
         return cuda_fail(e, "seqs_prepare", __FILE__, __LINE__);
@@ -893,6 +906,7 @@ int msb_seqs_destroy(msb_seqs *S) {
     if (S->ready) { cudaEventSynchronize(S->ready); cudaEventDestroy(S->ready); }
     cudaStreamSynchronize(S->ctx->stream);
     for (DevBuf *b : {&S->d_codes, &S->d_nmask, &S->d_poff, &S->d_len, &S->d_seq_off, &S->d_blk_seq, &S->d_limit}) dev_give(S->ctx, *b);
+    pinned_put(S->ctx, S->tables);
     delete S;
     return MSB_OK;
 }

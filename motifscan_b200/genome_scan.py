@@ -169,7 +169,7 @@ class Unit:
         return sum(b - a for _, a, b, _ in self.pieces)
 
 
-def plan_units(block_off, chrom_sizes, n_shares, unit_blocks, halo_bases, work_prefix=None):
+def plan_units(block_off, chrom_sizes, n_shares, unit_blocks, halo_bases, work_prefix=None, taper=False):
     """Cut the packed block space [0, B) into `n_shares` contiguous shares of (almost) equal size and every
     share into units of at most `unit_blocks` blocks.  Returns a list (per share) of lists of `Unit`.
     Every base of every chromosome is owned by exactly one unit; share and unit boundaries are multiples
@@ -193,9 +193,13 @@ def plan_units(block_off, chrom_sizes, n_shares, unit_blocks, halo_bases, work_p
     for k in range(n_shares):
         s0, s1 = cuts[k], cuts[k + 1]
         n_units = max(1, -(-(s1 - s0) // max(int(unit_blocks), 1)))
+        bounds = [s0 + (s1 - s0) * u // n_units for u in range(n_units + 1)]
+        if taper and bounds[-1] - bounds[-2] >= 4096:
+            # the copy-back of a share's LAST unit is the one transfer no scan hides: cut that unit into 1/2, 1/4, 1/4
+            a, b = bounds[-2], bounds[-1]
+            bounds[-1:] = [a + (b - a) // 2, a + 3 * (b - a) // 4, b]
         units = []
-        for u in range(n_units):
-            u0, u1 = s0 + (s1 - s0) * u // n_units, s0 + (s1 - s0) * (u + 1) // n_units
+        for u0, u1 in zip(bounds[:-1], bounds[1:]):
             if u1 <= u0:
                 continue
             pieces = []
@@ -288,7 +292,7 @@ class GenomeScanner:
         sizes = [pg.chrom_sizes[c] for c in pg.chroms]
         n_shares = self.world * len(self.devices)
         work = pg.work_prefix() if n_shares > 1 and hasattr(pg, "work_prefix") else None
-        shares = plan_units(pg.block_off, sizes, n_shares, max(int(unit_bp) // 32, 1), lmax - 1, work_prefix=work)
+        shares = plan_units(pg.block_off, sizes, n_shares, max(int(unit_bp) // 32, 1), lmax - 1, work_prefix=work, taper=True)
         self.shares = shares[self.rank * len(self.devices):(self.rank + 1) * len(self.devices)]
         self.ctxs = list(contexts) if contexts is not None else [engine.default_context(d) for d in self.devices]
         self.motifs = [engine.MotifSet(ctx, self.matrices, self.cutoffs) for ctx in self.ctxs]
