@@ -570,6 +570,8 @@ def run_ours(args, rank, local_rank, world):
     gs = GenomeScanner(pg, pwms, cutoffs=cutoffs, contexts=[ctx], world=world, rank=rank, unit_bp=unit_bp, resident=False)
     h2d_bytes = sum(12 * (u.upload1 - u.block0) for u in gs.shares[0])
 
+    e2e_phases = []
+
     def e2e_leg(collect_sites):
         sites_here, keep = 0, None
         for _ in range(min(args.warmup, 3)):
@@ -588,6 +590,7 @@ def run_ours(args, rank, local_rank, world):
                 keep = out
         barrier()
         ms = max_over_ranks(1e3 * (time.perf_counter() - t0) / args.steps)
+        e2e_phases.append({k: gs.last_stats[0][k] for k in ("prefilter", "exact", "order")})
         return ms, sites_here, total, keep
 
     counts_ms, _, total_b, _ = e2e_leg(False)
@@ -671,6 +674,7 @@ def run_ours(args, rank, local_rank, world):
                     "what": "GenomeScanner.scan: packed planes up from pinned host memory, ALL sites down to pinned host memory "
                             "(per-unit motif-major blocks), per-motif counts gathered over the ranks",
                     "host_merge_ms_rank0": merge_ms,
+                    "kernel_phase_ms_rank0": {"counts_out": e2e_phases[0], "sites_out": e2e_phases[1]},
                     "variants": {
                         "sites_out": {"value": units_total / (sites_ms / 1e3), "ms_per_step": sites_ms, "d2h_bytes_per_step": d2h_all},
                         "counts_out": {"value": units_total / (counts_ms / 1e3), "ms_per_step": counts_ms,

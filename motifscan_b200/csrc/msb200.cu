@@ -258,7 +258,9 @@ static int dev_take(msb_ctx *ctx, DevBuf &b, size_t bytes) {
         std::lock_guard<std::mutex> g(ctx->dev_mu);
         int best = -1;
         for (size_t i = 0; i < ctx->dev_free.size(); i++)
-            if (ctx->dev_free[i].cap >= bytes && ctx->dev_free[i].cap <= 2 * bytes + (1 << 20) &&
+            // best fit, whatever the excess: a unit of a quarter of the usual size takes a full-size buffer rather
+            // than a cudaMalloc (which synchronises the device in the middle of a pipelined scan)
+            if (ctx->dev_free[i].cap >= bytes &&
                 (best < 0 || ctx->dev_free[i].cap < ctx->dev_free[best].cap))
                 best = (int) i;
         if (best >= 0) {
@@ -273,7 +275,7 @@ static void dev_give(msb_ctx *ctx, DevBuf &b) {
     if (!b.p) return;
     if (ctx->opt_poison_pool) cudaMemsetAsync(b.p, 0xFF, b.cap, ctx->stream);
     std::lock_guard<std::mutex> g(ctx->dev_mu);
-    if (ctx->dev_free.size() < 24) {
+    if (ctx->dev_free.size() < 96) {
         ctx->dev_free.push_back(b);
         b.p = nullptr;
         b.cap = 0;
