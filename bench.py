@@ -10,8 +10,8 @@ Headline workload = BASELINE.json configs[3], north_star's target: the genome-wi
 synthetic hg19-shaped genome (25 chromosomes, 3.1 Gbp, ~7 % N) with a JASPAR-2020-vertebrates-shaped set
 of 750 PWMs (length 6-30), cutoffs at p = 1e-4.  STRONG scaling: the same genome at every N; the packed
 genome's position space is cut into N contiguous shares, rank r scans share r (one process per GPU), and the
-only cross-rank step is the final host-side gather of the per-motif site counts (an all-reduce of 750
-int64 over gloo -- no NCCL on this path), which sits INSIDE every timed step.
+only cross-rank step is the final host-side gather of the per-motif site counts (750 int64 per rank sent to
+rank 0 over gloo -- no NCCL on this path), which sits INSIDE every timed step.
 
 One "step" = one pass over the whole genome:
   value        the rank's share already resident in HBM (2-bit codes + N mask); prefilter + exact fp64
@@ -532,10 +532,18 @@ def run_ours(args, rank, local_rank, world):
     gs = GenomeScanner(pg, pwms, cutoffs=cutoffs, contexts=[ctx], world=world, rank=rank, unit_bp=unit_bp, resident=True)
     share_bp = sum(u.owned_bp for u in gs.shares[0])
 
+    gather_ms = []
+
+    def gather(counts):
+        """The final host-side gather of the per-motif counts (on rank 0), inside every timed step."""
+        t0 = time.perf_counter()
+        total = gather_counts(counts, dist, dst=0)
+        gather_ms.append(1e3 * (time.perf_counter() - t0))
+        return total
+
     def resident_step():
         out = gs.scan(collect_sites=False, order_sites=True)
-        total = gather_counts(out.counts, dist)               # the final host-side gather of the per-motif counts
-        return out, total
+        return out, gather(out.counts)
 
     for _ in range(args.warmup):
         out, total_counts = resident_step()
@@ -559,11 +567,20 @@ def run_ours(args, rank, local_rank, world):
         pre_launches = st["prefilter_launches"]
     barrier()
     wall_ms = 1e3 * (time.perf_counter() - t_wall0) / args.steps
+    # per-rank kernel time of a pass (the count gather makes every rank's step as long as the slowest rank's)
+    mine = [sum(phases[k]) / len(phases[k]) for k in ("prefilter", "exact", "order")] + [float(share_bp)]
+    if dist is not None:
+        every = [torch.zeros(4, dtype=torch.float64) for _ in range(world)]
+        dist.all_gather(every, torch.tensor(mine, dtype=torch.float64))
+        per_rank = [[round(float(x), 3) for x in t] for t in every]
+    else:
+        per_rank = [[round(x, 3) for x in mine]]
     candidates = gs.last_stats[0]["candidates"]
     n_units = gs.last_stats[0]["units"]
     ms_per_step = max_over_ranks(sum(step_ms) / len(step_ms))
     wall_ms = max_over_ranks(wall_ms)
-    n_sites_total = int(total_counts.sum())
+    n_sites_total = int(total_counts.sum()) if rank == 0 else 0
+    gather_resident_ms = sum(gather_ms[-args.steps:]) / args.steps
     gs.close()
 
     # ---- leg 2: end to end (host planes in, host sites / counts out) -----------------------------------------
@@ -576,13 +593,13 @@ def run_ours(args, rank, local_rank, world):
         sites_here, keep = 0, None
         for _ in range(min(args.warmup, 3)):
             out = gs.scan(collect_sites=collect_sites)
-            gather_counts(out.counts, dist)
+            gather(out.counts)
             out.close()
         barrier()
         t0 = time.perf_counter()
         for k in range(args.steps):
             out = gs.scan(collect_sites=collect_sites)        # returns when every unit's sites are in host memory
-            total = gather_counts(out.counts, dist)
+            total = gather(out.counts)
             sites_here = int(out.counts.sum())
             if k + 1 < args.steps or not collect_sites:
                 out.close()
@@ -598,7 +615,8 @@ def run_ours(args, rank, local_rank, world):
     clocks = sampler.stop()
     d2h_sites = 12 * sites_here + 8 * (N_MOTIFS + 1) * len(gs.shares[0])
     d2h_counts = 8 * N_MOTIFS * len(gs.shares[0])
-    assert np.array_equal(total_b, total_counts) and np.array_equal(total_c, total_counts), "legs disagree on the per-motif counts"
+    if rank == 0:
+        assert np.array_equal(total_b, total_counts) and np.array_equal(total_c, total_counts), "legs disagree on the per-motif counts"
     merge_ms = None
     if kept is not None:
         t0 = time.perf_counter()
@@ -663,11 +681,12 @@ def run_ours(args, rank, local_rank, world):
                        "cutoffs": f"p={P_VALUE} from {N_BACKGROUND} background samples, floored at 1e-6 ({cut_src})",
                        "l2": "inputs larger than L2 (0.375 B/bp packed genome share, >= 145 MB per rank, streamed once per step)",
                        "parallelism": f"position space cut into {world} contiguous share(s), one process per GPU, units of "
-                                      f"{unit_bp} bp; gather = all-reduce of {N_MOTIFS} int64 counts over gloo inside every step",
+                                      f"{unit_bp} bp; gather = {N_MOTIFS} int64 counts per rank sent to rank 0 over gloo inside every step",
                        "genome_generation_s": gen_s,
                        "host_cores_rank0": f"{len(cpus)} NUMA-local cores" if cpus else "unbound"},
             "phase_ms": {k: sum(v) / len(v) for k, v in phases.items()},
-            "wall_ms_per_step": wall_ms, "units_per_step_rank0": n_units,
+            "wall_ms_per_step": wall_ms, "units_per_step_rank0": n_units, "count_gather_ms_rank0": gather_resident_ms,
+            "per_rank_kernel_ms": {"columns": ["prefilter", "exact", "order", "share_bp"], "rows": per_rank},
             "sites_per_step": n_sites_total, "candidates_per_step_rank0": candidates,
             "e2e": {"value": units_total / (sites_ms / 1e3), "unit": UNIT, "ms_per_step": sites_ms, "steps": args.steps,
                     "h2d_bytes_per_step": h2d_all, "d2h_bytes_per_step": d2h_all,

@@ -43,16 +43,25 @@ def assign_lpt(costs, world):
     return owner, load
 
 
-def gather_counts(counts, dist=None):
-    """The final gather of a sharded scan: per-motif site counts summed over the ranks (one all-reduce of
-    n_motifs int64 on the process group's host backend; NCCL is not on this path).  Every rank gets the sum."""
+def gather_counts(counts, dist=None, dst=None):
+    """The final gather of a sharded scan: per-motif site counts summed over the ranks on the process group's
+    host backend (gloo; NCCL is not on this path).  `dst=None`: every rank gets the sum (one all-reduce of
+    n_motifs int64).  `dst=r`: the ranks send their counts straight to rank r (one hop each, the lowest-latency
+    form over loopback sockets), which returns the sum; the others return None."""
     counts = np.ascontiguousarray(np.asarray(counts, dtype=np.int64))
     if dist is None or not dist.is_initialized() or dist.get_world_size() == 1:
         return counts.copy()
     import torch
     t = torch.from_numpy(counts.copy())
-    dist.all_reduce(t)
-    return t.numpy()
+    if dst is None:
+        dist.all_reduce(t)
+        return t.numpy()
+    if dist.get_rank() == dst:
+        parts = [torch.zeros_like(t) for _ in range(dist.get_world_size())]
+        dist.gather(t, parts, dst=dst)
+        return torch.stack(parts).sum(dim=0).numpy()
+    dist.gather(t, None, dst=dst)
+    return None
 
 
 def gather_sites(local, n_motifs, dist=None, dst=0):

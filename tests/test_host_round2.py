@@ -137,10 +137,12 @@ def _worker(rank, world, port, q):
                 cnt, _, start, _, _ = oracle.scan_arrays(pwms, cutoffs, [seq], 3)
                 motif = np.repeat(np.arange(len(pwms)), cnt)
                 counts += np.bincount(motif[start < b - a], minlength=len(pwms))    # starts in the halo belong to the next unit
-        total = shard.gather_counts(counts, dist)
+        total = shard.gather_counts(counts, dist)                 # all-reduce form: every rank gets the sum
+        at_root = shard.gather_counts(counts, dist, dst=0)        # one-hop form: rank 0 gets the sum, the others None
         whole = [pg.decode_bytes(c, 0, pg.chrom_sizes[c]).decode() for c in pg.chroms]
         full = oracle.scan_arrays(pwms, cutoffs, whole, 3)[0]
-        q.put(bool(np.array_equal(total, full) and full.sum() > 100 and counts.sum() < full.sum()))
+        root_ok = np.array_equal(at_root, full) if rank == 0 else at_root is None
+        q.put(bool(np.array_equal(total, full) and root_ok and full.sum() > 100 and counts.sum() < full.sum()))
     finally:
         dist.barrier()
         dist.destroy_process_group()
