@@ -86,9 +86,10 @@ class ClockSampler:
               "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
               "clocks_event_reasons.sw_power_cap")
 
-    def __init__(self, index, uuid=None):
+    def __init__(self, index, uuid=None, period_s=0.005):
         self.index = index
         self.uuid = uuid
+        self.period_s = period_s
         self.proc = None
         self.path = None
         self.thread = None
@@ -106,7 +107,7 @@ class ClockSampler:
                                      nv.nvmlDeviceGetPowerUsage(handle) / 1e3, int(get_reasons(handle))))
             except Exception:
                 break
-            time.sleep(0.002)
+            time.sleep(self.period_s)
 
     def start(self):
         try:
@@ -162,7 +163,7 @@ class ClockSampler:
                 out.update(sm_mhz=statistics.median(x[0] for x in busy), sm_max_mhz=self.max_mhz,
                            sm_min_mhz=min(x[0] for x in self.samples), power_w_max=max(x[1] for x in self.samples),
                            reasons=sorted(k for k, b in bits.items() if mask & b), samples=len(self.samples),
-                           source="NVML, 2 ms period; median over the samples above half the peak power (under load)")
+                           source="NVML, 5 ms period; median over the samples above half the peak power (under load)")
             return out
         if self.proc is None:
             return out
@@ -547,11 +548,13 @@ def run_ours(args, rank, local_rank, world):
 
     for _ in range(args.warmup):
         out, total_counts = resident_step()
-    sampler = ClockSampler(local_rank, gpu_uuid)
+    # rank 0 samples its GPU (NVML takes driver-wide locks: eight ranks polling at once slow each other's CUDA calls)
+    sampler = ClockSampler(local_rank, gpu_uuid) if rank == 0 else None
     step_ms, phases, launches = [], {"prefilter": [], "exact": [], "order": []}, 0
     pre_launches = 0
     barrier()
-    sampler.start()
+    if sampler is not None:
+        sampler.start()
     t_wall0 = time.perf_counter()
     for _ in range(args.steps):
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -612,7 +615,7 @@ def run_ours(args, rank, local_rank, world):
 
     counts_ms, _, total_b, _ = e2e_leg(False)
     sites_ms, sites_here, total_c, kept = e2e_leg(True)
-    clocks = sampler.stop()
+    clocks = sampler.stop() if sampler is not None else None
     d2h_sites = 12 * sites_here + 8 * (N_MOTIFS + 1) * len(gs.shares[0])
     d2h_counts = 8 * N_MOTIFS * len(gs.shares[0])
     if rank == 0:
