@@ -99,12 +99,6 @@ class Scanner:
                 self._sequences = [c.decode("utf-8") for c in self._chunks]
         return self._sequences
 
-    def _flat(self):
-        off = np.zeros(len(self._chunks) + 1, dtype=np.int64)
-        if self._chunks:
-            np.cumsum([len(c) for c in self._chunks], out=off[1:])
-        return np.frombuffer(b"".join(self._chunks), dtype=np.uint8), off
-
     def scan_motifs(self, pwms, ctx=None):
         """Scan for motif occurrences; returns a `MotifSites` (nested-list view, (n_pwms,
         n_regions, n_sites))."""
