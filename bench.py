@@ -532,6 +532,7 @@ def run_ours(args, rank, local_rank, world):
     unit_bp = int(min(UNIT_BP, max(MIN_UNIT_BP, genome_bp // world // 8)))
     gs = GenomeScanner(pg, pwms, cutoffs=cutoffs, contexts=[ctx], world=world, rank=rank, unit_bp=unit_bp, resident=True)
     share_bp = sum(u.owned_bp for u in gs.shares[0])
+    gs_blocks = (gs.shares[0][0].block0, gs.shares[0][-1].block1)
 
     gather_ms = []
 
@@ -655,8 +656,20 @@ def run_ours(args, rank, local_rank, world):
                 traffic = json.load(open(tpath)).get("dram_bytes_per_launch")
             except Exception:
                 traffic = None
+        # MMA work actually issued (mirrors ensure_tc_tables / prefilter_tc_kernel): motifs sorted by length, 128 per
+        # 256-column tile, K steps of 32 = 8 bases up to the tile's longest motif; every 512-base position tile that
+        # holds a live window runs 4 shifted 128-row MMAs per tile and K step (tiles inside N runs are skipped)
+        lens_sorted = np.sort(pwm_lens)
+        ksteps = sum(int(-(-int(lens_sorted[i:i + 128].max()) // 8)) for i in range(0, len(lens_sorted), 128))
+        w = pg.work_prefix()
+        u0, u1 = gs_blocks
+        live_bases = float(w[u1] - w[u0]) - float(u1 - u0)
+        issued = live_bases / 512.0 * 4 * ksteps * (2.0 * 128 * 256 * 32) / (pre_ms / 1e3) / 1e12
         roofline = {
             "bound": "tensor", "kernel": "prefilter_tc_kernel", "achieved": achieved, "peak": peak, "unit": "TFLOP/s",
+            "issued": {"tflops": issued, "frac_of_peak": issued / peak, "k_steps_issued": ksteps,
+                       "k_steps_needed": float(np.ceil(pwm_lens).sum() / 8.0 / 128.0),
+                       "note": "MMA work issued on this rank's non-N bases: K padded to 8 bases per step, 256-column tiles"},
             "frac": achieved / peak,
             "peak_source": ("dense e4m3 tcgen05 peak measured live by bench_micro/fp8_peak (sustained over ~1 s)" if peak_fp8 else
                             f"2 x bf16_tflops_sustained from {peaks_src} (bench_micro/fp8_peak not built)"),

@@ -50,6 +50,7 @@ def load_genome(name):
 
 
 PACKED_MIN_BP = 1 << 26    # scans of at least this many window bases go through the packed, device-resident genome
+BUILD_RESIDENT_MIN_SAMPLES = 200000    # `motif --build` with at least this many background samples samples from it too
 
 
 def packed_genome(genome, window_bp, device=0):
@@ -145,7 +146,16 @@ def run_motif(args):
     for matrix_id, name, pfm in read_jaspar_pfms(pfm_path):
         pwms.append(PositionWeightMatrix(pfm_to_pwm(pfm, genome.bg_freq), name=name, matrix_id=matrix_id))
     logger.info("Sampling background sequences and scoring them on the device")
-    build_cutoffs(pwms, genome, n_random=args.n_random, n_repeat=args.n_repeat, max_n=args.max_n, seed=args.seed)
+    # a large sample is drawn from the device-resident genome: the reference's RNG sequence stays on the host, the N
+    # count of every attempt and the sampled windows come out of HBM instead of one FASTA fetch per attempt
+    source = genome
+    if args.n_random * args.n_repeat >= BUILD_RESIDENT_MIN_SAMPLES or os.path.isfile(
+            os.path.join(genome.path or "", f"{genome.name}.packed.chroms.tsv")):
+        pg = packed_genome(genome, PACKED_MIN_BP)
+        if pg is not None:
+            from .genome import DeviceGenome
+            source = DeviceGenome(pg)
+    build_cutoffs(pwms, source, n_random=args.n_random, n_repeat=args.n_repeat, max_n=args.max_n, seed=args.seed)
     pwms.write_motifscan_pwms(pwms_path(motif_dir, short, genome.name))
     logger.info("Successfully built!")
     return 0

@@ -152,3 +152,28 @@ def test_scan_through_the_packed_genome_and_on_several_gpus(workspace, tmp_path,
         cli.main(base + ["-o", str(tmp_path / "toomany"), "--gpus", "64"])
     for stale in gdir.glob("toyg.packed.*"):
         stale.unlink()
+
+
+def test_build_from_the_resident_genome_writes_the_same_file(workspace, tmp_path, monkeypatch):
+    """`motif --build` with a large sample draws it from the packed, device-resident genome (RNG on the host in
+    the reference's order, N counts and windows on the device): the built PWM file is the one the host sampler
+    gives, byte for byte."""
+    gdir, mdir = workspace / "toyg", workspace / "toym"
+    built = mdir / "toym_toyg_pwms.motifscan"
+    args = ["motif", "--build", str(mdir), "-g", str(gdir), "--n-random", "20000", "--seed", "1", "--max-n", "0"]
+    for stale in gdir.glob("toyg.packed.*"):
+        stale.unlink()
+    assert cli.main(args) == 0
+    want = built.read_text()
+    monkeypatch.setattr(cli, "BUILD_RESIDENT_MIN_SAMPLES", 1)
+    assert cli.main(args) == 0
+    assert (gdir / "toyg.packed.chroms.tsv").exists()          # the resident path ran (and left the cache)
+    assert built.read_text() == want
+    assert cli.main(args + ["--n-repeat", "2"]) == 0            # also with repeats (seed, seed + 1) and the cache present
+    monkeypatch.setattr(cli, "BUILD_RESIDENT_MIN_SAMPLES", 1 << 40)
+    for stale in gdir.glob("toyg.packed.*"):
+        stale.unlink()
+    two = built.read_text()
+    assert cli.main(args + ["--n-repeat", "2"]) == 0
+    assert built.read_text() == two
+    assert cli.main(args) == 0                                  # leave the single-repeat file for the other tests
