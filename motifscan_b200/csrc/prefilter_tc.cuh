@@ -424,7 +424,11 @@ prefilter_tc_kernel(const __grid_constant__ TcParams P) {
 #pragma unroll 1
                         for (int k = 0; k < 32; k++) {
                             const uint32_t bits = (uint32_t) (m64 >> k) & horizon;
-                            const uint64_t wide = ((m64 >> k) | (k ? m64hi << (64 - k) : 0ull)) & span;
+                            // bases behind the sequence's end do not exist: a motif that would reach them has no
+                            // window here (cscore.c:340), so for the all-N test they count as N
+                            const int64_t rem = left - k;
+                            const uint64_t beyond = rem >= 64 ? 0ull : (rem <= 0 ? ~0ull : (~0ull << rem));
+                            const uint64_t wide = ((m64 >> k) | (k ? m64hi << (64 - k) : 0ull) | beyond) & span;
                             dirtym |= (bits != 0 ? 1u : 0u) << k;
                             emitm |= ((bits != 0 && !(wide == span && !P.any_zero_hit)) ? 1u : 0u) << k;
                         }
