@@ -1588,6 +1588,13 @@ static int scan_device(msb_ctx *ctx, msb_motifs *M, const msb_seqs *S, int stran
         MSB_CUDA(cub::DeviceScan::ExclusiveSum(ctx->sort_tmp.p, scan_bytes, ctx->motif_counts.as<int64_t>(), F.offsets.as<int64_t>(), M->n + 1, st));
     } else if (n_hits) {
         const bool dedup = (flags & MSB_SCAN_DEDUP) != 0;
+        if ((size_t) n_hits * 25 > ((size_t) 4 << 30)) {
+            // a very large result (billions of sites): the other set of final arrays, which only exists so that a
+            // copy can overlap the next scan, gives its memory back first
+            msb_ctx::FinSet &O = ctx->fin[fin_set ^ 1];
+            if (O.pending) { MSB_CUDA(cudaEventSynchronize(O.read_done)); O.pending = false; }
+            for (DevBuf *b : {&O.key, &O.score, &O.seq, &O.start, &O.strand}) b->release();
+        }
         // without de-duplication the sorted arrays ARE the final ones; with it they are scratch and the
         // survivors are scattered into the final set
         DevBuf &s_key = dedup ? ctx->key_alt : F.key, &s_score = dedup ? ctx->score_alt : F.score;
