@@ -117,6 +117,7 @@ struct msb_ctx {
     int opt_ascii_slices = 4;        // msb_scan_ascii: upload slices (1..7)
     int opt_tc_first_lane_cap = 0;   // tests: records per lane buffer on the first attempt (0 = sized from the input)
     int opt_poison_pool = 0;         // tests: fill device buffers with 0xFF when they go back to the pool
+    int opt_tc_interleave = 1;       // tensor-core prefilter: short and long motif tiles alternate (0: ascending by length)
     int opt_select_pilot = 1;        // msb_score_select: 0 = always score every sample for every motif (the plain form)
 };
 
@@ -1188,10 +1189,27 @@ static int ensure_tc_tables(msb_ctx *ctx, msb_motifs *M, int strand, TcTableSet 
     }
     auto ksteps = [&](int32_t m) { return (std::min(M->lens[m], kMaxFastLen) + 7) / 8; };
     std::stable_sort(fast.begin(), fast.end(), [&](int32_t a, int32_t b) { return M->lens[a] < M->lens[b]; });
-    T.order = fast;
     const int cols_per_motif = strand == 3 ? 2 : 1;
     const int motifs_per_tile = kTcCols / cols_per_motif;
     const size_t n_tiles = (fast.size() + motifs_per_tile - 1) / motifs_per_tile;
+    if (ctx->opt_tc_interleave && n_tiles > 2) {
+        // Tile order.  Sorted by length the tiles' K steps ascend (750 motifs: 2 2 3 3 4 4).  An epilogue warp set
+        // has the duration of its unit's MMAs plus the next unit's to get through a unit (the two TMEM buffers
+        // alternate), and its work per unit does not depend on K: next to each other the two short tiles leave it
+        // 4 K steps of time, the long ones 8.  Short and long tiles alternate instead (2 4 2 3 3 4: never fewer than 5);
+        // the last, possibly partial, tile stays last.
+        const size_t n_full = fast.size() / motifs_per_tile;
+        std::vector<int32_t> mixed;
+        mixed.reserve(fast.size());
+        size_t lo = 0, hi = n_full;
+        for (size_t i = 0; lo < hi; i++) {
+            const size_t g = (i & 1) ? --hi : lo++;
+            mixed.insert(mixed.end(), fast.begin() + g * motifs_per_tile, fast.begin() + (g + 1) * motifs_per_tile);
+        }
+        mixed.insert(mixed.end(), fast.begin() + n_full * motifs_per_tile, fast.end());
+        fast.swap(mixed);
+    }
+    T.order = fast;
     std::vector<uint32_t> col_info(std::max<size_t>(n_tiles, 1) * kTcCols, 0xffffffffu);
     std::vector<int32_t> tc_len(std::max<size_t>(fast.size(), 1), 0);
     std::vector<uint8_t> btab;
@@ -1687,6 +1705,7 @@ int msb_ctx_set_option(msb_ctx *ctx, const char *name, int value) {
     if (name && !std::strcmp(name, "tc_first_lane_cap") && value >= 0) { ctx->opt_tc_first_lane_cap = value; return MSB_OK; }
     if (name && !std::strcmp(name, "ascii_slices") && value >= 1 && value <= 7) { ctx->opt_ascii_slices = value; return MSB_OK; }
     if (name && !std::strcmp(name, "poison_pool") && (value == 0 || value == 1)) { ctx->opt_poison_pool = value; return MSB_OK; }
+    if (name && !std::strcmp(name, "tc_interleave") && (value == 0 || value == 1)) { ctx->opt_tc_interleave = value; return MSB_OK; }
     if (name && !std::strcmp(name, "select_pilot") && (value == 0 || value == 1)) { ctx->opt_select_pilot = value; return MSB_OK; }
     set_error("msb_ctx_set_option: unknown option or value");
     return MSB_EINVAL;
