@@ -31,7 +31,8 @@
 // Compile-time experiment switch (bench_micro/tc_ablate.sh builds one library per value; results in
 // profiles/): 0 = product, 1 = no candidate emission, 2 = no accumulator scan either, 3 = no TMEM
 // read-back either (tensor pipe alone), 8 = records stored without computing the flag words,
-// 9 = flag words computed but nothing stored.  Anything but 0 gives wrong results by design.
+// 9 = flag words computed but nothing stored, 10 = sign scan + branch only (a hit just counts), 11 = sign scan, no branch (predicated count).  Anything but 0 gives
+// wrong results by design.
 #ifndef MSB_TC_EXP
 #define MSB_TC_EXP 0
 #endif
@@ -56,6 +57,14 @@ constexpr int kTcWarpCols = 128;                        // accumulator columns o
 constexpr int kTcSmemBytes = kTcBOff + kTcMaxUnits * kTcUnitBytes;   // dynamic shared memory of the kernel
 constexpr int kTcLanesPerCta = kTcEpiWarps * 32;        // epilogue lanes, each with its own candidate-record buffer
 constexpr int kTcStaticSmemReserve = 1024;             // static __shared__ (barriers) + alignment slack
+// Warp roles.  MSB_TC_ISSUER_LAST = 1: epilogue warps 0-15, MMA issuer warp 16, producers 17-19 (the issuer and the
+// producers are the highest warp ids of their sub-partitions); 0: issuer 0, producers 1-3, epilogue 4-19.
+#ifndef MSB_TC_ISSUER_LAST
+#define MSB_TC_ISSUER_LAST 0
+#endif
+constexpr int kTcIssuerWarp = MSB_TC_ISSUER_LAST ? kTcEpiWarps : 0;
+constexpr int kTcFirstProducer = kTcIssuerWarp + 1;
+constexpr int kTcFirstEpi = MSB_TC_ISSUER_LAST ? 0 : 4;
 
 struct TcBatch {
     uint32_t n_tiles;
@@ -202,7 +211,15 @@ __device__ __forceinline__ void scan_chunk(const TcParams &P, LaneOut &out, cons
 #if MSB_TC_EXP >= 1 && MSB_TC_EXP <= 3
     hit = false;
 #endif
+#if MSB_TC_EXP == 11
+    out.n += hit ? 1u : 0u;   // ablation: the sign scan without any branch
+    return;
+#endif
     if (hit) {   // divergent, rare; usually one lane and one half: only that half's flag word is computed
+#if MSB_TC_EXP == 10
+        out.n++;     // ablation: the sign scan and the branch, nothing else
+        return;
+#endif
         uint32_t z = 0, w = 0;
 #if MSB_TC_EXP != 8
         if ((g_lo & M) != M) z = flag_word(r, 0);
@@ -291,7 +308,7 @@ prefilter_tc_kernel(const __grid_constant__ TcParams P) {
         const uint32_t bt = smem_u32(s_b) + (uint32_t) P.batch.unit_off[threadIdx.x] * kTcUnitBytes;
         s_tile[threadIdx.x] = make_uint2(((bt & 0x3FFFFu) >> 4) | ((4096u >> 4) << 16), P.batch.ks[threadIdx.x]);
     }
-    if (warp == 0) {
+    if (warp == kTcIssuerWarp) {
         asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], 512;" ::"r"(smem_u32(&s_tmem_base)));
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
     }
@@ -313,7 +330,7 @@ prefilter_tc_kernel(const __grid_constant__ TcParams P) {
     B.tmem_full = smem_u32(&bar_tmem_full[0]);
     B.tmem_empty = smem_u32(&bar_tmem_empty[0]);
 
-    if (warp == 0) {
+    if (warp == kTcIssuerWarp) {
         // ---- MMA issuer: the whole warp runs the loop (uniform values), one elected lane issues ----
         // D = F16 (0 << 4), A = B = E4M3 (0), both K-major, N = 256 (>> 3 at bit 17), M = 128 (>> 4 at bit 24)
         const uint32_t idesc = ((uint32_t) (kTcCols >> 3) << 17) | ((uint32_t) (128 >> 4) << 24);
@@ -370,9 +387,9 @@ prefilter_tc_kernel(const __grid_constant__ TcParams P) {
             long long *o = P.prof + blockIdx.x * 16;
             o[0] = now() - t_begin; o[1] = t_ws; o[2] = t_we; o[3] = t_is; o[4] = u;
         }
-    } else if (warp <= kTcProducerWarps) {
+    } else if (warp >= kTcFirstProducer && warp < kTcFirstProducer + kTcProducerWarps) {
         // ---- producers: packed codes -> 4 shifted one-hot streams, ignore bits, dirty windows -----
-        const int tid_p = (warp - 1) * 32 + lane;
+        const int tid_p = (warp - kTcFirstProducer) * 32 + lane;
         const uint32_t horizon = P.lmax_all >= 32 ? 0xffffffffu : ((1u << P.lmax_all) - 1u);
         uint32_t it = 0;
         for (int64_t t = pt_first; t < n_ptiles; t += gridDim.x, it++) {
@@ -394,7 +411,7 @@ prefilter_tc_kernel(const __grid_constant__ TcParams P) {
                     if (i >= 0 && i < kTcStreamBases) dst[s * kTcStreamBases + i] = word;
                 }
             }
-            if (warp == 1) {
+            if (warp == kTcFirstProducer) {
                 uint32_t ign = 0xffffffffu;
                 if (lane < 16) {
                     const int64_t q0 = tile_start + lane * 32;
@@ -461,10 +478,11 @@ prefilter_tc_kernel(const __grid_constant__ TcParams P) {
         }
     } else {
         // ---- epilogue: warp reads TMEM lanes 32 q .. 32 q + 31 (its 32 windows), 128 of the 256 columns
-        const int q = warp & 3, h = ((warp - 4) >> 2) & 1, set = (warp - 4) >> 3;
+        const int ew = warp - kTcFirstEpi;       // epilogue warp 0..15; kTcFirstEpi is a multiple of 4, so ew % 4 == warp % 4
+        const int q = warp & 3, h = (ew >> 2) & 1, set = ew >> 3;
         const int row = q * 32 + lane;
         LaneOut out;
-        const size_t lane_id = ((size_t) blockIdx.x * kTcEpiWarps + (warp - 4)) * 32 + lane;
+        const size_t lane_id = ((size_t) blockIdx.x * kTcEpiWarps + ew) * 32 + lane;
         out.buf = P.cand + lane_id * (size_t) P.cand_cap;
         out.n = P.lane_count[lane_id];
         const uint32_t taddr0 = tmem + set * kTcCols + h * kTcWarpCols + ((uint32_t) (q * 32) << 16);
@@ -525,7 +543,7 @@ prefilter_tc_kernel(const __grid_constant__ TcParams P) {
                     const long long c3 = now();
                     t_pr += c3 - c2;
                     if (__any_sync(0xffffffffu, out.n != n_before)) { t_slow += c3 - c2; n_slow++; }
-                    if (P.prof && blockIdx.x == 0 && lane == 0 && (warp == 4 || warp == 12) && uu >= 2000 && uu < 2012) {
+                    if (P.prof && blockIdx.x == 0 && lane == 0 && (ew == 0 || ew == 8) && uu >= 2000 && uu < 2012) {
                         long long *o = P.prof + gridDim.x * 16 + (uu - 2000) * 8;
                         o[2] = c0; o[3] = c1; o[4] = c2; o[5] = c3; o[6] = warp;
                     }
@@ -536,14 +554,14 @@ prefilter_tc_kernel(const __grid_constant__ TcParams P) {
             u += n_units;
         }
         P.lane_count[lane_id] = out.n;
-        if (kProf && P.prof && warp == 4 && lane == 0) {
+        if (kProf && P.prof && ew == 0 && lane == 0) {
             long long *o = P.prof + blockIdx.x * 16;
             o[8] = t_wf; o[9] = t_ld; o[10] = t_pr; o[11] = t_wsf; o[12] = u; o[13] = t_slow; o[14] = n_slow;
         }
     }
     fence_before();
     __syncthreads();
-    if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 512;" ::"r"(tmem));
+    if (warp == kTcIssuerWarp) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 512;" ::"r"(tmem));
 }
 
 }  // namespace msb
