@@ -6,7 +6,7 @@ cd "$(dirname "$0")/.."
 if [ "$1" = "run" ]; then
   for e in ${EXPS:-0 1 2 3}; do
     MSB200_LIB=$PWD/bench_micro/libmsb200_exp$e.so python bench.py --steps 5 --warmup 3 --no-cpu 2>/dev/null | python -c "
-import json,sys; d=json.loads(sys.stdin.read()); print('MSB_TC_EXP=$e', 'prefilter_ms', round(d['phase_ms']['prefilter'],3), 'step_ms', round(d['ms_per_step'],3))"
+import json,sys; d=json.loads(sys.stdin.read()); print('MSB_TC_EXP=$e', 'prefilter_ms', round(d['phase_ms']['prefilter'],3), 'step_ms', round(d['ms_per_step'],3), 'clocks', d['clocks'].get('sm_mhz'), d['clocks'].get('sm_min_mhz'), 'power_w_max', d['clocks'].get('power_w_max'), d['clocks'].get('reasons'))"
   done
 else
   for e in ${EXPS:-0 1 2 3}; do
